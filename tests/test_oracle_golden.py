@@ -1,0 +1,109 @@
+"""The oracle restatement vs fixtures produced by RUNNING THE REFERENCE (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import msunet_oracle as O
+
+CASES = {"t32_160": (O.T32, 160, 2), "t96_224": (O.T96, 224, 2)}
+
+
+def relmax(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_backward_matches_reference(name):
+    kw, img, batch = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = O.Cfg(img_size=img, **kw)
+    sd = O.make_weights(cfg)
+    assert list(sd.keys()) == list(g["sd_keys"])
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == list(g["sd_shapes"])
+    x, y = O.make_inputs(cfg, batch)
+    logits, loss, grads = O.train_step(sd, x, y, cfg)
+    assert relmax(logits.numpy(), g["logits"]) < 2e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * abs(float(g["loss"])) + 1e-7
+    assert abs(O.dynamic_loss(logits, y * 255, 0.2, 0.8, 0.45).item() - float(g["loss_255"])) < 1e-6
+    dead = set(g["dead"])
+    assert dead == {k for k in grads if k.startswith(O.DEAD_PREFIXES)}
+    for k in dead:
+        assert grads[k] is None
+    for k, n, s in zip(g["grad_names"], g["grad_norms"], g["grad_sums"]):
+        gn = grads[k].double().norm().item()
+        if "attn.qkv.bias" in k:  # K-third is mathematically zero: rounding noise
+            assert abs(gn - n) < 1e-4 * n + 1e-5, k
+        else:
+            assert abs(gn - n) < 2e-4 * n + 1e-7, (k, gn, n)
+    for key in g.files:
+        if key.startswith("grad::"):
+            k = key[6:]
+            tol = 5e-4 if "qkv.bias" not in k else 2e-3
+            assert relmax(grads[k].numpy(), g[key]) < tol, k
+
+
+def test_dead_branches_do_not_change_logits():
+    cfg = O.Cfg(img_size=96, **O.T32)
+    sd = O.make_weights(cfg)
+    x, _ = O.make_inputs(cfg, 1)
+    a = O.forward(sd, x, cfg, run_dead=False)
+    b = O.forward(sd, x, cfg, run_dead=True)
+    assert torch.equal(a, b)
+
+
+def test_window_attention_matches_torchvision():
+    from torchvision.models.swin_transformer import SwinTransformerBlock
+    for (H, W, shift, C, nH) in [(14, 14, 3, 32, 1), (16, 16, 3, 64, 2), (16, 16, 0, 64, 2),
+                                 (7, 7, 3, 32, 1), (10, 12, 3, 32, 1), (5, 5, 3, 64, 2)]:
+        torch.manual_seed(H * 100 + W + shift)
+        blk = SwinTransformerBlock(C, nH, [7, 7], [shift, shift]).eval()
+        with torch.no_grad():
+            for p in blk.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        sd = {"b." + k: v for k, v in blk.state_dict().items()}
+        x = torch.randn(2, H, W, C)
+        with torch.no_grad():
+            ref = blk(x)
+            got = O.swin_block(x, sd, "b", nH, shift)
+        assert relmax(got.numpy(), ref.numpy()) < 1e-5, (H, W, shift)
+
+
+def test_loss_known_answers():
+    g = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    for tag in ("a", "b"):
+        lg = torch.from_numpy(g[tag + "_logits"]).requires_grad_(True)
+        t = torch.from_numpy(g[tag + "_target"])
+        for (al, be, mx) in ((0.4, 0.6, 0.5), (0.2, 0.8, 0.45)):
+            lg.grad = None
+            l = O.dynamic_loss(lg, t, al, be, mx)
+            l.backward()
+            key = f"{tag}_{al}_{be}_{mx}"
+            assert abs(l.item() - float(g[key + "_loss"])) < 2e-7
+            assert relmax(lg.grad.numpy(), g[key + "_grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_metrics_match_reference(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    kw, img, batch = CASES[name]
+    cfg = O.Cfg(img_size=img, **kw)
+    _, y = O.make_inputs(cfg, batch)
+    for i in range(batch):
+        pred = torch.sigmoid(torch.from_numpy(g["logits"][i, 0])).numpy()
+        pb = pred > 0.5
+        gt = y[i].numpy() > 0
+        if gt.any():
+            r = O.metrics_fake(pb, pred, gt)
+            assert np.array_equal(np.array(r[6]), g[f"fake{i}_cm_bin"])  # bit-exact integers
+            np.testing.assert_allclose(list(r[:6]) + [r[8], r[9]], g[f"fake{i}_scalars"], rtol=2e-6)
+            np.testing.assert_allclose(np.array(r[7]), g[f"fake{i}_cm_soft"], rtol=2e-6)
+        else:
+            cb, cs, acc, fpr = O.metrics_real(pb, pred, gt)
+            assert np.array_equal(np.array(cb), g[f"real{i}_cm_bin"])
+            np.testing.assert_allclose(np.array(cs), g[f"real{i}_cm_soft"], rtol=2e-6)
+            np.testing.assert_allclose([acc, fpr], g[f"real{i}_scalars"], rtol=1e-12)
