@@ -1,0 +1,170 @@
+/*
+ * msunet_b200.h — C ABI of libmsunet_sm100.so: hand-written sm_100a kernels for the MS-UNet hot path
+ * (forward/backward of the Swin-UNet, DynamicLoss, Dice/IoU counting).
+ *
+ * The reference (Sara-H-dev/Semantic_Segmentation_Of_StyleGAN2_Artifacts) is pure Python/PyTorch and has
+ * no FFI layer; each entry below names the reference code whose arithmetic it replaces (paths relative to
+ * the reference root; "TV:" = torchvision 0.26 `torchvision/`).  The Python host in
+ * semantic_segmentation_of_stylegan2_artifacts_b200/ binds these through ctypes.
+ *
+ * Conventions
+ *   - every entry returns int: 0 ok, >0 a cudaError_t, <0 an argument/shape error; nothing throws or
+ *     aborts; msu_last_error_string() describes the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch); the library allocates nothing
+ *     persistent except cached TMA descriptors / function attributes, and keeps no pointer after return.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - activation dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (loss/metrics inputs only).
+ *   - activations are token-major, channels-last, contiguous: [rows, C].
+ */
+#ifndef MSUNET_B200_H
+#define MSUNET_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSU_F32 0
+#define MSU_BF16 1
+#define MSU_F16 2
+
+/* Row maps: how a logical (row, col) of a GEMM operand / output / LayerNorm row is found in memory. */
+#define MSU_MAP_NONE 0     /* memory row = row                                                             */
+#define MSU_MAP_WINDOW 1   /* row is a window-order index (b, window, i<49) of the padded+rolled map;       \
+                              memory row = source pixel, or absent (zero on load, skipped on store).       \
+                              geo = {H, W, Ph, Pw, shift_h, shift_w}. TV:models/swin_transformer.py:152-172,219-227 */
+#define MSU_MAP_SHUFFLE 2  /* depth-to-space: logical [token(b,h,w), (p1 p2 c)] <-> memory [(b,h*p+p1,w*p+p2), c]; \
+                              geo = {H, W, p, c}. network/model_parts.py:402, 463-464 (einops rearrange)   */
+#define MSU_MAP_CONV3 3    /* implicit 3x3 im2col: logical [pixel(b,y,x), (tap ci)] -> memory [(b,y+dy,x+dx), ci], \
+                              zero outside the image; geo = {H, W, C}. network/model_parts.py:468-471       */
+#define MSU_MAP_MERGE 4    /* 2x2 neighbourhood concat: logical [(b,h/2,w/2), (q c)] -> memory [(b,2h'+q%2,2w'+q/2), c]; \
+                              geo = {H, W, C}. network/model_parts.py:87-92                                  */
+
+typedef struct {
+    const void* ptr;        /* base pointer                                                              */
+    const void* ptr2;       /* second source for logical columns >= k_split (skip concat), or NULL       */
+    int64_t ld, ld2;        /* leading dimensions in elements                                            */
+    int32_t k_split;        /* network/model_parts.py:792,804,823 torch.cat([x, skip], -1) folded here    */
+    int32_t orient;         /* 0: memory is [i, k] (k contiguous); 1: memory is [k, i] (i contiguous)      */
+    int32_t map;            /* MSU_MAP_* applied to the memory row                                        */
+    int32_t dtype;          /* MSU_F32 / MSU_BF16                                                        */
+    int32_t geo[6];
+    const float* rowscale;  /* optional per-sample scale (stochastic depth) on memory rows, or NULL      */
+    int32_t rows_per_sample;
+    int32_t _pad;
+} MsuOperand;
+
+typedef struct {
+    void* C;                /* output [M(mapped), N(mapped)], dtype `dtype`                               */
+    void* Cpre;             /* optional pre-activation copy (same mapping), or NULL                       */
+    const float* bias;      /* [N] fp32 or NULL                                                           */
+    const void* R;          /* residual, indexed like C, or NULL                                          */
+    const void* H;          /* if set: multiply by gelu'(H[m,n]) (unmapped, ld = ldh) — MLP backward       */
+    int64_t ldc, ldr, ldh;
+    const float* rowscale;  /* per-sample scale of the branch before the residual add                     */
+    int32_t rows_per_sample;
+    int32_t act;            /* 0 none, 1 exact (erf) GELU                                                  */
+    int32_t map;            /* MSU_MAP_NONE / WINDOW / SHUFFLE on the output                              */
+    int32_t dtype;          /* dtype of C, Cpre, R, H                                                     */
+    int32_t geo[6];
+    int32_t out_f32;        /* 1: C is fp32 regardless of dtype (weight gradients)                        */
+    int32_t accumulate;     /* 1: C += result (shared weights / gradient accumulation)                    */
+} MsuEpilogue;
+
+/* C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ), fp32 accumulation.
+ * Replaces every nn.Linear / F.linear / Conv2d on MSUNetSys.forward and their autograd backward:
+ * TV:models/swin_transformer.py:179,215; TV:ops/misc.py:292-303; network/model_parts.py:95, 395, 459,
+ * 468-471, 793, 805, 824.  `splitk_ws` (fp32, >= splits*M*N, or NULL) enables deterministic split-K.
+ * `backend`: 0 auto (tcgen05 when the operand pattern is supported, else SIMT), 1 force SIMT fp32-accumulate. */
+int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
+             float* splitk_ws, int64_t splitk_ws_elems, int backend, void* stream);
+
+/* Column sums: out[n] (+)= sum_m X(m,n) — bias gradients. `ws` fp32 >= 256*N. */
+int msu_colsum(const MsuOperand* X, int64_t M, int64_t N, float* out, int accumulate, float* ws,
+               int64_t ws_elems, void* stream);
+
+/* LayerNorm forward over `rows` output rows of width C (eps 1e-5, fp32 statistics).
+ * in_map: NONE | MERGE (gathers 2x2 neighbours, C = 4*Cin);  out_map: NONE | WINDOW (rows are window-order
+ * indices; absent rows are written as zeros — the unmasked zero padding of TV:...:152-156).
+ * mean/rstd are indexed by LayerNorm row (source pixel for WINDOW).  If `dotw` != NULL the kernel writes
+ * logits[row] = dot(LN(x), dotw) instead of Y (head LN + 1x1 conv, network/model_parts.py:475, 846).
+ * Replaces nn.LayerNorm at TV:...:453-454, network/model_parts.py:94, 224, 404, 475, 813, 827. */
+int msu_ln_fwd(int dtype, const void* X, const float* gamma, const float* beta, void* Y, float* mean,
+               float* rstd, int64_t rows, int32_t C, int32_t in_map, int32_t out_map, const int32_t* geo,
+               const float* dotw, void* stream);
+
+/* LayerNorm backward.  dY is read through `dy_map` (NONE, or WINDOW: gradient rows live in window order),
+ * dX written through `dx_map` (NONE or MERGE scatter).  dX = LN'(dY) + dRes (dRes optional).
+ * partial: fp32 workspace [msu_ln_bwd_partial_rows(rows,C), 3, C] for deterministic dgamma/dbeta/(ddotw) reduction, finished by
+ * msu_ln_param_reduce.  If dotw != NULL, dY is a per-row scalar (d logits) times dotw. */
+int msu_ln_bwd_partial_rows(int64_t rows, int32_t C);
+int msu_ln_bwd(int dtype, const void* dY, const void* X, const float* gamma, const float* beta,
+               const float* mean, const float* rstd, const void* dRes, void* dX, int64_t rows, int32_t C,
+               int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,
+               void* stream);
+int msu_ln_param_reduce(const float* partial, int32_t partial_rows, int32_t C, float* dgamma, float* dbeta,
+                        float* ddotw, int accumulate, void* stream);
+
+/* Window attention core on window-ordered qkv [nWinTotal*49, 3C] -> O [nWinTotal*49, C]; head dim 32.
+ * S = (q*32^-1/2) k^T + bias[h] + mask, softmax fp32, O = P v.  `bias` is the expanded [nH,49,49] table.
+ * geo = {H, W, Ph, Pw, shift_h, shift_w}: the -100 shift mask is derived from the window index.
+ * Replaces TV:models/swin_transformer.py:181-214. */
+int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
+                    const int32_t* geo, void* stream);
+/* Backward (recomputes P from qkv; O is the forward output): dqkv [.,3C];
+ * dbias_partial fp32 [msu_winattn_bwd_grid(n_windows,nH), nH, 2401], reduced by msu_relbias_reduce. */
+int msu_winattn_bwd_grid(int64_t n_windows, int32_t nH);
+int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
+                    float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, void* stream);
+/* bias[h,i,j] = table[index(i,j), h]  (TV:...:49-56) and its deterministic transpose-reduction. */
+int msu_relbias_expand(const float* table, float* bias, int32_t nH, void* stream);
+int msu_relbias_reduce(const float* dbias_partial, int32_t grid, int32_t nH, float* dtable, int accumulate,
+                       void* stream);
+
+/* Weight / layout preparation (fp32 master -> compute dtype):
+ * mode 0: cast [R,C]; 1: transpose+cast -> [C,R]; 2: conv [co,ci,3,3] -> [co,(tap ci)];
+ * 3: conv -> flipped-transposed [ci,(tap' co)] for dgrad; 4: conv-grad [co,(tap ci)] fp32 -> [co,ci,3,3] fp32
+ * 5: patch-embed conv [E,3,4,4] -> [E, 64] zero-padded K (48 -> 64); 6: inverse of 5 for the gradient. */
+int msu_prep_weight(int mode, int dst_dtype, const float* src, void* dst, int64_t R, int64_t C, void* stream);
+
+/* im2col of non-overlapping 4x4 patches: image [B,3,S,S] fp32 NCHW -> [B*(S/4)^2, 64] (cols >=48 zero).
+ * network/model_parts.py:222 (Conv2d k=4 s=4 as a GEMM). */
+int msu_patchify4(int dst_dtype, const float* img, void* out, int32_t B, int32_t S, void* stream);
+
+/* Fused BCE-with-logits + Tversky loss (loss/DynamicLoss.py:82-111), no host sync.
+ * logits [B, N] (dtype f32/bf16/f16), target [B, N] fp32 ({0,1} or {0,255}: binarised at 127.5 when the
+ * global max exceeds 1).  stats fp32 [B, 8] (per-sample backward coefficients),
+ * flag int32[1] (global max>1), loss fp32[1].  msu_loss_bwd writes dlogits (same dtype) scaled by *gscale. */
+int msu_loss_fwd(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
+                 float beta, float mix, float* ws /* fp32 >= B*64*16 */, float* stats /* [B,8] */, int32_t* flag,
+                 float* loss, void* stream);
+int msu_loss_bwd(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
+                 float beta, float mix, const float* stats, const int32_t* flag, const float* gscale,
+                 void* dlogits, void* stream);
+
+/* Dice/IoU counting (scripts/validation_functions.py:106-108, 219-227, 267-292).
+ * from_logits=1: pred = sigmoid(logit) rounded to `dtype`, pred_bin = pred > thr, gt = label > 0.
+ * from_logits=0: `in` is pred (dtype), pred_bin uint8 given, gt uint8 given.
+ * counts int64 [B,4] = tp, fp, fn, tn (bit exact); soft fp64 [B,8] = TP, FP, FN, TN, sum p^2, sum g^2, sum p, sum g.
+ * pred_out (optional, dtype) receives the probabilities. */
+int msu_metrics(int dtype, int from_logits, const void* in, const void* label_or_gt, const uint8_t* pred_bin,
+                int32_t B, int64_t N, float thr, long long* ws_counts /* >= B*64*4 */, double* ws_soft /* >= B*64*8 */,
+                long long* counts, double* soft, void* pred_out, void* stream);
+
+/* Elementwise helpers used by the host (cast fp32 <-> compute dtype, y = a + b). */
+int msu_cast(int src_dtype, int dst_dtype, const void* src, void* dst, int64_t n, void* stream);
+int msu_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);
+
+int msu_version(void);
+/* sizeof(MsuOperand) (which=0) / sizeof(MsuEpilogue) (which=1): lets a binding verify its struct layout. */
+int msu_struct_size(int which);
+const char* msu_last_error_string(void);
+/* Number of kernels this library has launched on the calling process (bench.py "gpu_launches"). */
+long long msu_launch_count(void);
+/* 1 if the tcgen05 GEMM path was used by the last msu_gemm call on this thread, else 0. */
+int msu_last_gemm_backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

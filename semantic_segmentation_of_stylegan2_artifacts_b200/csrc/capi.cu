@@ -1,0 +1,59 @@
+// C-ABI glue: error state, launch counter, GEMM backend dispatch.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace msu {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static thread_local int g_last_backend = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
+              float* splitk_ws, int64_t splitk_ws_elems, cudaStream_t st);
+// returns 1 if the pattern is not supported by the tcgen05 path (caller falls back to SIMT), 0 ok, else error
+int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
+            float* splitk_ws, int64_t splitk_ws_elems, cudaStream_t st);
+
+}  // namespace msu
+
+using namespace msu;
+
+extern "C" int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
+                        float* splitk_ws, int64_t splitk_ws_elems, int backend, void* stream) {
+    MSU_REQUIRE(A && B && E && A->ptr && B->ptr && E->C, "msu_gemm: null pointer");
+    MSU_REQUIRE(M >= 0 && N > 0 && K > 0, "msu_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    g_last_backend = 0;
+    if (backend == 0) {
+        const int rc = gemm_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+        if (rc == 0) { g_last_backend = 1; return 0; }
+        if (rc != 1) return rc;
+    }
+    return gemm_simt(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+}
+
+extern "C" int msu_version(void) { return 100; }
+extern "C" int msu_struct_size(int which) { return which == 0 ? (int)sizeof(MsuOperand) : (int)sizeof(MsuEpilogue); }
+extern "C" const char* msu_last_error_string(void) { return g_err; }
+extern "C" long long msu_launch_count(void) { return g_launches.load(); }
+extern "C" int msu_last_gemm_backend(void) { return g_last_backend; }

@@ -1,0 +1,182 @@
+// Shared device/host helpers for libmsunet_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/msunet_b200.h"
+
+namespace msu {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> code, records message
+
+#define MSU_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            msu::set_error(__VA_ARGS__); \
+            return -1;                  \
+        }                               \
+    } while (0)
+
+__host__ __device__ inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+
+constexpr int WS = 7;
+constexpr int WT = 49;  // tokens per window
+constexpr int HD = 32;  // head dim (C / num_heads is 32 for every config of the reference)
+
+// ---- dtype helpers --------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ float ld_as_f(const void* p, int64_t idx, int dtype) {
+    return dtype == MSU_F32 ? reinterpret_cast<const float*>(p)[idx]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+}
+__device__ __forceinline__ void st_from_f(void* p, int64_t idx, int dtype, float v) {
+    if (dtype == MSU_F32) reinterpret_cast<float*>(p)[idx] = v;
+    else reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+}
+
+// 4-element vector load/store converting to/from fp32 (16 B for float, 8 B for bf16)
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+        uint2 r = *reinterpret_cast<const uint2*>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+        float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<uint32_t*>(&a);
+        r.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = r;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// exact (erf) GELU and its derivative — nn.GELU() default, TV:ops/misc.py:264-305
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ---- window geometry (index math that replaces pad/roll/partition/reverse/crop) -------------
+// TV:models/swin_transformer.py:152-172 (forward gather) and :219-227 (reverse scatter).
+struct WinGeo {
+    int H, W, Ph, Pw, sh, sw;
+    __host__ __device__ int nwx() const { return Pw / WS; }
+    __host__ __device__ int nwin() const { return (Ph / WS) * (Pw / WS); }
+};
+__host__ __device__ inline WinGeo make_wingeo(const int32_t* g) { return WinGeo{g[0], g[1], g[2], g[3], g[4], g[5]}; }
+
+// window-order row (b, w, i) -> source pixel row (b, y, x) or -1 for a padding token
+__device__ __forceinline__ int64_t win_to_pix(const WinGeo& g, int64_t wr) {
+    const int per_img = g.nwin() * WT;
+    const int64_t b = wr / per_img;
+    const int r = (int)(wr - b * per_img);
+    const int w = r / WT, i = r - w * WT;
+    const int ry = (w / g.nwx()) * WS + i / WS, rx = (w % g.nwx()) * WS + i % WS;
+    int py = ry + g.sh; if (py >= g.Ph) py -= g.Ph;
+    int px = rx + g.sw; if (px >= g.Pw) px -= g.Pw;
+    if (py >= g.H || px >= g.W) return -1;
+    return b * (int64_t)(g.H * g.W) + py * g.W + px;
+}
+// source pixel row -> window-order row (every real pixel appears exactly once)
+__device__ __forceinline__ int64_t pix_to_win(const WinGeo& g, int64_t pr) {
+    const int hw = g.H * g.W;
+    const int64_t b = pr / hw;
+    const int r = (int)(pr - b * hw);
+    const int y = r / g.W, x = r - y * g.W;
+    int ry = y - g.sh; if (ry < 0) ry += g.Ph;
+    int rx = x - g.sw; if (rx < 0) rx += g.Pw;
+    const int w = (ry / WS) * g.nwx() + rx / WS;
+    const int i = (ry % WS) * WS + rx % WS;
+    return b * (int64_t)(g.nwin() * WT) + w * WT + i;
+}
+
+// generic row/col mapping shared by GEMM operands and outputs.  Returns memory row (or -1) and col.
+struct RowCol { int64_t row; int col; };
+__device__ __forceinline__ RowCol map_rc(int map, const int32_t* geo, int64_t r, int c) {
+    switch (map) {
+        case MSU_MAP_WINDOW: {
+            WinGeo g = make_wingeo(geo);
+            return RowCol{win_to_pix(g, r), c};
+        }
+        case MSU_MAP_SHUFFLE: {  // geo = {H, W, p, cc}
+            const int H = geo[0], W = geo[1], p = geo[2], cc = geo[3];
+            const int q = c / cc, p1 = q / p, p2 = q - p1 * p;
+            const int hw = H * W;
+            const int64_t b = r / hw;
+            const int t = (int)(r - b * hw);
+            const int h = t / W, w = t - h * W;
+            return RowCol{(b * (H * p) + (h * p + p1)) * (int64_t)(W * p) + (w * p + p2), c - q * cc};
+        }
+        case MSU_MAP_CONV3: {  // geo = {H, W, C}
+            const int H = geo[0], W = geo[1], C = geo[2];
+            const int tap = c / C, ci = c - tap * C;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int hw = H * W;
+            const int64_t b = r / hw;
+            const int t = (int)(r - b * hw);
+            const int y = t / W + dy, x = t % W + dx;
+            if (y < 0 || y >= H || x < 0 || x >= W) return RowCol{-1, ci};
+            return RowCol{b * hw + y * W + x, ci};
+        }
+        case MSU_MAP_MERGE: {  // geo = {H, W, C}: r indexes (b, h/2, w/2)
+            const int H = geo[0], W = geo[1], C = geo[2];
+            const int q = c / C, ci = c - q * C;
+            const int h2w2 = (H / 2) * (W / 2);
+            const int64_t b = r / h2w2;
+            const int t = (int)(r - b * h2w2);
+            const int y = 2 * (t / (W / 2)) + (q & 1), x = 2 * (t % (W / 2)) + (q >> 1);
+            return RowCol{b * (int64_t)(H * W) + y * W + x, ci};
+        }
+        default:
+            return RowCol{r, c};
+    }
+}
+
+inline int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace msu

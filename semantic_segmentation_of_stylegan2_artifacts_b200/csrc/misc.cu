@@ -1,0 +1,157 @@
+// Layout / dtype preparation kernels: weight shadows (fp32 master -> compute dtype, rearranged for the
+// GEMM operand conventions), the 4x4 patch im2col of PatchEmbed, casts and adds.  All memory-bound.
+#include "common.cuh"
+
+namespace msu {
+
+template <typename T>
+__global__ void prep_weight_kernel(int mode, const float* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    switch (mode) {
+        case 0: {  // cast [R,C]
+            if (idx < R * C) dst[idx] = from_f<T>(src[idx]);
+            break;
+        }
+        case 1: {  // dst[C,R] = src[R,C]^T   (idx walks dst)
+            if (idx < R * C) {
+                const int64_t c = idx / R, r = idx % R;
+                dst[idx] = from_f<T>(src[r * C + c]);
+            }
+            break;
+        }
+        case 2: {  // conv [co=R, ci=C, 3,3] -> [co, (tap ci)]
+            if (idx < R * C * 9) {
+                const int64_t co = idx / (9 * C);
+                const int rem = (int)(idx % (9 * C)), tap = rem / (int)C, ci = rem % (int)C;
+                dst[idx] = from_f<T>(src[(co * C + ci) * 9 + tap]);
+            }
+            break;
+        }
+        case 3: {  // conv [co=R, ci=C, 3,3] -> [ci, (tap' co)], tap' = 8 - tap (dgrad = correlation with flipped kernel)
+            if (idx < R * C * 9) {
+                const int64_t ci = idx / (9 * R);
+                const int rem = (int)(idx % (9 * R)), tapf = rem / (int)R, co = rem % (int)R;
+                dst[idx] = from_f<T>(src[((int64_t)co * C + ci) * 9 + (8 - tapf)]);
+            }
+            break;
+        }
+        case 5: {  // patch-embed conv [E=R, 48] -> [E, 64], zero padded K
+            if (idx < R * 64) {
+                const int64_t e = idx / 64;
+                const int k = (int)(idx % 64);
+                dst[idx] = from_f<T>(k < 48 ? src[e * 48 + k] : 0.f);
+            }
+            break;
+        }
+    }
+}
+// fp32 -> fp32 gradient re-layouts
+__global__ void prep_grad_kernel(int mode, const float* __restrict__ src, float* __restrict__ dst, int64_t R, int64_t C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 4) {  // [co, (tap ci)] -> [co, ci, 3, 3]   (idx walks dst)
+        if (idx < R * C * 9) {
+            const int64_t co = idx / (9 * C);
+            const int rem = (int)(idx % (9 * C)), ci = rem / 9, tap = rem % 9;
+            dst[idx] = src[(co * 9 + tap) * C + ci];
+        }
+    } else if (mode == 6) {  // [E, 64] -> [E, 48]
+        if (idx < R * 48) dst[idx] = src[(idx / 48) * 64 + idx % 48];
+    }
+}
+
+// image [B,3,S,S] NCHW fp32 -> rows [(b, py, px), 64]; col = c*16 + ky*4 + kx (Conv2d weight order), cols 48..63 zero
+template <typename T>
+__global__ void patchify4_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int S) {
+    const int P = S / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (token, c, ky): 4 contiguous pixels
+    const int64_t total = (int64_t)B * P * P * 16;
+    if (idx >= total) return;
+    const int64_t tok = idx / 16;
+    const int sub = (int)(idx % 16);
+    T* o = out + tok * 64 + sub * 4;
+    if (sub >= 12) {
+        Vec4<T>::st(o, make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+    const int c = sub / 4, ky = sub % 4;
+    const int64_t b = tok / (P * P);
+    const int t = (int)(tok % (P * P)), py = t / P, px = t % P;
+    const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * S + (py * 4 + ky)) * (int64_t)S + px * 4);
+    Vec4<T>::st(o, v);
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = from_f<TD>(to_f<TS>(s[i]));
+}
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 x = Vec4<T>::ld(a + i * 4), z = Vec4<T>::ld(b + i * 4);
+        Vec4<T>::st(y + i * 4, make_float4(x.x + z.x, x.y + z.y, x.z + z.z, x.w + z.w));
+    }
+}
+
+}  // namespace msu
+
+using namespace msu;
+
+extern "C" int msu_prep_weight(int mode, int dst_dtype, const float* src, void* dst, int64_t R, int64_t C, void* stream) {
+    MSU_REQUIRE(src && dst && R > 0 && C > 0, "msu_prep_weight: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n;
+    if (mode == 0 || mode == 1) n = R * C;
+    else if (mode == 2 || mode == 3 || mode == 4) n = R * C * 9;
+    else if (mode == 5) n = R * 64;
+    else if (mode == 6) n = R * 48;
+    else MSU_REQUIRE(false, "msu_prep_weight: bad mode %d", mode);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (mode == 4 || mode == 6) prep_grad_kernel<<<grid, 256, 0, st>>>(mode, src, (float*)dst, R, C);
+    else if (dst_dtype == MSU_F32) prep_weight_kernel<float><<<grid, 256, 0, st>>>(mode, src, (float*)dst, R, C);
+    else if (dst_dtype == MSU_BF16) prep_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(mode, src, (__nv_bfloat16*)dst, R, C);
+    else MSU_REQUIRE(false, "msu_prep_weight: bad dtype %d", dst_dtype);
+    count_launch();
+    return check_launch("msu_prep_weight");
+}
+
+extern "C" int msu_patchify4(int dst_dtype, const float* img, void* out, int32_t B, int32_t S, void* stream) {
+    MSU_REQUIRE(img && out && B > 0 && S > 0 && S % 4 == 0, "msu_patchify4: bad arguments");
+    const int64_t total = (int64_t)B * (S / 4) * (S / 4) * 16;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == MSU_F32) patchify4_kernel<float><<<grid, 256, 0, st>>>(img, (float*)out, B, S);
+    else if (dst_dtype == MSU_BF16) patchify4_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (__nv_bfloat16*)out, B, S);
+    else MSU_REQUIRE(false, "msu_patchify4: bad dtype %d", dst_dtype);
+    count_launch();
+    return check_launch("msu_patchify4");
+}
+
+extern "C" int msu_cast(int sd, int dd, const void* src, void* dst, int64_t n, void* stream) {
+    MSU_REQUIRE(src && dst, "msu_cast: null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (sd == MSU_F32 && dd == MSU_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    else if (sd == MSU_BF16 && dd == MSU_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    else if (sd == MSU_F16 && dd == MSU_F32) cast_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)src, (float*)dst, n);
+    else if (sd == MSU_F32 && dd == MSU_F16) cast_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+    else if (sd == MSU_F32 && dd == MSU_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    else if (sd == MSU_BF16 && dd == MSU_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    else MSU_REQUIRE(false, "msu_cast: unsupported %d -> %d", sd, dd);
+    count_launch();
+    return check_launch("msu_cast");
+}
+
+extern "C" int msu_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream) {
+    MSU_REQUIRE(a && b && y && n % 4 == 0, "msu_add: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n / 4 + 255) / 256);
+    if (dtype == MSU_F32) add_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)y, n / 4);
+    else if (dtype == MSU_BF16) add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, n / 4);
+    else MSU_REQUIRE(false, "msu_add: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("msu_add");
+}

@@ -1,0 +1,388 @@
+"""autograd.Function layer: each Function is one fused module of the MS-UNet with a hand-written
+forward AND backward made only of C-ABI kernel launches (ops.py).  torch.autograd is used for graph
+bookkeeping (accumulating gradients of shared weights, skip connections) and nothing else.
+
+Activations are token-major `[rows, C]` tensors in the compute dtype (bf16 or fp32); parameters
+stay fp32 `nn.Parameter`s and gradients are returned in fp32.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .ops import MAP_CONV3, MAP_MERGE, MAP_SHUFFLE, MAP_WINDOW, epilogue, gemm, operand
+
+WS = 7
+
+
+def window_geo(H: int, W: int, shift: int):
+    """{H, W, Ph, Pw, sh, sw}; the shift is disabled when the padded map is one window
+    (TV:models/swin_transformer.py:158-163)."""
+    Ph = WS * ((H + WS - 1) // WS)
+    Pw = WS * ((W + WS - 1) // WS)
+    return [H, W, Ph, Pw, 0 if WS >= Ph else shift, 0 if WS >= Pw else shift]
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+class SwinBlockFn(Function):
+    """x + SD(attn(LN1 x)) then + SD(mlp(LN2 .)) — TV:models/swin_transformer.py:401-455."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkvw, qkvb, projw, projb, table, n2w, n2b, f1w, f1b, f2w, f2b, sd1, sd2,
+                B, H, W, nH, shift):
+        ops._need_cuda(x, "x")
+        x = _c(x)
+        dev = x.device
+        Cd = x.shape[-1]
+        T = B * H * W
+        geo = window_geo(H, W, shift)
+        nW = (geo[2] // WS) * (geo[3] // WS)
+        Tw = B * nW * 49
+        hid = f1w.shape[0]
+        HW = H * W
+        # LN1 + zero-pad + roll + window partition in one gather pass
+        xw, mean1, rstd1 = ops.ln_fwd(x, n1w, n1b, Tw, Cd, out_map=MAP_WINDOW, geo=geo, n_stat_rows=T)
+        qkv = torch.empty(Tw, 3 * Cd, dtype=x.dtype, device=dev)
+        gemm(operand(xw), operand(qkvw), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
+        bias = ops.relbias_expand(table, nH)
+        o = ops.winattn_fwd(qkv, bias, B * nW, nH, geo)
+        # proj + window reverse + un-roll + crop + stochastic depth + residual in the GEMM epilogue
+        x1 = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(o), operand(projw),
+             epilogue(x1, bias=projb, R=x, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), Tw, Cd, Cd, dev)
+        xn, mean2, rstd2 = ops.ln_fwd(x1, n2w, n2b, T, Cd)
+        h = torch.empty(T, hid, dtype=x.dtype, device=dev)
+        a = torch.empty(T, hid, dtype=x.dtype, device=dev)
+        gemm(operand(xn), operand(f1w), epilogue(a, Cpre=h, bias=f1b, act=1), T, hid, Cd, dev)
+        x2 = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(a), operand(f2w), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
+        ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
+                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a)
+        ctx.cfg = (B, H, W, nH, geo, nW)
+        return x2.view(B, H, W, Cd)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx2):
+        (x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
+         xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a) = ctx.saved_tensors
+        B, H, W, nH, geo, nW = ctx.cfg
+        dev = x.device
+        Cd = x.shape[-1]
+        T, HW, Tw, hid = B * H * W, H * W, B * nW * 49, f1w.shape[0]
+        dx2 = _c(dx2).view(T, Cd)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # ---- MLP half
+        db2 = ops.colsum(operand(dx2, rowscale=sd2, rps=HW), T, Cd, dev)
+        dW2 = torch.empty(Cd, hid, **f32)
+        gemm(operand(dx2, orient=1, rowscale=sd2, rps=HW), operand(a, orient=1), epilogue(dW2, out_f32=True),
+             Cd, hid, T, dev)
+        dh = torch.empty(T, hid, dtype=x.dtype, device=dev)
+        gemm(operand(dx2, rowscale=sd2, rps=HW), operand(f2w, orient=1), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
+        db1 = ops.colsum(operand(dh), T, hid, dev)
+        dW1 = torch.empty(hid, Cd, **f32)
+        gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True), hid, Cd, T, dev)
+        dxn = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(dh), operand(f1w, orient=1), epilogue(dxn), T, Cd, hid, dev)
+        dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
+        # ---- attention half (gradient rows gathered into window order by the operand map)
+        dbp = ops.colsum(operand(dx1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), Tw, Cd, dev)
+        dWp = torch.empty(Cd, Cd, **f32)
+        gemm(operand(dx1, orient=1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), operand(o, orient=1),
+             epilogue(dWp, out_f32=True), Cd, Cd, Tw, dev)
+        do = torch.empty(Tw, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(dx1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), operand(projw, orient=1), epilogue(do),
+             Tw, Cd, Cd, dev)
+        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo)
+        dbqkv = ops.colsum(operand(dqkv), Tw, 3 * Cd, dev)
+        dWqkv = torch.empty(3 * Cd, Cd, **f32)
+        gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True), 3 * Cd, Cd, Tw, dev)
+        dxw = torch.empty(Tw, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(dqkv), operand(qkvw, orient=1), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
+        dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
+        return (dx.view(B, H, W, Cd), dn1w, dn1b, dWqkv, dbqkv, dWp, dbp, dtable, dn2w, dn2b, dW1, db1, dW2, db2,
+                None, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+class PatchEmbedFn(Function):
+    """Conv2d(3,E,4,4)/4 as patchify + GEMM, then LayerNorm(E) — network/model_parts.py:211-224."""
+
+    @staticmethod
+    def forward(ctx, img, pw, pb, nw, nb, dtype):
+        ops._need_cuda(img, "image")
+        img = _c(img.float())
+        dev = img.device
+        B, _, S, _ = img.shape
+        E = pw.shape[0]
+        T = B * (S // 4) ** 2
+        patches = ops.patchify4(img, dtype)
+        w64 = ops.prep_weight(5, pw, E, 48, (E, 64), torch.float32)
+        y = torch.empty(T, E, dtype=dtype, device=dev)
+        gemm(operand(patches), operand(w64), epilogue(y, bias=pb), T, E, 64, dev)
+        out, mean, rstd = ops.ln_fwd(y, nw, nb, T, E)
+        ctx.save_for_backward(patches, y, nw, nb, mean, rstd)
+        ctx.E = E
+        return out.view(B, (S // 4) ** 2, E)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        patches, y, nw, nb, mean, rstd = ctx.saved_tensors
+        E = ctx.E
+        dev = y.device
+        T = y.shape[0]
+        dout = _c(dout).view(T, E)
+        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, T, E)
+        dpb = ops.colsum(operand(dy), T, E, dev)
+        dW64 = torch.empty(E, 64, dtype=torch.float32, device=dev)
+        gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True), E, 64, T, dev)
+        dpw = ops.prep_weight(6, dW64, E, 48, (E, 3, 4, 4), torch.float32)
+        return None, dpw, dpb, dnw, dnb, None
+
+
+class PatchMergeFn(Function):
+    """2x2 gather + LayerNorm(4C) + Linear(4C,2C,no bias) — network/model_parts.py:87-95."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, rw, B, H, W):
+        x = _c(x)
+        dev = x.device
+        Cd = x.shape[-1]
+        Tm = B * (H // 2) * (W // 2)
+        geo = [H, W, Cd]
+        xm, mean, rstd = ops.ln_fwd(x, nw, nb, Tm, 4 * Cd, in_map=MAP_MERGE, geo=geo)
+        y = torch.empty(Tm, 2 * Cd, dtype=x.dtype, device=dev)
+        gemm(operand(xm), operand(rw), epilogue(y), Tm, 2 * Cd, 4 * Cd, dev)
+        ctx.save_for_backward(x, nw, nb, rw, xm, mean, rstd)
+        ctx.cfg = (B, H, W)
+        return y.view(B, (H // 2) * (W // 2), 2 * Cd)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, nw, nb, rw, xm, mean, rstd = ctx.saved_tensors
+        B, H, W = ctx.cfg
+        dev = x.device
+        Cd = x.shape[-1]
+        Tm = B * (H // 2) * (W // 2)
+        dy = _c(dy).view(Tm, 2 * Cd)
+        drw = torch.empty(2 * Cd, 4 * Cd, dtype=torch.float32, device=dev)
+        gemm(operand(dy, orient=1), operand(xm, orient=1), epilogue(drw, out_f32=True), 2 * Cd, 4 * Cd, Tm, dev)
+        dxm = torch.empty(Tm, 4 * Cd, dtype=x.dtype, device=dev)
+        gemm(operand(dy), operand(rw, orient=1), epilogue(dxm), Tm, 4 * Cd, 2 * Cd, dev)
+        dx, dnw, dnb, _ = ops.ln_bwd(dxm, x, nw, nb, mean, rstd, Tm, 4 * Cd, dx_map=MAP_MERGE, geo=[H, W, Cd])
+        return dx, dnw, dnb, drw, None, None, None
+
+
+class PatchExpandFn(Function):
+    """Linear(C,2C,no bias) -> depth-to-space x2 (GEMM output map) -> LayerNorm(C/2) — model_parts.py:395-405."""
+
+    @staticmethod
+    def forward(ctx, x, ew, nw, nb, B, H, W):
+        x = _c(x)
+        dev = x.device
+        Cd = x.shape[-1]
+        T = B * H * W
+        x2d = x.view(T, Cd)
+        c2 = Cd // 2
+        geo = [H, W, 2, c2]
+        y = torch.empty(4 * T, c2, dtype=x.dtype, device=dev)
+        gemm(operand(x2d), operand(ew), epilogue(y, ldc=c2, map=MAP_SHUFFLE, geo=geo), T, 2 * Cd, Cd, dev)
+        out, mean, rstd = ops.ln_fwd(y, nw, nb, 4 * T, c2)
+        ctx.save_for_backward(x2d, ew, nw, nb, y, mean, rstd)
+        ctx.cfg = (B, H, W, geo, x.shape)
+        return out.view(B, 4 * H * W, c2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x2d, ew, nw, nb, y, mean, rstd = ctx.saved_tensors
+        B, H, W, geo, xshape = ctx.cfg
+        dev = y.device
+        T, Cd = x2d.shape
+        c2 = Cd // 2
+        dout = _c(dout).view(4 * T, c2)
+        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2)
+        dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
+        gemm(operand(dy, ld=c2, orient=1, map=MAP_SHUFFLE, geo=geo), operand(x2d, orient=1),
+             epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
+        dx = torch.empty(T, Cd, dtype=y.dtype, device=dev)
+        gemm(operand(dy, ld=c2, map=MAP_SHUFFLE, geo=geo), operand(ew, orient=1), epilogue(dx), T, Cd, 2 * Cd, dev)
+        return dx.view(xshape), dew, dnw, dnb, None, None, None
+
+
+class ConcatLinearFn(Function):
+    """Linear(2C,C)+bias on cat([x, skip], -1) without materialising the concat (dual-source K) —
+    network/model_parts.py:792-793, 804-805, 823-824."""
+
+    @staticmethod
+    def forward(ctx, x, skip, w, b):
+        x, skip = _c(x), _c(skip)
+        dev = x.device
+        Cd = x.shape[-1]
+        T = x.numel() // Cd
+        y = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(x.view(T, Cd), t2=skip.view(T, Cd), ld2=Cd, k_split=Cd), operand(w), epilogue(y, bias=b),
+             T, Cd, 2 * Cd, dev)
+        ctx.save_for_backward(x, skip, w)
+        return y.view(x.shape[0], -1, Cd)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, skip, w = ctx.saved_tensors
+        dev = x.device
+        Cd = x.shape[-1]
+        T = x.numel() // Cd
+        dy = _c(dy).view(T, Cd)
+        db = ops.colsum(operand(dy), T, Cd, dev)
+        dw = torch.empty(Cd, 2 * Cd, dtype=torch.float32, device=dev)
+        gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True),
+             Cd, Cd, T, dev)
+        gemm(operand(dy, orient=1), operand(skip.view(T, Cd), orient=1),
+             epilogue(dw, ldc=2 * Cd, out_f32=True, offset=Cd), Cd, Cd, T, dev)
+        dx = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        dskip = torch.empty(T, Cd, dtype=x.dtype, device=dev)
+        gemm(operand(dy), operand(w, ld=2 * Cd, orient=1), epilogue(dx), T, Cd, Cd, dev)
+        gemm(operand(dy), operand(w, ld=2 * Cd, orient=1, offset=Cd), epilogue(dskip), T, Cd, Cd, dev)
+        return dx.view(x.shape), dskip.view(skip.shape), dw, db
+
+
+class LayerNormFn(Function):
+    """Plain LayerNorm over the last dim (norm / norm_up, network/model_parts.py:813, 827)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _c(x)
+        Cd = x.shape[-1]
+        rows = x.numel() // Cd
+        y, mean, rstd = ops.ln_fwd(x, w, b, rows, Cd)
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, b, mean, rstd = ctx.saved_tensors
+        Cd = x.shape[-1]
+        rows = x.numel() // Cd
+        dx, dw, db, _ = ops.ln_bwd(_c(dy), x, w, b, mean, rstd, rows, Cd)
+        return dx, dw, db
+
+
+class HeadFn(Function):
+    """FinalPatchExpand_X4_V2 + 1x1 output conv (network/model_parts.py:451-476, 842-846), NHWC end to end:
+    Linear(E,16E)+GELU with the x4 depth-to-space as the GEMM output map, two implicit-GEMM 3x3 convs
+    (+bias, GELU after the first), LayerNorm(E) fused with the 1x1 conv (a per-pixel dot product)."""
+
+    @staticmethod
+    def forward(ctx, x, ew, c1w, c1b, c2w, c2b, nw, nb, ow, B, r):
+        x = _c(x)
+        dev = x.device
+        E = x.shape[-1]
+        T = B * r * r
+        S = 4 * r
+        Mp = B * S * S
+        x2d = x.view(T, E)
+        sgeo = [r, r, 4, E]
+        cgeo = [S, S, E]
+        h0 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        a0 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        gemm(operand(x2d), operand(ew), epilogue(a0, ldc=E, Cpre=h0, act=1, map=MAP_SHUFFLE, geo=sgeo), T, 16 * E, E, dev)
+        w1 = ops.prep_weight(2, c1w, E, E, (E, 9 * E), torch.float32)
+        w2 = ops.prep_weight(2, c2w, E, E, (E, 9 * E), torch.float32)
+        z1 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        a1 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        gemm(operand(a0, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1), epilogue(a1, Cpre=z1, bias=c1b, act=1),
+             Mp, E, 9 * E, dev)
+        z2 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
+        owv = _c(ow).view(E)
+        logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
+        ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd)
+        ctx.cfg = (B, r, x.shape, ow.shape)
+        return logits.view(B, 1, S, S)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits):
+        x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd = ctx.saved_tensors
+        B, r, xshape, owshape = ctx.cfg
+        dev = x2d.device
+        T, E = x2d.shape
+        S = 4 * r
+        Mp = B * S * S
+        sgeo = [r, r, 4, E]
+        cgeo = [S, S, E]
+        f32 = dict(dtype=torch.float32, device=dev)
+        dl = _c(dlogits).view(Mp)
+        dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
+        # conv2
+        dc2b = ops.colsum(operand(dz2), Mp, E, dev)
+        dw2r = torch.empty(E, 9 * E, **f32)
+        gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw2r, out_f32=True),
+             E, 9 * E, Mp, dev)
+        dc2w = ops.prep_weight(4, dw2r, E, E, (E, E, 3, 3), torch.float32)
+        w2f = ops.prep_weight(3, c2w, E, E, (E, 9 * E), torch.float32)
+        dz1 = torch.empty(Mp, E, dtype=x2d.dtype, device=dev)
+        gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
+        # conv1
+        dc1b = ops.colsum(operand(dz1), Mp, E, dev)
+        dw1r = torch.empty(E, 9 * E, **f32)
+        gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw1r, out_f32=True),
+             E, 9 * E, Mp, dev)
+        dc1w = ops.prep_weight(4, dw1r, E, E, (E, E, 3, 3), torch.float32)
+        w1f = ops.prep_weight(3, c1w, E, E, (E, 9 * E), torch.float32)
+        dh0 = torch.empty(Mp, E, dtype=x2d.dtype, device=dev)
+        gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f), epilogue(dh0, H=h0, ldh=E), Mp, E, 9 * E, dev)
+        # expand
+        dew = torch.empty(16 * E, E, **f32)
+        gemm(operand(dh0, ld=E, orient=1, map=MAP_SHUFFLE, geo=sgeo), operand(x2d, orient=1),
+             epilogue(dew, out_f32=True), 16 * E, E, T, dev)
+        dx = torch.empty(T, E, dtype=x2d.dtype, device=dev)
+        gemm(operand(dh0, ld=E, map=MAP_SHUFFLE, geo=sgeo), operand(ew, orient=1), epilogue(dx), T, E, 16 * E, dev)
+        return (dx.view(xshape), dew, dc1w, dc1b, dc2w, dc2b, dnw, dnb, dow.view(owshape), None, None)
+
+
+class DynamicLossFn(Function):
+    """Fused per-sample BCE-with-logits + Tversky mix, batch mean — loss/DynamicLoss.py:82-111."""
+
+    @staticmethod
+    def forward(ctx, logits, target, alpha, beta, mix):
+        ops._need_cuda(logits, "logits")
+        B = logits.shape[0]
+        lg = _c(logits).view(B, -1)
+        tg = _c(target.float()).view(B, -1)
+        loss, stats, flag = ops.loss_fwd(lg, tg, alpha, beta, mix)
+        ctx.save_for_backward(lg, tg, stats, flag)
+        ctx.cfg = (alpha, beta, mix, logits.shape)
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lg, tg, stats, flag = ctx.saved_tensors
+        alpha, beta, mix, shape = ctx.cfg
+        gs = _c(g.float()).view(1)
+        d = ops.loss_bwd(lg, tg, alpha, beta, mix, stats, flag, gs)
+        return d.view(shape), None, None, None, None
+
+
+def drop_path_noise(p: float, training: bool, B: int, device) -> Optional[torch.Tensor]:
+    """Row-mode stochastic depth noise Bernoulli(1-p)/(1-p) per sample (TV:ops/stochastic_depth.py:35-44)."""
+    if not training or p == 0.0:
+        return None
+    keep = 1.0 - p
+    n = torch.empty(B, dtype=torch.float32, device=device).bernoulli_(keep)
+    if keep > 0.0:
+        n.div_(keep)
+    return n

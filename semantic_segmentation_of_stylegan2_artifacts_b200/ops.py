@@ -1,0 +1,233 @@
+"""Thin, allocation-explicit wrappers over the C ABI (one Python function per kernel entry).
+
+Every function enqueues on torch's current CUDA stream and returns immediately.  Tensors are
+plain torch tensors used as device buffers; no torch math happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from ._lib import (BF16, F16, F32, MAP_CONV3, MAP_MERGE, MAP_NONE, MAP_SHUFFLE, MAP_WINDOW,  # noqa: F401
+                   MsuEpilogue, MsuOperand)
+
+_ws_cache: dict = {}
+GEMM_BACKEND = 0  # 0 auto (tcgen05 where supported), 1 force SIMT
+
+
+def _need_cuda(t: torch.Tensor, name: str = "tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: the MS-UNet hot path has no CPU fallback")
+
+
+def workspace(device: torch.device, elems: int = 16 << 20) -> torch.Tensor:
+    """Per-device fp32 scratch for deterministic split-K / column-sum partials."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < elems:
+        ws = torch.empty(elems, dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def operand(t: torch.Tensor, ld: Optional[int] = None, *, t2: Optional[torch.Tensor] = None, ld2: int = 0,
+            k_split: int = 0, orient: int = 0, map: int = MAP_NONE, geo: Optional[Sequence[int]] = None,
+            rowscale: Optional[torch.Tensor] = None, rps: int = 0, offset: int = 0) -> MsuOperand:
+    o = MsuOperand()
+    o.ptr = t.data_ptr() + offset * t.element_size()
+    o.ptr2 = L.ptr(t2)
+    o.ld = t.shape[-1] if ld is None else ld
+    o.ld2 = ld2
+    o.k_split = k_split
+    o.orient = orient
+    o.map = map
+    o.dtype = L.dt(t)
+    o.geo = L.geo6(geo)
+    o.rowscale = L.ptr(rowscale)
+    o.rows_per_sample = rps
+    o._keep = (t, t2, rowscale)
+    return o
+
+
+def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=None, R=None, ldr: Optional[int] = None,
+             H=None, ldh: int = 0, rowscale=None, rps: int = 0, act: int = 0, map: int = MAP_NONE, geo=None,
+             out_f32: bool = False, accumulate: bool = False, offset: int = 0) -> MsuEpilogue:
+    e = MsuEpilogue()
+    e.C = Cm.data_ptr() + offset * Cm.element_size()
+    e.Cpre = L.ptr(Cpre)
+    e.bias = L.ptr(bias)
+    e.R = L.ptr(R)
+    e.H = L.ptr(H)
+    e.ldc = Cm.shape[-1] if ldc is None else ldc
+    e.ldr = e.ldc if ldr is None else ldr
+    e.ldh = ldh
+    e.rowscale = L.ptr(rowscale)
+    e.rows_per_sample = rps
+    e.act = act
+    e.map = map
+    e.dtype = F32 if out_f32 else L.dt(Cm)
+    e.geo = L.geo6(geo)
+    e.out_f32 = 1 if out_f32 else 0
+    e.accumulate = 1 if accumulate else 0
+    if out_f32 and Cm.dtype != torch.float32:
+        raise TypeError("out_f32 needs an fp32 output tensor")
+    for t in (Cpre, R, H):
+        if t is not None and t.dtype != Cm.dtype:
+            raise TypeError("epilogue tensors must share the output dtype")
+    e._keep = (Cm, Cpre, bias, R, H, rowscale)
+    return e
+
+
+def gemm(A: MsuOperand, B: MsuOperand, E: MsuEpilogue, M: int, N: int, K: int, dev: torch.device) -> None:
+    ws = workspace(dev)
+    L.check(L.lib().msu_gemm(C.byref(A), C.byref(B), C.byref(E), M, N, K, ws.data_ptr(), ws.numel(), GEMM_BACKEND,
+                             L.stream_ptr()), "msu_gemm")
+
+
+def colsum(X: MsuOperand, M: int, N: int, dev: torch.device) -> torch.Tensor:
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    ws = workspace(dev)
+    L.check(L.lib().msu_colsum(C.byref(X), M, N, out.data_ptr(), 0, ws.data_ptr(), ws.numel(), L.stream_ptr()),
+            "msu_colsum")
+    return out
+
+
+def _geo_arr(geo):
+    return None if geo is None else L.geo6(geo)
+
+
+def ln_fwd(x: torch.Tensor, gamma, beta, rows: int, Cdim: int, *, in_map=MAP_NONE, out_map=MAP_NONE, geo=None,
+           n_stat_rows: Optional[int] = None, dotw: Optional[torch.Tensor] = None):
+    """Returns (y, mean, rstd).  y is [rows, C] (or [rows] logits when dotw is given)."""
+    _need_cuda(x, "x")
+    y = torch.empty((rows,) if dotw is not None else (rows, Cdim), dtype=x.dtype, device=x.device)
+    ns = rows if n_stat_rows is None else n_stat_rows
+    mean = torch.empty(ns, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(ns, dtype=torch.float32, device=x.device)
+    g = _geo_arr(geo)
+    L.check(L.lib().msu_ln_fwd(L.dt(x), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                               mean.data_ptr(), rstd.data_ptr(), rows, Cdim, in_map, out_map,
+                               None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), L.stream_ptr()), "msu_ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int, Cdim: int, *, dres=None,
+           dy_map=MAP_NONE, dx_map=MAP_NONE, geo=None, dotw=None, dx_shape=None):
+    """Returns (dx, dgamma, dbeta, ddotw|None); rows = number of LayerNorm rows."""
+    dev = x.device
+    dx = torch.empty(x.shape if dx_shape is None else dx_shape, dtype=x.dtype, device=dev)
+    P = L.lib().msu_ln_bwd_partial_rows(rows, Cdim)
+    part = torch.empty(P * 3 * Cdim, dtype=torch.float32, device=dev)
+    g = _geo_arr(geo)
+    L.check(L.lib().msu_ln_bwd(L.dt(x), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                               mean.data_ptr(), rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), rows, Cdim, dy_map,
+                               dx_map, None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), part.data_ptr(),
+                               L.stream_ptr()), "msu_ln_bwd")
+    dg = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    db = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    dw = torch.empty(Cdim, dtype=torch.float32, device=dev) if dotw is not None else None
+    L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), L.ptr(dw), 0,
+                                        L.stream_ptr()), "msu_ln_param_reduce")
+    return dx, dg, db, dw
+
+
+def relbias_expand(table: torch.Tensor, nH: int) -> torch.Tensor:
+    bias = torch.empty(nH, 49, 49, dtype=torch.float32, device=table.device)
+    L.check(L.lib().msu_relbias_expand(table.data_ptr(), bias.data_ptr(), nH, L.stream_ptr()), "msu_relbias_expand")
+    return bias
+
+
+def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, geo) -> torch.Tensor:
+    o = torch.empty(n_windows * 49, nH * 32, dtype=qkv.dtype, device=qkv.device)
+    g = L.geo6(geo)
+    L.check(L.lib().msu_winattn_fwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), n_windows, nH,
+                                    C.cast(g, C.c_void_p), L.stream_ptr()), "msu_winattn_fwd")
+    return o
+
+
+def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
+    """Returns (dqkv, dtable[169, nH])."""
+    dev = qkv.device
+    dqkv = torch.empty_like(qkv)
+    gx = L.lib().msu_winattn_bwd_grid(n_windows, nH)
+    part = torch.empty(gx * nH * 2401, dtype=torch.float32, device=dev)
+    g = L.geo6(geo)
+    L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
+                                    dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p),
+                                    L.stream_ptr()), "msu_winattn_bwd")
+    dtable = torch.empty(169, nH, dtype=torch.float32, device=dev)
+    L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
+            "msu_relbias_reduce")
+    return dqkv, dtable
+
+
+def prep_weight(mode: int, src: torch.Tensor, R: int, Cc: int, out_shape, dtype: torch.dtype) -> torch.Tensor:
+    out = torch.empty(out_shape, dtype=dtype, device=src.device)
+    L.check(L.lib().msu_prep_weight(mode, L.dt(out), src.data_ptr(), out.data_ptr(), R, Cc, L.stream_ptr()),
+            "msu_prep_weight")
+    return out
+
+
+def patchify4(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    B, _, S, _ = img.shape
+    out = torch.empty(B * (S // 4) ** 2, 64, dtype=dtype, device=img.device)
+    L.check(L.lib().msu_patchify4(L.dt(out), img.data_ptr(), out.data_ptr(), B, S, L.stream_ptr()), "msu_patchify4")
+    return out
+
+
+def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if src.dtype == dtype:
+        return src
+    src = src.contiguous()
+    out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    L.check(L.lib().msu_cast(L.dt(src), L.dt(out), src.data_ptr(), out.data_ptr(), src.numel(), L.stream_ptr()),
+            "msu_cast")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(a)
+    L.check(L.lib().msu_add(L.dt(a), a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), L.stream_ptr()), "msu_add")
+    return y
+
+
+def loss_fwd(logits: torch.Tensor, target: torch.Tensor, alpha: float, beta: float, mix: float):
+    """logits [B, N] (any of f32/bf16/f16), target [B, N] fp32 -> (loss[1], stats[B,8], flag[1])."""
+    B, N = logits.shape
+    dev = logits.device
+    ws = torch.empty(B * 64 * 16, dtype=torch.float32, device=dev)
+    stats = torch.empty(B, 8, dtype=torch.float32, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    L.check(L.lib().msu_loss_fwd(L.dt(logits), logits.data_ptr(), target.data_ptr(), B, N, alpha, beta, mix,
+                                 ws.data_ptr(), stats.data_ptr(), flag.data_ptr(), loss.data_ptr(), L.stream_ptr()),
+            "msu_loss_fwd")
+    return loss, stats, flag
+
+
+def loss_bwd(logits, target, alpha, beta, mix, stats, flag, gscale: torch.Tensor) -> torch.Tensor:
+    B, N = logits.shape
+    d = torch.empty_like(logits)
+    L.check(L.lib().msu_loss_bwd(L.dt(logits), logits.data_ptr(), target.data_ptr(), B, N, alpha, beta, mix,
+                                 stats.data_ptr(), flag.data_ptr(), gscale.data_ptr(), d.data_ptr(), L.stream_ptr()),
+            "msu_loss_bwd")
+    return d
+
+
+def metrics(inp: torch.Tensor, label_or_gt: torch.Tensor, pred_bin: Optional[torch.Tensor], from_logits: bool,
+            thr: float, want_pred: bool = False):
+    """inp [B, N]; returns (counts int64 [B,4] = tp,fp,fn,tn, soft float64 [B,8], pred|None)."""
+    B, N = inp.shape
+    dev = inp.device
+    wc = torch.empty(B * 64 * 4, dtype=torch.int64, device=dev)
+    wsf = torch.empty(B * 64 * 8, dtype=torch.float64, device=dev)
+    counts = torch.empty(B, 4, dtype=torch.int64, device=dev)
+    soft = torch.empty(B, 8, dtype=torch.float64, device=dev)
+    pred = torch.empty_like(inp) if (want_pred and from_logits) else None
+    L.check(L.lib().msu_metrics(L.dt(inp), 1 if from_logits else 0, inp.data_ptr(), label_or_gt.data_ptr(),
+                                L.ptr(pred_bin), B, N, thr, wc.data_ptr(), wsf.data_ptr(), counts.data_ptr(),
+                                soft.data_ptr(), L.ptr(pred), L.stream_ptr()), "msu_metrics")
+    return counts, soft, pred

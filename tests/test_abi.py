@@ -1,0 +1,111 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, and the host modules keep the reference's names / signatures / state_dict keys."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+PKG = "semantic_segmentation_of_stylegan2_artifacts_b200"
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, PKG, "libmsunet_sm100.so")):
+        g.build()
+    import importlib
+    return importlib.import_module(PKG)
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "msunet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(msu_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(built.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert built.lib().msu_version() >= 100
+
+
+def test_struct_layout_matches_header(built):
+    from semantic_segmentation_of_stylegan2_artifacts_b200._lib import MsuEpilogue, MsuOperand
+    assert ctypes.sizeof(MsuOperand) == built.lib().msu_struct_size(0) == 88
+    assert ctypes.sizeof(MsuEpilogue) == built.lib().msu_struct_size(1) == 120
+
+
+@pytest.mark.parametrize("name,kw,img", [("t32_160", dict(embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8]), 160),
+                                         ("t96_224", dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24]), 224)])
+def test_state_dict_contract(built, name, kw, img):
+    """Keys, order and shapes equal the reference's MSUNetSys.state_dict() (golden from the reference)."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m = MSUNetSys(img_size=img, drop_path_rate=0.0, **kw)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["sd_keys"])
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == list(g["sd_shapes"])
+    idx = sd["layers.0.blocks.0.attn.relative_position_index"]
+    from oracle import msunet_oracle as O
+    assert idx.dtype == torch.int64 and torch.equal(idx, O.relative_position_index())
+
+
+def test_signatures_match_reference(built):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.MSUNet import MSUNet
+    from semantic_segmentation_of_stylegan2_artifacts_b200.scripts import validation_functions as VF
+    assert list(inspect.signature(MSUNet.__init__).parameters) == ["self", "config", "img_size", "num_classes", "zero_head", "vis"]
+    p = inspect.signature(DynamicLoss.__init__).parameters
+    assert [(k, v.default) for k, v in p.items()][1:] == [("roi_thresh", 0.04), ("alpha", 0.4), ("beta", 0.6), ("tversky_bce_mix", 0.5)]
+    assert list(inspect.signature(VF.calculate_metrics).parameters) == [
+        "model", "logging", "testloader", "dynamic_loss", "csv_all_epoch", "csv_fake_epoch", "csv_real_epoch",
+        "csv_batch_real", "csv_batch_fake", "mean_train_loss", "epoch", "device", "split", "img_size", "sig_threshold",
+        "output_num"]
+    assert list(inspect.signature(VF.validation_loss).parameters) == ["model", "device", "val_loader", "dynamic_loss", "bool_break", "n_batches"]
+    for fn in ("calculate_metrics_real", "calculate_metrics_fake"):
+        assert list(inspect.signature(getattr(VF, fn)).parameters) == ["pred_bin", "pred", "ground_truth"]
+    assert list(inspect.signature(VF.atrifact_prediction).parameters) == ["model", "testloader", "device", "img_size"]
+
+
+def test_errors_and_no_cpu_fallback(built):
+    from types import SimpleNamespace as NS
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.MSUNet import MSUNet
+    cfg = NS(MODEL=NS(SWIN=NS(PATCH_SIZE=4, IN_CHANS=3, EMBED_DIM=32, DEPTHS=[2, 2, 2, 2], NUM_HEADS=[1, 2, 4, 8],
+                              WINDOW_SIZE=7, MLP_RATIO=4.0, QKV_BIAS=True, APE=False, PATCH_NORM=True),
+                      DROP_RATE=0.0, DROP_PATH_RATE=0.1, ATTN_DROP_RATE=0.0),
+             TRAIN=NS(USE_CHECKPOINT=False))
+    m = MSUNet(cfg, img_size=64, num_classes=1)
+    assert next(iter(m.state_dict())).startswith("ms_unet.patch_embed.")
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, 64, 64))                      # channel check, network/MSUNet.py:48-51
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))                      # CPU tensors: loud failure, never a fallback
+    with pytest.raises(ValueError):
+        DynamicLoss()(torch.zeros(2, 1, 8, 8), torch.zeros(3, 8, 8))   # loss/DynamicLoss.py:93-94
+    with pytest.raises(RuntimeError):
+        DynamicLoss()(torch.zeros(2, 1, 8, 8), torch.zeros(2, 8, 8))
+    m.freeze_encoder(True)
+    assert not any(p.requires_grad for p in m.ms_unet.layers.parameters())
+    m.unfreeze_encoder(0)
+    assert all(p.requires_grad for p in m.ms_unet.patch_embed.parameters())
+    with pytest.raises(ValueError):
+        m.unfreeze_encoder(7)
+
+
+def test_encoder_key_remap():
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.MSUNet import _remap
+    assert _remap("backbone.0.0.0.weight", "backbone.0.") == "patch_embed.proj.weight"
+    assert _remap("backbone.0.0.2.bias", "backbone.0.") == "patch_embed.norm.bias"
+    assert _remap("backbone.0.1.1.attn.qkv.weight", "backbone.0.") == "layers.0.blocks.1.attn.qkv.weight"
+    assert _remap("backbone.0.5.17.mlp.3.bias", "backbone.0.") == "layers.2.blocks.17.mlp.3.bias"
+    assert _remap("features.6.reduction.weight", "features.") == "layers.2.downsample.reduction.weight"
+    assert _remap("features.7.0.norm1.weight", "features.") == "layers.3.blocks.0.norm1.weight"
+    assert _remap("features.9.x", "features.") is None

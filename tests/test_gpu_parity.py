@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference-generated
+golden fixtures.  Tolerances (stated per BASELINE.json north_star):
+  fp32 mode : max|a-b| / max|b| <= 1e-3 on logits and every gradient tensor; loss rel <= 1e-4
+  bf16 mode : logits <= 3e-2 (max-rel) / 2e-2 (rel-L2); gradients rel-L2 <= 4e-2
+  counts    : bit exact
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import msunet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def relmax(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rell2(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import semantic_segmentation_of_stylegan2_artifacts_b200 as p
+    p.lib()
+    return p
+
+
+def build_model(cfg, prec, sd=None):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    m = MSUNetSys(img_size=cfg.img_size, embed_dim=cfg.embed_dim, depths=list(cfg.depths),
+                  num_heads=list(cfg.num_heads), drop_path_rate=0.0)
+    m.load_state_dict(sd if sd is not None else O.make_weights(cfg), strict=True)
+    return m.set_precision(prec).to(DEV).train()
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel-level
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [16, 48, 96, 384, 1536])
+def test_layernorm_plain(pkg, dtype, C):
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import functional as Fn
+    torch.manual_seed(C)
+    rows = 333
+    x = torch.randn(rows, C) * 2 + 0.5
+    w, b = torch.randn(C) * 0.2 + 1, torch.randn(C) * 0.1
+    dy = torch.randn(rows, C)
+    xr = x.to(dtype).float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    yr.backward(dy.to(dtype).float())
+    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    wg, bg = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    y = Fn.LayerNormFn.apply(xg, wg, bg)
+    y.backward(dy.to(dtype).to(DEV))
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+    assert relmax(y.float(), yr) < tol
+    assert relmax(xg.grad.float(), xr.grad) < tol
+    assert relmax(wg.grad, wr.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert relmax(bg.grad, br.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+def _gemm_case(pkg, dtype, M, N, K):
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K) * 0.5).to(dtype)
+    w = torch.randn(N, K) * 0.1
+    bias = torch.randn(N) * 0.1
+    res = (torch.randn(M, N)).to(dtype)
+    ref = torch.nn.functional.gelu(a.float() @ w.t() + bias) + res.float()
+    ag, wg, bg, rg = a.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV)
+    y = torch.empty(M, N, dtype=dtype, device=DEV)
+    pre = torch.empty(M, N, dtype=dtype, device=DEV)
+    ops.gemm(ops.operand(ag), ops.operand(wg), ops.epilogue(y, Cpre=pre, bias=bg, act=1, R=rg), M, N, K, ag.device)
+    return y, pre, ref, a.float() @ w.t() + bias
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(300, 96, 96), (1000, 288, 96), (257, 64, 384), (128, 1536, 96), (77, 40, 24)])
+def test_gemm_epilogue(pkg, dtype, shape):
+    y, pre, ref, refpre = _gemm_case(pkg, dtype, *shape)
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    assert relmax(y.float(), ref) < tol
+    assert relmax(pre.float(), refpre) < tol
+
+
+def test_gemm_wgrad_splitk_deterministic(pkg):
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops
+    torch.manual_seed(3)
+    T, N, K = 20000, 96, 64
+    dy, x = torch.randn(T, N), torch.randn(T, K)
+    ref = dy.t().double() @ x.double()
+    dyg, xg = dy.to(DEV), x.to(DEV)
+    outs = []
+    for _ in range(2):
+        dw = torch.empty(N, K, device=DEV)
+        ops.gemm(ops.operand(dyg, orient=1), ops.operand(xg, orient=1), ops.epilogue(dw, out_f32=True), N, K, T, dyg.device)
+        outs.append(dw.cpu())
+    assert torch.equal(outs[0], outs[1])           # deterministic reduction order
+    assert relmax(outs[0], ref) < 1e-5
+    cs = ops.colsum(ops.operand(dyg), T, N, dyg.device)
+    assert relmax(cs, dy.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(14, 14, 3, 32, 1), (16, 16, 3, 64, 2), (16, 16, 0, 64, 2), (7, 7, 3, 32, 1),
+                                  (10, 12, 3, 96, 3), (5, 5, 3, 64, 2), (7, 14, 3, 32, 1)])
+def test_swin_block_vs_oracle(pkg, dtype, geom):
+    """Forward + every gradient of one Swin block, incl. padded (unmasked zero tokens), shifted and
+    shift-disabled geometries (TV:models/swin_transformer.py:152-163)."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import SwinTransformerBlock
+    H, W, shift, C, nH = geom
+    torch.manual_seed(H * 31 + W + shift)
+    blk = SwinTransformerBlock(C, nH, [7, 7], [shift, shift])
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn_like(p) * (0.3 if p.dim() == 2 and p.shape[0] == 169 else 0.08))
+            if p.dim() == 1 and "norm" in str(p.shape):
+                pass
+        blk.norm1.weight.add_(1.0)
+        blk.norm2.weight.add_(1.0)
+    sd = {"b." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, H, W, C)
+    dy = torch.randn(2, H, W, C)
+    xr = x.to(dtype).float().requires_grad_(True)
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    yr = O.swin_block(xr, leaves, "b", nH, shift)
+    yr.backward(dy.to(dtype).float())
+    blk = blk.to(DEV)
+    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    y = blk(xg)
+    y.backward(dy.to(dtype).to(DEV))
+    f32 = dtype == torch.float32
+    assert relmax(y.float(), yr) < (2e-5 if f32 else 2e-2)
+    assert (relmax if f32 else rell2)(xg.grad.float(), xr.grad) < (1e-4 if f32 else 3e-2)
+    for k, p in blk.named_parameters():
+        r = leaves["b." + k].grad
+        if k == "attn.qkv.bias":  # K-third is mathematically zero (softmax shift invariance): absolute check
+            assert float((p.grad.cpu() - r).abs().max()) < (1e-4 if f32 else 3e-2) * float(r.abs().max()), k
+        else:
+            assert (relmax if f32 else rell2)(p.grad, r) < (2e-4 if f32 else 4e-2), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_loss_known_answers(pkg, dtype):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    g = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    for tag in ("a", "b"):
+        t = torch.from_numpy(g[tag + "_target"]).to(DEV)
+        for (al, be, mx) in ((0.4, 0.6, 0.5), (0.2, 0.8, 0.45)):
+            key = f"{tag}_{al}_{be}_{mx}"
+            lg = torch.from_numpy(g[tag + "_logits"]).to(DEV).to(dtype).requires_grad_(True)
+            crit = DynamicLoss(alpha=al, beta=be, tversky_bce_mix=mx)
+            l = crit(lg, t)
+            (l * 8.0).backward()  # upstream scale (GradScaler-style) must flow through
+            if dtype == torch.float32:
+                assert abs(l.item() - float(g[key + "_loss"])) < 1e-5 * abs(float(g[key + "_loss"]))
+                assert relmax(lg.grad / 8.0, torch.from_numpy(g[key + "_grad"])) < 1e-4
+                l255 = crit(lg.detach(), t * 255)  # {0,255} labels, loss/DynamicLoss.py:87-88
+                assert abs(l255.item() - l.item()) < 1e-6
+            else:
+                ref = O.dynamic_loss(lg.detach().float().cpu(), t.cpu(), al, be, mx)
+                assert abs(l.item() - ref.item()) < 1e-5 * abs(ref.item())
+                assert relmax(lg.grad.float() / 8.0, torch.from_numpy(g[key + "_grad"])) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_metric_counts_bit_exact(pkg, dtype):
+    """TP/FP/FN/TN must equal the reference formulas applied to the same logits, bit for bit
+    (sigmoid rounded to the logits dtype THEN thresholded: SURVEY.md App. H)."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.scripts import validation_functions as VF
+    torch.manual_seed(11)
+    B, S = 3, 97
+    lg = (torch.randn(B, 1, S, S) * 0.02)      # many logits close to the threshold
+    lg[0, 0, :8, :8] = torch.tensor([0.0, 1e-7, 2e-7, 0.0078125, 0.0079, 0.00098, 0.000977, -1e-7]).repeat(8, 1)
+    label = (torch.rand(B, S, S) > 0.7).float()
+    label[2] = 0
+    lgd = lg.to(DEV).to(dtype)
+    counts, soft, pred = VF.image_counts_from_logits(lgd, label.to(DEV), 0.5)
+    ref_pred = torch.sigmoid(lgd).squeeze(1)          # the reference's own expression on the same device/dtype
+    assert torch.equal(pred, ref_pred)
+    pb, gt = (ref_pred > 0.5), (label.to(DEV) > 0)
+    for i in range(B):
+        tp, fp, fn, tn = O.confusion_counts(pb[i].cpu().numpy(), gt[i].cpu().numpy())
+        assert counts[i].tolist() == [tp, fp, fn, tn]
+        s = O.soft_sums(ref_pred[i].float().cpu().numpy(), gt[i].cpu().numpy())
+        np.testing.assert_allclose(soft[i].cpu().numpy(), np.array(s), rtol=1e-6)
+        if gt[i].any():
+            got = VF.calculate_metrics_fake(pb[i], ref_pred[i], gt[i])
+            want = O.metrics_fake(pb[i].cpu().numpy(), ref_pred[i].float().cpu().numpy(), gt[i].cpu().numpy())
+            assert got[6] == want[6]
+            np.testing.assert_allclose(list(got[:6]) + [got[8], got[9]], list(want[:6]) + [want[8], want[9]], rtol=1e-6)
+        else:
+            got = VF.calculate_metrics_real(pb[i], ref_pred[i], gt[i])
+            want = O.metrics_real(pb[i].cpu().numpy(), ref_pred[i].float().cpu().numpy(), gt[i].cpu().numpy())
+            assert got[0] == want[0] and got[2] == want[2] and got[3] == want[3]
+
+
+# ------------------------------------------------------------------------------------------------
+# whole model vs golden fixtures generated by running the reference
+# ------------------------------------------------------------------------------------------------
+CASES = {"t32_160": (O.T32, 160, 2), "t96_224": (O.T96, 224, 2)}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_model_vs_reference_golden(pkg, name, prec):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    kw, img, batch = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = O.Cfg(img_size=img, **kw)
+    m = build_model(cfg, prec)
+    x, y = O.make_inputs(cfg, batch)
+    logits = m(x.to(DEV))
+    assert logits.shape == (batch, 1, img, img)
+    loss = DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)(logits, y.to(DEV))
+    loss.backward()
+    ref_logits = torch.from_numpy(g["logits"])
+    f32 = prec == "fp32"
+    assert relmax(logits.float(), ref_logits) < (1e-3 if f32 else 3e-2)
+    assert rell2(logits.float(), ref_logits) < (1e-4 if f32 else 2e-2)
+    assert abs(loss.item() - float(g["loss"])) < (1e-4 if f32 else 2e-3) * float(g["loss"])
+    dead = set(g["dead"])
+    params = dict(m.named_parameters())
+    for k in dead:
+        assert params[k].grad is None, k
+    worst = 0.0
+    for k, n in zip(g["grad_names"], g["grad_norms"]):
+        gn = params[k].grad.double().norm().item()
+        tol = (1e-3 if f32 else 5e-2)
+        if "attn.qkv.bias" in k:
+            tol *= 3
+        worst = max(worst, abs(gn - n) / n)
+        assert abs(gn - n) < tol * n + 1e-7, (k, gn, n)
+    for key in g.files:
+        if key.startswith("grad::"):
+            k = key[6:]
+            r = torch.from_numpy(g[key])
+            if "qkv.bias" in k:
+                assert float((params[k].grad.cpu() - r).abs().max()) < (1e-3 if f32 else 5e-2) * float(r.abs().max())
+            elif f32:
+                assert relmax(params[k].grad, r) < 1e-3, k
+            else:
+                assert rell2(params[k].grad, r) < 5e-2, k
+    print(f"{name}[{prec}] logits relmax {relmax(logits.float(), ref_logits):.2e} loss {loss.item():.6f} "
+          f"worst grad-norm rel {worst:.2e}")
+
+
+def test_drop_path_and_dead_branches_and_eval(pkg):
+    cfg = O.Cfg(img_size=96, **O.T32)
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    sd = O.make_weights(cfg)
+    x, _ = O.make_inputs(cfg, 2)
+    m = MSUNetSys(img_size=96, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], drop_path_rate=0.5)
+    m.load_state_dict(sd)
+    m.set_precision("fp32").to(DEV)
+    m.eval()
+    with torch.no_grad():
+        a = m(x.to(DEV))
+        m.run_dead_branches = True
+        b = m(x.to(DEV))
+    assert torch.equal(a, b)                                      # dead stacks do not change the logits
+    ref = O.forward(sd, x, cfg)
+    assert relmax(a, ref) < 1e-4                                   # eval: stochastic depth is the identity
+    m.train()
+    torch.manual_seed(0)
+    c = m(x.to(DEV))
+    assert relmax(c, ref) > 1e-3                                   # train: rows are dropped / rescaled
+    c.float().sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
