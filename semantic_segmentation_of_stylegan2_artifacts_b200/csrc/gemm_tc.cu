@@ -1,8 +1,465 @@
-// tcgen05 GEMM path (placeholder until the TMA/TMEM kernel lands): reports "pattern unsupported".
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C[m,n] = epilogue(sum_k A(m,k) B(n,k)), bf16 operands, fp32 accumulate.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer (+TMEM
+// alloc), warps 2..9 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).  Operands are staged
+// in 128B-swizzled shared memory by cp.async.bulk.tensor; accumulators live in TMEM (2 x 256 columns so
+// the epilogue of tile i overlaps the MMAs of tile i+1).  UMMA shape M=128, N=BN (16..256), K=16.
+//
+// A-operand modes (all K-major, i.e. contraction index contiguous in memory):
+//   plain   : [M, K] rows                              (2-D tensor map)
+//   dual    : cat([X1, X2], -1) without the concat      (two 2-D maps; network/model_parts.py:792,804,823)
+//   conv3x3 : implicit im2col of an NHWC image          (4-D map, zero fill outside the image does the
+//             padding; network/model_parts.py:468-471)
+// B is always a K-major [N, K] bf16 weight shadow.  K tails are zero-filled by TMA (out-of-bounds).
+// Every output map / fused epilogue of MsuEpilogue is honoured (each epilogue thread owns one output row).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace msu {
-int gemm_tc(const MsuOperand*, const MsuOperand*, const MsuEpilogue*, int64_t, int64_t, int64_t, float*, int64_t,
-            cudaStream_t) {
-    return 1;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor: rows at 128 B pitch, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+    int64_t M;
+    int N, BN, num_m_tiles, num_n_tiles;
+    int mode;                 // 0 plain, 1 dual, 2 conv3x3
+    int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
+    int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
+    int stages;
+    MsuEpilogue E;
+};
+
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int B_BYTES = p.BN * TC_BK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)p.stages * TC_A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;   // [2]
+    uint64_t* tempty = tfull + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int KB = p.kb1 + p.kb2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+                int cb = 0, cy = 0, cx = 0;
+                if (p.mode == 2) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    cb = mt / per_img;
+                    const int r = mt % per_img;
+                    cy = (r / p.tiles_x) * p.bmh;
+                    cx = (r % p.tiles_x) * p.bmw;
+                }
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], TC_A_BYTES + B_BYTES);
+                    void* a_dst = sA + (size_t)stage * TC_A_BYTES;
+                    void* b_dst = sB + (size_t)stage * B_BYTES;
+                    int bk;
+                    if (p.mode == 2) {
+                        const int tap = kb / p.cblocks, c0 = (kb % p.cblocks) * TC_BK;
+                        tma_load_4d(a_dst, &tmA, &full[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, cb);
+                        bk = tap * p.C + c0;
+                    } else if (kb < p.kb1) {
+                        tma_load_2d(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+                        bk = kb * TC_BK;
+                    } else {
+                        tma_load_2d(a_dst, &tmA2, &full[stage], (kb - p.kb1) * TC_BK, mt * TC_BM);
+                        bk = p.k_split + (kb - p.kb1) * TC_BK;
+                    }
+                    tma_load_2d(b_dst, &tmB, &full[stage], bk, nt * p.BN);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
+                    const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle row
+                        tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    tc_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                  // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const MsuEpilogue& E = p.E;
+        const int ew = warp - 2;              // 0..7
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;             // which interleaved set of 16-column chunks
+        const int nchunks = p.BN / 16;
+        int acc = 0; uint32_t acc_phase = 0;
+        __nv_bfloat16* Cp = reinterpret_cast<__nv_bfloat16*>(E.C);
+        __nv_bfloat16* Cpre = reinterpret_cast<__nv_bfloat16*>(E.Cpre);
+        const __nv_bfloat16* Rp = reinterpret_cast<const __nv_bfloat16*>(E.R);
+        const __nv_bfloat16* Hp = reinterpret_cast<const __nv_bfloat16*>(E.H);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            const int rl = quad * 32 + lane;
+            int64_t m;
+            if (p.mode == 2) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int cb = mt / per_img, r = mt % per_img;
+                const int y = (r / p.tiles_x) * p.bmh + rl / p.bmw, x = (r % p.tiles_x) * p.bmw + rl % p.bmw;
+                m = ((int64_t)cb * p.H + y) * p.W + x;
+            } else {
+                m = (int64_t)mt * TC_BM + rl;
+            }
+            const bool row_ok = m < p.M;
+            // row part of the output map
+            int64_t row_out = m;
+            int64_t sh_b = 0; int sh_h = 0, sh_w = 0;
+            if (row_ok) {
+                if (E.map == MSU_MAP_WINDOW) {
+                    row_out = win_to_pix(make_wingeo(E.geo), m);
+                } else if (E.map == MSU_MAP_SHUFFLE) {
+                    const int hw = E.geo[0] * E.geo[1];
+                    sh_b = m / hw;
+                    const int t = (int)(m - sh_b * hw);
+                    sh_h = t / E.geo[1];
+                    sh_w = t - sh_h * E.geo[1];
+                }
+            }
+            const bool store_ok = row_ok && row_out >= 0;
+            float rscale = 1.f;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+            for (int c = half; c < nchunks; c += 2) {
+                float v[16];
+                tc_ld16(t_base + c * 16, v);     // warp-collective: executed by all lanes
+                const int n0 = nt * p.BN + c * 16;
+                if (!store_ok || n0 >= p.N) continue;
+#pragma unroll
+                for (int g8 = 0; g8 < 2; g8++) {
+                    const int n = n0 + g8 * 8;
+                    if (n >= p.N) break;
+                    float* w = v + g8 * 8;
+                    if (E.bias != nullptr) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(E.bias + n);
+                        const float4 b1 = *reinterpret_cast<const float4*>(E.bias + n + 4);
+                        w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+                        w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+                    }
+                    int64_t ro = row_out;
+                    int co = n;
+                    if (E.map == MSU_MAP_SHUFFLE) {
+                        const int pp = E.geo[2], cc = E.geo[3];
+                        const int q = n / cc, p1 = q / pp, p2 = q - p1 * pp;
+                        ro = (sh_b * (E.geo[0] * pp) + (sh_h * pp + p1)) * (int64_t)(E.geo[1] * pp) + (sh_w * pp + p2);
+                        co = n - q * cc;
+                    }
+                    const int64_t o = ro * E.ldc + co;
+                    if (Cpre != nullptr) {
+                        uint4 u = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                                             pack_bf16x2(w[6], w[7]));
+                        *reinterpret_cast<uint4*>(Cpre + o) = u;
+                    }
+                    if (E.act == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] = gelu_f(w[i]);
+                    }
+                    if (Hp != nullptr) {
+                        float hf[8];
+                        unpack8(*reinterpret_cast<const uint4*>(Hp + m * E.ldh + n), hf);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] *= gelu_grad_f(hf[i]);
+                    }
+                    if (E.rowscale != nullptr) {
+                        rscale = E.rowscale[ro / E.rows_per_sample];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] *= rscale;
+                    }
+                    if (Rp != nullptr) {
+                        float rf[8];
+                        unpack8(*reinterpret_cast<const uint4*>(Rp + ro * E.ldr + co), rf);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] += rf[i];
+                    }
+                    uint4 u = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                                         pack_bf16x2(w[6], w[7]));
+                    *reinterpret_cast<uint4*>(Cp + o) = u;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+// 2-D bf16 map over [rows, cols] (cols contiguous, row pitch ld elements), box = [box_rows, 64], 128B swizzle.
+static bool make_map_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// 4-D bf16 map over NHWC [B, H, W, C]; box = [64 ch, bmw, bmh, 1]
+static bool make_map_nhwc(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bmw, int bmh) {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bmw, (cuuint32_t)bmh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int pick_bn(int64_t N) {
+    // largest tile <= 256 (multiple of 16) that wastes the least of the last N tile
+    if (N <= 256) return (int)((N + 15) / 16 * 16);
+    int best = 256;
+    int64_t best_waste = (N + 255) / 256 * 256 - N;
+    for (int bn = 256; bn >= 96; bn -= 16) {
+        const int64_t waste = (N + bn - 1) / bn * bn - N;
+        if (waste < best_waste) { best = bn; best_waste = waste; }
+    }
+    return best;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// returns 0 = launched, 1 = pattern unsupported (caller uses the SIMT engine), other = error
+int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
+            float* /*splitk_ws*/, int64_t /*splitk_ws_elems*/, cudaStream_t st) {
+    // ---- eligibility
+    if (A->dtype != MSU_BF16 || B->dtype != MSU_BF16 || E->dtype != MSU_BF16 || E->out_f32 || E->accumulate) return 1;
+    if (A->orient != 0 || B->orient != 0 || B->map != MSU_MAP_NONE || B->ptr2 != nullptr) return 1;
+    if (A->rowscale != nullptr || B->rowscale != nullptr) return 1;
+    if (!(A->map == MSU_MAP_NONE || A->map == MSU_MAP_CONV3)) return 1;
+    if (!(E->map == MSU_MAP_NONE || E->map == MSU_MAP_WINDOW || E->map == MSU_MAP_SHUFFLE)) return 1;
+    if (N % 8 != 0 || (E->ldc % 8) != 0 || (E->R && E->ldr % 8 != 0) || (E->H && E->ldh % 8 != 0)) return 1;
+    if (E->map == MSU_MAP_SHUFFLE && E->geo[3] % 8 != 0) return 1;
+    if ((A->ld % 8) != 0 || (B->ld % 8) != 0 || !aligned16(A->ptr) || !aligned16(B->ptr) || !aligned16(E->C)) return 1;
+    if ((E->Cpre && !aligned16(E->Cpre)) || (E->R && !aligned16(E->R)) || (E->H && !aligned16(E->H))) return 1;
+    if (E->bias && !aligned16(E->bias)) return 1;
+    if (M < 64) return 1;  // tiny problems: not worth a 128-row tile
+    if (get_encode() == nullptr) return 1;
+
+    TcParams p{};
+    p.M = M; p.N = (int)N;
+    p.BN = pick_bn(N);
+    p.num_n_tiles = (int)((N + p.BN - 1) / p.BN);
+    p.E = *E;
+    CUtensorMap tmA, tmA2, tmB;
+    if (A->map == MSU_MAP_CONV3) {
+        if (A->ptr2 != nullptr) return 1;
+        const int H = A->geo[0], W = A->geo[1], C = A->geo[2];
+        if (A->ld != C || C % 8 != 0 || K != 9 * (int64_t)C || M % ((int64_t)H * W) != 0) return 1;
+        int bmw, bmh;
+        if (W % 128 == 0) { bmw = 128; bmh = 1; }
+        else if (W % 64 == 0 && H % 2 == 0) { bmw = 64; bmh = 2; }
+        else if (W % 32 == 0 && H % 4 == 0) { bmw = 32; bmh = 4; }
+        else if (W % 16 == 0 && H % 8 == 0) { bmw = 16; bmh = 8; }
+        else return 1;
+        const int Bn = (int)(M / ((int64_t)H * W));
+        p.mode = 2; p.C = C; p.H = H; p.W = W; p.bmw = bmw; p.bmh = bmh;
+        p.cblocks = (C + TC_BK - 1) / TC_BK;
+        p.tiles_x = W / bmw; p.tiles_y = H / bmh;
+        p.num_m_tiles = Bn * p.tiles_x * p.tiles_y;
+        p.kb1 = 9 * p.cblocks; p.kb2 = 0; p.k_split = 0;
+        if (!make_map_nhwc(&tmA, A->ptr, Bn, H, W, C, bmw, bmh)) return 1;
+        tmA2 = tmA;
+    } else {
+        p.mode = A->ptr2 ? 1 : 0;
+        p.num_m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+        if (A->ptr2) {
+            if ((A->ld2 % 8) != 0 || !aligned16(A->ptr2) || A->k_split % 8 != 0) return 1;
+            const int64_t K1 = A->k_split, K2 = K - K1;
+            p.kb1 = (int)((K1 + TC_BK - 1) / TC_BK); p.kb2 = (int)((K2 + TC_BK - 1) / TC_BK); p.k_split = (int)K1;
+            if (!make_map_2d(&tmA, A->ptr, M, K1, A->ld, TC_BM)) return 1;
+            if (!make_map_2d(&tmA2, A->ptr2, M, K2, A->ld2, TC_BM)) return 1;
+        } else {
+            if (K % 8 != 0) return 1;
+            p.kb1 = (int)((K + TC_BK - 1) / TC_BK); p.kb2 = 0; p.k_split = 0;
+            if (!make_map_2d(&tmA, A->ptr, M, K, A->ld, TC_BM)) return 1;
+            tmA2 = tmA;
+        }
+    }
+    if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
+
+    const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return 1;
+    const int smem = p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        smem_set = 227 * 1024;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, p);
+    count_launch();
+    return check_launch("gemm_tc");
+}
+
 }  // namespace msu

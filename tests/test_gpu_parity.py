@@ -56,11 +56,11 @@ def test_layernorm_plain(pkg, dtype, C):
     x = torch.randn(rows, C) * 2 + 0.5
     w, b = torch.randn(C) * 0.2 + 1, torch.randn(C) * 0.1
     dy = torch.randn(rows, C)
-    xr = x.to(dtype).float().requires_grad_(True)
+    xr = x.to(dtype).float().clone().requires_grad_(True)
     wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
     yr.backward(dy.to(dtype).float())
-    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    xg = x.detach().to(dtype).to(DEV).requires_grad_(True)
     wg, bg = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
     y = Fn.LayerNormFn.apply(xg, wg, bg)
     y.backward(dy.to(dtype).to(DEV))
@@ -133,12 +133,12 @@ def test_swin_block_vs_oracle(pkg, dtype, geom):
     sd = {"b." + k: v.detach().clone() for k, v in blk.state_dict().items()}
     x = torch.randn(2, H, W, C)
     dy = torch.randn(2, H, W, C)
-    xr = x.to(dtype).float().requires_grad_(True)
+    xr = x.to(dtype).float().clone().requires_grad_(True)
     leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     yr = O.swin_block(xr, leaves, "b", nH, shift)
     yr.backward(dy.to(dtype).float())
     blk = blk.to(DEV)
-    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    xg = x.detach().to(dtype).to(DEV).requires_grad_(True)
     y = blk(xg)
     y.backward(dy.to(dtype).to(DEV))
     f32 = dtype == torch.float32
