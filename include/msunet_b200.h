@@ -151,6 +151,11 @@ int msu_metrics(int dtype, int from_logits, const void* in, const void* label_or
                 int32_t B, int64_t N, float thr, long long* ws_counts /* >= B*64*4 */, double* ws_soft /* >= B*64*8 */,
                 long long* counts, double* soft, void* pred_out, void* stream);
 
+/* dst[m, n] = src(m, n) read through the operand's row map and per-sample scale (absent rows -> 0):
+ * materialises the window-ordered gradient rows (backward of TV:models/swin_transformer.py:219-227) or the
+ * inverse depth-to-space view (backward of network/model_parts.py:402, 463) as a dense [M, N] matrix. */
+int msu_gather_rows(const MsuOperand* src, void* dst, int64_t M, int64_t N, void* stream);
+
 /* Elementwise helpers used by the host (cast fp32 <-> compute dtype, y = a + b). */
 int msu_cast(int src_dtype, int dst_dtype, const void* src, void* dst, int64_t n, void* stream);
 int msu_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);

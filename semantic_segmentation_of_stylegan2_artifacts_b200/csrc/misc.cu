@@ -80,6 +80,28 @@ __global__ void patchify4_kernel(const float* __restrict__ img, T* __restrict__ 
     Vec4<T>::st(o, v);
 }
 
+// dst[m, n] = src[map(m, n)] * rowscale[sample]  (zero where the map has no source): materialises a
+// window-ordered / inverse-depth-to-space view so that the following GEMMs read dense, TMA-able rows.
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t M, int N, int64_t ld_src, int map,
+                                   MsuOperand geo_holder) {
+    const int nv = N / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * nv) return;
+    const int64_t m = idx / nv;
+    const int n = (int)(idx - m * nv) * 4;
+    const RowCol rc = map_rc(map, geo_holder.geo, m, n);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rc.row >= 0) {
+        v = Vec4<T>::ld(src + rc.row * ld_src + rc.col);
+        if (geo_holder.rowscale != nullptr) {
+            const float s = geo_holder.rowscale[rc.row / geo_holder.rows_per_sample];
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        }
+    }
+    Vec4<T>::st(dst + m * N + n, v);
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,6 +148,23 @@ extern "C" int msu_patchify4(int dst_dtype, const float* img, void* out, int32_t
     else MSU_REQUIRE(false, "msu_patchify4: bad dtype %d", dst_dtype);
     count_launch();
     return check_launch("msu_patchify4");
+}
+
+extern "C" int msu_gather_rows(const MsuOperand* src, void* dst, int64_t M, int64_t N, void* stream) {
+    MSU_REQUIRE(src && src->ptr && dst, "msu_gather_rows: null pointer");
+    MSU_REQUIRE(src->orient == 0 && src->ptr2 == nullptr, "msu_gather_rows: operand must be a single [row, col] source");
+    MSU_REQUIRE(N % 4 == 0 && src->ld % 4 == 0, "msu_gather_rows: N and ld must be multiples of 4");
+    if (src->map == MSU_MAP_SHUFFLE || src->map == MSU_MAP_CONV3 || src->map == MSU_MAP_MERGE)
+        MSU_REQUIRE((src->map == MSU_MAP_SHUFFLE ? src->geo[3] : src->geo[2]) % 4 == 0, "msu_gather_rows: chunk width must be a multiple of 4");
+    if (M == 0) return 0;
+    const int64_t total = M * (N / 4);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src->dtype == MSU_F32) gather_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)src->ptr, (float*)dst, M, (int)N, src->ld, src->map, *src);
+    else if (src->dtype == MSU_BF16) gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src->ptr, (__nv_bfloat16*)dst, M, (int)N, src->ld, src->map, *src);
+    else MSU_REQUIRE(false, "msu_gather_rows: bad dtype %d", src->dtype);
+    count_launch();
+    return check_launch("msu_gather_rows");
 }
 
 extern "C" int msu_cast(int sd, int dd, const void* src, void* dst, int64_t n, void* stream) {

@@ -178,6 +178,13 @@ def patchify4(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
+def gather_rows(src: MsuOperand, M: int, N: int, like: torch.Tensor) -> torch.Tensor:
+    """Dense [M, N] copy of a mapped / scaled operand (same dtype as `like`)."""
+    out = torch.empty(M, N, dtype=like.dtype, device=like.device)
+    L.check(L.lib().msu_gather_rows(C.byref(src), out.data_ptr(), M, N, L.stream_ptr()), "msu_gather_rows")
+    return out
+
+
 def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if src.dtype == dtype:
         return src

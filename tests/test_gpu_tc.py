@@ -1,0 +1,159 @@
+"""tcgen05 GEMM path vs the fp32-accumulate SIMT engine on identical bf16 inputs (both through msu_gemm),
+and vs an fp64 CPU product.  Every operand mode / output map the tensor-core kernel claims is exercised."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops as o
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    _lib.lib()
+    return o
+
+
+def run_both(ops, fn):
+    """fn(backend) -> tensor; returns (tc_result, simt_result) and asserts the TC path really ran."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    ops.GEMM_BACKEND = 0
+    try:
+        a = fn()
+        torch.cuda.synchronize()
+        assert _lib.lib().msu_last_gemm_backend() == 1, "tcgen05 path was not taken"
+        ops.GEMM_BACKEND = 1
+        b = fn()
+        torch.cuda.synchronize()
+        assert _lib.lib().msu_last_gemm_backend() == 0
+    finally:
+        ops.GEMM_BACKEND = 0
+    return a, b
+
+
+def relmax(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape", [(128, 96, 96), (1000, 288, 96), (4096, 384, 96), (777, 96, 384), (300, 1152, 384),
+                                   (5000, 2304, 768), (256, 768, 3072), (130, 16, 64), (2048, 1536, 96)])
+def test_plain_bias_gelu_residual(ops, shape):
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K) * 0.5).bfloat16().to(DEV)
+    w = (torch.randn(N, K) * 0.1).bfloat16().to(DEV)
+    bias = (torch.randn(N) * 0.1).to(DEV)
+    res = torch.randn(M, N).bfloat16().to(DEV)
+
+    def go():
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        pre = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=bias, act=1, R=res), M, N, K, a.device)
+        return torch.stack([y.float(), pre.float()])
+
+    tc, simt = run_both(ops, go)
+    ref_pre = a.double().cpu() @ w.double().cpu().t() + bias.double().cpu()
+    ref = torch.nn.functional.gelu(ref_pre) + res.double().cpu()
+    assert relmax(tc[1], ref_pre) < 1e-2
+    assert relmax(tc[0], ref) < 1e-2
+    assert relmax(tc, simt) < 8e-3   # both round an fp32 accumulator to bf16
+
+
+def test_dual_source_concat(ops):
+    for (M, C) in [(1000, 96), (640, 192), (300, 32)]:
+        torch.manual_seed(C)
+        x = torch.randn(M, C).bfloat16().to(DEV)
+        s = torch.randn(M, C).bfloat16().to(DEV)
+        w = (torch.randn(C, 2 * C) * 0.1).bfloat16().to(DEV)
+        b = torch.randn(C).to(DEV) * 0.1
+
+        def go():
+            y = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+            ops.gemm(ops.operand(x, t2=s, ld2=C, k_split=C), ops.operand(w), ops.epilogue(y, bias=b), M, C, 2 * C, x.device)
+            return y.float()
+
+        tc, simt = run_both(ops, go)
+        ref = torch.cat([x, s], -1).double().cpu() @ w.double().cpu().t() + b.double().cpu()
+        assert relmax(tc, ref) < 1e-2 and relmax(tc, simt) < 8e-3
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128)])
+def test_conv3x3_implicit(ops, geom):
+    B, S, E = geom
+    torch.manual_seed(S + E)
+    x = torch.randn(B, S, S, E).bfloat16().to(DEV)
+    wt = (torch.randn(E, E, 3, 3) * 0.05)
+    bias = (torch.randn(E) * 0.1).to(DEV)
+    wr = ops.prep_weight(2, wt.to(DEV), E, E, (E, 9 * E), torch.bfloat16)
+    Mp = B * S * S
+
+    def go():
+        y = torch.empty(Mp, E, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(x.view(Mp, E), ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(wr),
+                 ops.epilogue(y, bias=bias), Mp, E, 9 * E, x.device)
+        return y.float()
+
+    tc, simt = run_both(ops, go)
+    ref = torch.nn.functional.conv2d(x.float().cpu().permute(0, 3, 1, 2).double(), wt.bfloat16().double(),
+                                     bias.double().cpu(), padding=1).permute(0, 2, 3, 1).reshape(Mp, E)
+    assert relmax(tc, ref) < 1e-2 and relmax(tc, simt) < 8e-3
+
+
+def test_output_maps_window_and_shuffle(ops):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.functional import window_geo
+    torch.manual_seed(5)
+    # window-reverse scatter + residual + per-sample scale (proj GEMM epilogue)
+    B, H, W, C = 3, 16, 16, 96
+    geo = window_geo(H, W, 3)
+    nW = (geo[2] // 7) * (geo[3] // 7)
+    Tw, T = B * nW * 49, B * H * W
+    o = torch.randn(Tw, C).bfloat16().to(DEV)
+    w = (torch.randn(C, C) * 0.1).bfloat16().to(DEV)
+    res = torch.randn(T, C).bfloat16().to(DEV)
+    sd = torch.tensor([2.0, 0.0, 2.0], device=DEV)
+
+    def go():
+        y = torch.zeros(T, C, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(o), ops.operand(w), ops.epilogue(y, R=res, map=ops.MAP_WINDOW, geo=geo, rowscale=sd, rps=H * W),
+                 Tw, C, C, o.device)
+        return y.float()
+
+    tc, simt = run_both(ops, go)
+    assert relmax(tc, simt) < 8e-3
+    # depth-to-space x2 and x4 (PatchExpand / head expand) with GELU and pre-activation copy
+    for (p, Cin, cc) in [(2, 192, 96), (4, 96, 96), (2, 96, 48)]:
+        Hh = 8
+        T = 2 * Hh * Hh
+        x = torch.randn(T, Cin).bfloat16().to(DEV)
+        N = p * p * cc
+        w = (torch.randn(N, Cin) * 0.1).bfloat16().to(DEV)
+
+        def go2():
+            y = torch.zeros(T * p * p, cc, dtype=torch.bfloat16, device=DEV)
+            pre = torch.zeros(T * p * p, cc, dtype=torch.bfloat16, device=DEV)
+            ops.gemm(ops.operand(x), ops.operand(w), ops.epilogue(y, ldc=cc, Cpre=pre, act=1, map=ops.MAP_SHUFFLE, geo=[Hh, Hh, p, cc]),
+                     T, N, Cin, x.device)
+            return torch.stack([y.float(), pre.float()])
+
+        tc, simt = run_both(ops, go2)
+        assert relmax(tc, simt) < 8e-3
+        ref = (x.double().cpu() @ w.double().cpu().t()).view(2, Hh, Hh, p, p, cc).permute(0, 1, 3, 2, 4, 5).reshape(-1, cc)
+        assert relmax(tc[1], ref) < 1e-2
+
+
+def test_gelu_grad_epilogue(ops):
+    torch.manual_seed(9)
+    M, N, K = 900, 384, 96
+    dy = torch.randn(M, K).bfloat16().to(DEV)
+    wT = (torch.randn(N, K) * 0.1).bfloat16().to(DEV)
+    h = torch.randn(M, N).bfloat16().to(DEV)
+
+    def go():
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(dy), ops.operand(wT), ops.epilogue(y, H=h, ldh=N), M, N, K, dy.device)
+        return y.float()
+
+    tc, simt = run_both(ops, go)
+    assert relmax(tc, simt) < 8e-3
