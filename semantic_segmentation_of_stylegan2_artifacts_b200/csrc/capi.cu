@@ -32,6 +32,8 @@ int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, in
 // returns 1 if the pattern is not supported by the tcgen05 path (caller falls back to SIMT), 0 ok, else error
 int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
             float* splitk_ws, int64_t splitk_ws_elems, cudaStream_t st);
+int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
+             float* ws, int64_t ws_elems, cudaStream_t st);
 
 }  // namespace msu
 
@@ -45,7 +47,9 @@ extern "C" int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilo
     cudaStream_t st = (cudaStream_t)stream;
     g_last_backend = 0;
     if (backend == 0) {
-        const int rc = gemm_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+        const int rc = (A->orient == 1 && B->orient == 1)
+                           ? wgrad_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st)
+                           : gemm_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
         if (rc == 0) { g_last_backend = 1; return 0; }
         if (rc != 1) return rc;
     }

@@ -152,6 +152,12 @@ __global__ void splitk_reduce_kernel(MsuEpilogue E, int64_t M, int64_t N, int sp
     epilogue_store(E, idx / N, (int)(idx % N), s);
 }
 
+void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st) {
+    const int64_t tot = M * N;
+    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, M, N, splits, ws);
+    count_launch();
+}
+
 int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
               float* splitk_ws, int64_t splitk_ws_elems, cudaStream_t st) {
     const int64_t gm = (M + BM - 1) / BM, gn = (N + BN - 1) / BN;

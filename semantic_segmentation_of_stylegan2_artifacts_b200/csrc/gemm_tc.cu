@@ -462,4 +462,207 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     return check_launch("gemm_tc");
 }
 
+// ================================================================================================
+// Weight-gradient GEMM on tcgen05:  C[i, j] = sum_t P[t, i] * Q[t, j]   (contraction over token rows)
+//
+// Both operands are read exactly as autograd leaves them — row-major [tokens, channels] — i.e. MN-major for
+// the tensor core (no transposes are materialised).  One CTA owns a token slab (deterministic split-K) and
+// up to MT 128-row accumulators in TMEM, so every activation element is fetched once per N tile.
+// Partials go to an fp32 workspace [split][I][J]; splitk_reduce_kernel adds them in a fixed order.
+// ================================================================================================
+struct WgParams {
+    int64_t T;          // tokens (contraction length)
+    int I, J;           // logical output [I, J]
+    int Pn, Qn;         // extent of the M-side / N-side operands (== I,J or J,I when swapped)
+    int swap;           // 1: M side is the logical j index
+    int MT, BN, n_super, n_q_tiles, splits;
+    int64_t tok_per_split;
+    int stages, qboxes;
+    float* ws;
+};
+
+constexpr int WG_BK = 64;            // tokens per stage
+constexpr int WG_BOX_BYTES = 64 * 64 * 2;
+constexpr int WG_THREADS = 192;
+
+// MN-major, 128B-swizzled descriptor: 64-channel chunks `lbo` bytes apart, 8-token groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int A_BYTES = p.MT * 2 * WG_BOX_BYTES;
+    const int B_BYTES = p.qboxes * WG_BOX_BYTES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work decomposition: blockIdx.x = (split * n_super + sup) * n_q_tiles + qt
+    const int qt = blockIdx.x % p.n_q_tiles;
+    const int sup = (blockIdx.x / p.n_q_tiles) % p.n_super;
+    const int split = blockIdx.x / (p.n_q_tiles * p.n_super);
+    const int64_t t0 = (int64_t)split * p.tok_per_split;
+    int64_t t1 = t0 + p.tok_per_split;
+    if (t1 > p.T) t1 = p.T;
+    const int KB = (int)((t1 - t0 + WG_BK - 1) / WG_BK);
+    const int p0 = sup * p.MT * 128;   // first M-side channel of this CTA
+    const int q0 = qt * p.BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                const int tok = (int)(t0 + (int64_t)kb * WG_BK);
+                uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
+                uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+                for (int bx = 0; bx < p.MT * 2; bx++) tma_load_2d(a_dst + bx * WG_BOX_BYTES, &tmP, &full[stage], p0 + bx * 64, tok);
+                for (int bx = 0; bx < p.qboxes; bx++) tma_load_2d(b_dst + bx * WG_BOX_BYTES, &tmQ, &full[stage], q0 + bx * 64, tok);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sA + (size_t)stage * A_BYTES);
+                const uint32_t b_base = smem_u32(sB + (size_t)stage * B_BYTES);
+                for (int mt = 0; mt < p.MT; mt++) {
+#pragma unroll
+                    for (int k = 0; k < WG_BK / 16; k++) {   // 16 tokens = 2048 B per K step
+                        const uint64_t adesc = make_desc_mnmajor_sw128(a_base + mt * 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES);
+                        const uint64_t bdesc = make_desc_mnmajor_sw128(b_base + k * 2048, WG_BOX_BYTES);
+                        tc_mma_bf16(tmem_base + mt * p.BN, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                }
+                tc_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tfull);
+        }
+    } else {
+        const int quad = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float* wsz = p.ws + (int64_t)split * p.I * p.J;
+        for (int mt = 0; mt < p.MT; mt++) {
+            const int pr = p0 + mt * 128 + quad * 32 + lane;   // M-side channel of this thread
+            for (int c = 0; c < p.BN / 16; c++) {
+                float v[16];
+                tc_ld16(tmem_base + mt * p.BN + c * 16 + ((uint32_t)(quad * 32) << 16), v);
+                if (KB == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                }
+                if (pr >= p.Pn) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int qc = q0 + c * 16 + i;
+                    if (qc >= p.Qn) break;
+                    if (p.swap) wsz[(int64_t)qc * p.J + pr] = v[i];
+                    else wsz[(int64_t)pr * p.J + qc] = v[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
+void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st);
+
+static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    return make_map_2d(tm, ptr, rows, cols, ld, 64);
+}
+
+// returns 0 = launched, 1 = unsupported (SIMT fallback), other = error.  A(i, t) and B(j, t) both orient=1.
+int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
+             float* ws, int64_t ws_elems, cudaStream_t st) {
+    if (A->dtype != MSU_BF16 || B->dtype != MSU_BF16 || !E->out_f32) return 1;
+    if (A->orient != 1 || B->orient != 1 || A->map != MSU_MAP_NONE || B->map != MSU_MAP_NONE) return 1;
+    if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale) return 1;
+    if (E->map != MSU_MAP_NONE || E->bias || E->R || E->H || E->Cpre || E->act || E->rowscale) return 1;
+    if ((A->ld % 8) || (B->ld % 8) || !aligned16(A->ptr) || !aligned16(B->ptr) || (I % 8) || (J % 8)) return 1;
+    if (T < 512 || ws == nullptr || get_encode() == nullptr) return 1;
+    WgParams p{};
+    p.T = T; p.I = (int)I; p.J = (int)J; p.ws = ws;
+    p.swap = J > I ? 1 : 0;
+    const MsuOperand* P = p.swap ? B : A;
+    const MsuOperand* Q = p.swap ? A : B;
+    p.Pn = p.swap ? (int)J : (int)I;
+    p.Qn = p.swap ? (int)I : (int)J;
+    p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn);
+    p.n_q_tiles = (p.Qn + p.BN - 1) / p.BN;
+    p.qboxes = (p.BN + 63) / 64;
+    const int m_tiles = (p.Pn + 127) / 128;
+    p.MT = m_tiles < 4 ? m_tiles : 4;
+    while (p.MT > 1 && p.MT * p.BN > TC_TMEM_COLS) p.MT--;
+    // keep at least 2 pipeline stages in 200 KB
+    while (p.MT > 1 && 2 * (p.MT * 2 + p.qboxes) * WG_BOX_BYTES > 200 * 1024) p.MT--;
+    p.n_super = (m_tiles + p.MT - 1) / p.MT;
+    const int stage_bytes = (p.MT * 2 + p.qboxes) * WG_BOX_BYTES;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 6) p.stages = 6;
+    if (p.stages < 2) return 1;
+    const int base_ctas = p.n_super * p.n_q_tiles;
+    int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
+    const int64_t max_splits_t = (T + 511) / 512;
+    if (splits > max_splits_t) splits = (int)max_splits_t;
+    while (splits > 1 && (int64_t)splits * I * J > ws_elems) splits--;
+    if ((int64_t)splits * I * J > ws_elems) return 1;
+    int64_t tps = (T + splits - 1) / splits;
+    tps = (tps + WG_BK - 1) / WG_BK * WG_BK;
+    splits = (int)((T + tps - 1) / tps);
+    p.splits = splits; p.tok_per_split = tps;
+    CUtensorMap tmP, tmQ;
+    if (!make_map_2d_box64(&tmP, P->ptr, T, p.Pn, P->ld)) return 1;
+    if (!make_map_2d_box64(&tmQ, Q->ptr, T, p.Qn, Q->ld)) return 1;
+    const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, p);
+    count_launch();
+    launch_splitk_reduce(*E, I, J, splits, ws, st);
+    return check_launch("wgrad_tc");
+}
+
 }  // namespace msu

@@ -4,9 +4,16 @@ bookkeeping (accumulating gradients of shared weights, skip connections) and not
 
 Activations are token-major `[rows, C]` tensors in the compute dtype (bf16 or fp32); parameters
 stay fp32 `nn.Parameter`s and gradients are returned in fp32.
+
+bf16 mode feeds the tcgen05 GEMMs: weights are read through cached bf16 shadows (plain for the forward,
+transposed for dgrad so that every tensor-core operand is K-major), and gradient rows that autograd
+hands over in pixel order are materialised once in window / depth-to-space order (msu_gather_rows) so
+that dgrad and wgrad both read dense TMA tiles.  fp32 mode (the <=1e-3 parity mode) reads the fp32
+parameters directly through the mapped-operand SIMT engine.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -17,6 +24,7 @@ from . import ops
 from .ops import MAP_CONV3, MAP_MERGE, MAP_SHUFFLE, MAP_WINDOW, epilogue, gemm, operand
 
 WS = 7
+BF16 = torch.bfloat16
 
 
 def window_geo(H: int, W: int, shift: int):
@@ -32,6 +40,56 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# bf16 weight shadows (caller-owned tensors, refreshed when the fp32 master changes)
+# ----------------------------------------------------------------------------------------------
+_shadows: dict = {}
+
+
+def shadow(p: torch.Tensor, mode: int, R: int, Cc: int, shape, dtype=BF16) -> torch.Tensor:
+    """prep_weight(mode) of parameter `p`, cached on (parameter identity, version, storage)."""
+    key = (id(p), mode, dtype)
+    ver = (p._version, p.data_ptr())
+    ent = _shadows.get(key)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if ent is not None and ent[0]() is p and ent[1] == ver and not capturing:
+        return ent[2]
+    t = ops.prep_weight(mode, p, R, Cc, shape, dtype)
+    try:
+        ref = weakref.ref(p, lambda _r, k=key: _shadows.pop(k, None))
+    except TypeError:  # pragma: no cover
+        ref = (lambda q=p: q)
+    _shadows[key] = (ref, ver, t)
+    return t
+
+
+def w_fwd(w: torch.Tensor, dt):
+    """B operand of Y = X W^T for a [N, K] weight."""
+    if dt == BF16:
+        N, K = w.shape
+        return operand(shadow(w, 0, N, K, (N, K)))
+    return operand(w)
+
+
+def w_dgrad(w: torch.Tensor, dt, col0: int = 0, ncols: Optional[int] = None):
+    """B operand of dX = dY W[:, col0:col0+ncols] for a [N, K] weight."""
+    N, K = w.shape
+    if dt == BF16:
+        wt = shadow(w, 1, N, K, (K, N))          # W^T, K-major for the tensor core
+        return operand(wt, offset=col0 * N)
+    return operand(w, ld=K, orient=1, offset=col0)
+
+
+def rows(t: torch.Tensor, M: int, N: int, dt, **kw):
+    """A operand whose logical rows are read through a map / per-sample scale.  bf16: materialise once
+    (dense rows for TMA) and return (operand, orient-1 operand); fp32: mapped operands, no copy."""
+    mapped = kw.get("map", 0) != 0 or kw.get("rowscale") is not None
+    if dt == BF16 and mapped:
+        d = ops.gather_rows(operand(t, **kw), M, N, t)
+        return operand(d), operand(d, orient=1)
+    return operand(t, **kw), operand(t, orient=1, **kw)
+
+
+# ----------------------------------------------------------------------------------------------
 class SwinBlockFn(Function):
     """x + SD(attn(LN1 x)) then + SD(mlp(LN2 .)) — TV:models/swin_transformer.py:401-455."""
 
@@ -40,7 +98,7 @@ class SwinBlockFn(Function):
                 B, H, W, nH, shift):
         ops._need_cuda(x, "x")
         x = _c(x)
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = B * H * W
         geo = window_geo(H, W, shift)
@@ -50,20 +108,20 @@ class SwinBlockFn(Function):
         HW = H * W
         # LN1 + zero-pad + roll + window partition in one gather pass
         xw, mean1, rstd1 = ops.ln_fwd(x, n1w, n1b, Tw, Cd, out_map=MAP_WINDOW, geo=geo, n_stat_rows=T)
-        qkv = torch.empty(Tw, 3 * Cd, dtype=x.dtype, device=dev)
-        gemm(operand(xw), operand(qkvw), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
+        qkv = torch.empty(Tw, 3 * Cd, dtype=dt, device=dev)
+        gemm(operand(xw), w_fwd(qkvw, dt), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
         bias = ops.relbias_expand(table, nH)
         o = ops.winattn_fwd(qkv, bias, B * nW, nH, geo)
         # proj + window reverse + un-roll + crop + stochastic depth + residual in the GEMM epilogue
-        x1 = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(o), operand(projw),
+        x1 = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(operand(o), w_fwd(projw, dt),
              epilogue(x1, bias=projb, R=x, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), Tw, Cd, Cd, dev)
         xn, mean2, rstd2 = ops.ln_fwd(x1, n2w, n2b, T, Cd)
-        h = torch.empty(T, hid, dtype=x.dtype, device=dev)
-        a = torch.empty(T, hid, dtype=x.dtype, device=dev)
-        gemm(operand(xn), operand(f1w), epilogue(a, Cpre=h, bias=f1b, act=1), T, hid, Cd, dev)
-        x2 = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(a), operand(f2w), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
+        h = torch.empty(T, hid, dtype=dt, device=dev)
+        a = torch.empty(T, hid, dtype=dt, device=dev)
+        gemm(operand(xn), w_fwd(f1w, dt), epilogue(a, Cpre=h, bias=f1b, act=1), T, hid, Cd, dev)
+        x2 = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(operand(a), w_fwd(f2w, dt), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
         ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
                               xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a)
         ctx.cfg = (B, H, W, nH, geo, nW)
@@ -75,38 +133,37 @@ class SwinBlockFn(Function):
         (x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
          xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a) = ctx.saved_tensors
         B, H, W, nH, geo, nW = ctx.cfg
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T, HW, Tw, hid = B * H * W, H * W, B * nW * 49, f1w.shape[0]
         dx2 = _c(dx2).view(T, Cd)
         f32 = dict(dtype=torch.float32, device=dev)
         # ---- MLP half
-        db2 = ops.colsum(operand(dx2, rowscale=sd2, rps=HW), T, Cd, dev)
+        dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
+        db2 = ops.colsum(dy2, T, Cd, dev)
         dW2 = torch.empty(Cd, hid, **f32)
-        gemm(operand(dx2, orient=1, rowscale=sd2, rps=HW), operand(a, orient=1), epilogue(dW2, out_f32=True),
-             Cd, hid, T, dev)
-        dh = torch.empty(T, hid, dtype=x.dtype, device=dev)
-        gemm(operand(dx2, rowscale=sd2, rps=HW), operand(f2w, orient=1), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
+        gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True), Cd, hid, T, dev)
+        dh = torch.empty(T, hid, dtype=dt, device=dev)
+        gemm(dy2, w_dgrad(f2w, dt), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
         db1 = ops.colsum(operand(dh), T, hid, dev)
         dW1 = torch.empty(hid, Cd, **f32)
         gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True), hid, Cd, T, dev)
-        dxn = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(dh), operand(f1w, orient=1), epilogue(dxn), T, Cd, hid, dev)
+        dxn = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
         dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
-        # ---- attention half (gradient rows gathered into window order by the operand map)
-        dbp = ops.colsum(operand(dx1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), Tw, Cd, dev)
+        # ---- attention half: gradient rows gathered into window order (zero rows for the padding tokens)
+        dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
+        dbp = ops.colsum(dy1, Tw, Cd, dev)
         dWp = torch.empty(Cd, Cd, **f32)
-        gemm(operand(dx1, orient=1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), operand(o, orient=1),
-             epilogue(dWp, out_f32=True), Cd, Cd, Tw, dev)
-        do = torch.empty(Tw, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(dx1, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), operand(projw, orient=1), epilogue(do),
-             Tw, Cd, Cd, dev)
+        gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True), Cd, Cd, Tw, dev)
+        do = torch.empty(Tw, Cd, dtype=dt, device=dev)
+        gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
         dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo)
         dbqkv = ops.colsum(operand(dqkv), Tw, 3 * Cd, dev)
         dWqkv = torch.empty(3 * Cd, Cd, **f32)
         gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True), 3 * Cd, Cd, Tw, dev)
-        dxw = torch.empty(Tw, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(dqkv), operand(qkvw, orient=1), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
+        dxw = torch.empty(Tw, Cd, dtype=dt, device=dev)
+        gemm(operand(dqkv), w_dgrad(qkvw, dt), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
         dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
         return (dx.view(B, H, W, Cd), dn1w, dn1b, dWqkv, dbqkv, dWp, dbp, dtable, dn2w, dn2b, dW1, db1, dW2, db2,
                 None, None, None, None, None, None, None)
@@ -125,7 +182,7 @@ class PatchEmbedFn(Function):
         E = pw.shape[0]
         T = B * (S // 4) ** 2
         patches = ops.patchify4(img, dtype)
-        w64 = ops.prep_weight(5, pw, E, 48, (E, 64), torch.float32)
+        w64 = shadow(pw, 5, E, 48, (E, 64), dtype)
         y = torch.empty(T, E, dtype=dtype, device=dev)
         gemm(operand(patches), operand(w64), epilogue(y, bias=pb), T, E, 64, dev)
         out, mean, rstd = ops.ln_fwd(y, nw, nb, T, E)
@@ -155,13 +212,13 @@ class PatchMergeFn(Function):
     @staticmethod
     def forward(ctx, x, nw, nb, rw, B, H, W):
         x = _c(x)
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         Tm = B * (H // 2) * (W // 2)
         geo = [H, W, Cd]
         xm, mean, rstd = ops.ln_fwd(x, nw, nb, Tm, 4 * Cd, in_map=MAP_MERGE, geo=geo)
-        y = torch.empty(Tm, 2 * Cd, dtype=x.dtype, device=dev)
-        gemm(operand(xm), operand(rw), epilogue(y), Tm, 2 * Cd, 4 * Cd, dev)
+        y = torch.empty(Tm, 2 * Cd, dtype=dt, device=dev)
+        gemm(operand(xm), w_fwd(rw, dt), epilogue(y), Tm, 2 * Cd, 4 * Cd, dev)
         ctx.save_for_backward(x, nw, nb, rw, xm, mean, rstd)
         ctx.cfg = (B, H, W)
         return y.view(B, (H // 2) * (W // 2), 2 * Cd)
@@ -171,14 +228,14 @@ class PatchMergeFn(Function):
     def backward(ctx, dy):
         x, nw, nb, rw, xm, mean, rstd = ctx.saved_tensors
         B, H, W = ctx.cfg
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         Tm = B * (H // 2) * (W // 2)
         dy = _c(dy).view(Tm, 2 * Cd)
         drw = torch.empty(2 * Cd, 4 * Cd, dtype=torch.float32, device=dev)
         gemm(operand(dy, orient=1), operand(xm, orient=1), epilogue(drw, out_f32=True), 2 * Cd, 4 * Cd, Tm, dev)
-        dxm = torch.empty(Tm, 4 * Cd, dtype=x.dtype, device=dev)
-        gemm(operand(dy), operand(rw, orient=1), epilogue(dxm), Tm, 4 * Cd, 2 * Cd, dev)
+        dxm = torch.empty(Tm, 4 * Cd, dtype=dt, device=dev)
+        gemm(operand(dy), w_dgrad(rw, dt), epilogue(dxm), Tm, 4 * Cd, 2 * Cd, dev)
         dx, dnw, dnb, _ = ops.ln_bwd(dxm, x, nw, nb, mean, rstd, Tm, 4 * Cd, dx_map=MAP_MERGE, geo=[H, W, Cd])
         return dx, dnw, dnb, drw, None, None, None
 
@@ -189,14 +246,14 @@ class PatchExpandFn(Function):
     @staticmethod
     def forward(ctx, x, ew, nw, nb, B, H, W):
         x = _c(x)
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = B * H * W
         x2d = x.view(T, Cd)
         c2 = Cd // 2
         geo = [H, W, 2, c2]
-        y = torch.empty(4 * T, c2, dtype=x.dtype, device=dev)
-        gemm(operand(x2d), operand(ew), epilogue(y, ldc=c2, map=MAP_SHUFFLE, geo=geo), T, 2 * Cd, Cd, dev)
+        y = torch.empty(4 * T, c2, dtype=dt, device=dev)
+        gemm(operand(x2d), w_fwd(ew, dt), epilogue(y, ldc=c2, map=MAP_SHUFFLE, geo=geo), T, 2 * Cd, Cd, dev)
         out, mean, rstd = ops.ln_fwd(y, nw, nb, 4 * T, c2)
         ctx.save_for_backward(x2d, ew, nw, nb, y, mean, rstd)
         ctx.cfg = (B, H, W, geo, x.shape)
@@ -207,16 +264,16 @@ class PatchExpandFn(Function):
     def backward(ctx, dout):
         x2d, ew, nw, nb, y, mean, rstd = ctx.saved_tensors
         B, H, W, geo, xshape = ctx.cfg
-        dev = y.device
+        dev, dt = y.device, y.dtype
         T, Cd = x2d.shape
         c2 = Cd // 2
         dout = _c(dout).view(4 * T, c2)
         dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2)
+        dyr, dyrt = rows(dy, T, 2 * Cd, dt, ld=c2, map=MAP_SHUFFLE, geo=geo)   # inverse depth-to-space view [T, 2C]
         dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
-        gemm(operand(dy, ld=c2, orient=1, map=MAP_SHUFFLE, geo=geo), operand(x2d, orient=1),
-             epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
-        dx = torch.empty(T, Cd, dtype=y.dtype, device=dev)
-        gemm(operand(dy, ld=c2, map=MAP_SHUFFLE, geo=geo), operand(ew, orient=1), epilogue(dx), T, Cd, 2 * Cd, dev)
+        gemm(dyrt, operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
+        dx = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(dyr, w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
         return dx.view(xshape), dew, dnw, dnb, None, None, None
 
 
@@ -227,11 +284,11 @@ class ConcatLinearFn(Function):
     @staticmethod
     def forward(ctx, x, skip, w, b):
         x, skip = _c(x), _c(skip)
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = x.numel() // Cd
-        y = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(x.view(T, Cd), t2=skip.view(T, Cd), ld2=Cd, k_split=Cd), operand(w), epilogue(y, bias=b),
+        y = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(operand(x.view(T, Cd), t2=skip.view(T, Cd), ld2=Cd, k_split=Cd), w_fwd(w, dt), epilogue(y, bias=b),
              T, Cd, 2 * Cd, dev)
         ctx.save_for_backward(x, skip, w)
         return y.view(x.shape[0], -1, Cd)
@@ -240,7 +297,7 @@ class ConcatLinearFn(Function):
     @once_differentiable
     def backward(ctx, dy):
         x, skip, w = ctx.saved_tensors
-        dev = x.device
+        dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = x.numel() // Cd
         dy = _c(dy).view(T, Cd)
@@ -250,10 +307,10 @@ class ConcatLinearFn(Function):
              Cd, Cd, T, dev)
         gemm(operand(dy, orient=1), operand(skip.view(T, Cd), orient=1),
              epilogue(dw, ldc=2 * Cd, out_f32=True, offset=Cd), Cd, Cd, T, dev)
-        dx = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        dskip = torch.empty(T, Cd, dtype=x.dtype, device=dev)
-        gemm(operand(dy), operand(w, ld=2 * Cd, orient=1), epilogue(dx), T, Cd, Cd, dev)
-        gemm(operand(dy), operand(w, ld=2 * Cd, orient=1, offset=Cd), epilogue(dskip), T, Cd, Cd, dev)
+        dx = torch.empty(T, Cd, dtype=dt, device=dev)
+        dskip = torch.empty(T, Cd, dtype=dt, device=dev)
+        gemm(operand(dy), w_dgrad(w, dt, 0, Cd), epilogue(dx), T, Cd, Cd, dev)
+        gemm(operand(dy), w_dgrad(w, dt, Cd, Cd), epilogue(dskip), T, Cd, Cd, dev)
         return dx.view(x.shape), dskip.view(skip.shape), dw, db
 
 
@@ -264,8 +321,8 @@ class LayerNormFn(Function):
     def forward(ctx, x, w, b):
         x = _c(x)
         Cd = x.shape[-1]
-        rows = x.numel() // Cd
-        y, mean, rstd = ops.ln_fwd(x, w, b, rows, Cd)
+        nrows = x.numel() // Cd
+        y, mean, rstd = ops.ln_fwd(x, w, b, nrows, Cd)
         ctx.save_for_backward(x, w, b, mean, rstd)
         return y.view(x.shape)
 
@@ -274,8 +331,8 @@ class LayerNormFn(Function):
     def backward(ctx, dy):
         x, w, b, mean, rstd = ctx.saved_tensors
         Cd = x.shape[-1]
-        rows = x.numel() // Cd
-        dx, dw, db, _ = ops.ln_bwd(_c(dy), x, w, b, mean, rstd, rows, Cd)
+        nrows = x.numel() // Cd
+        dx, dw, db, _ = ops.ln_bwd(_c(dy), x, w, b, mean, rstd, nrows, Cd)
         return dx, dw, db
 
 
@@ -287,7 +344,7 @@ class HeadFn(Function):
     @staticmethod
     def forward(ctx, x, ew, c1w, c1b, c2w, c2b, nw, nb, ow, B, r):
         x = _c(x)
-        dev = x.device
+        dev, dt = x.device, x.dtype
         E = x.shape[-1]
         T = B * r * r
         S = 4 * r
@@ -295,16 +352,17 @@ class HeadFn(Function):
         x2d = x.view(T, E)
         sgeo = [r, r, 4, E]
         cgeo = [S, S, E]
-        h0 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
-        a0 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
-        gemm(operand(x2d), operand(ew), epilogue(a0, ldc=E, Cpre=h0, act=1, map=MAP_SHUFFLE, geo=sgeo), T, 16 * E, E, dev)
-        w1 = ops.prep_weight(2, c1w, E, E, (E, 9 * E), torch.float32)
-        w2 = ops.prep_weight(2, c2w, E, E, (E, 9 * E), torch.float32)
-        z1 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
-        a1 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        h0 = torch.empty(Mp, E, dtype=dt, device=dev)
+        a0 = torch.empty(Mp, E, dtype=dt, device=dev)
+        gemm(operand(x2d), w_fwd(ew, dt), epilogue(a0, ldc=E, Cpre=h0, act=1, map=MAP_SHUFFLE, geo=sgeo), T, 16 * E, E, dev)
+        wd = dt if dt == BF16 else torch.float32
+        w1 = shadow(c1w, 2, E, E, (E, 9 * E), wd)
+        w2 = shadow(c2w, 2, E, E, (E, 9 * E), wd)
+        z1 = torch.empty(Mp, E, dtype=dt, device=dev)
+        a1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(a0, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1), epilogue(a1, Cpre=z1, bias=c1b, act=1),
              Mp, E, 9 * E, dev)
-        z2 = torch.empty(Mp, E, dtype=x.dtype, device=dev)
+        z2 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
         owv = _c(ow).view(E)
         logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
@@ -317,13 +375,14 @@ class HeadFn(Function):
     def backward(ctx, dlogits):
         x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd = ctx.saved_tensors
         B, r, xshape, owshape = ctx.cfg
-        dev = x2d.device
+        dev, dt = x2d.device, x2d.dtype
         T, E = x2d.shape
         S = 4 * r
         Mp = B * S * S
         sgeo = [r, r, 4, E]
         cgeo = [S, S, E]
         f32 = dict(dtype=torch.float32, device=dev)
+        wd = dt if dt == BF16 else torch.float32
         dl = _c(dlogits).view(Mp)
         dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
         # conv2
@@ -332,8 +391,8 @@ class HeadFn(Function):
         gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw2r, out_f32=True),
              E, 9 * E, Mp, dev)
         dc2w = ops.prep_weight(4, dw2r, E, E, (E, E, 3, 3), torch.float32)
-        w2f = ops.prep_weight(3, c2w, E, E, (E, 9 * E), torch.float32)
-        dz1 = torch.empty(Mp, E, dtype=x2d.dtype, device=dev)
+        w2f = shadow(c2w, 3, E, E, (E, 9 * E), wd)
+        dz1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
         # conv1
         dc1b = ops.colsum(operand(dz1), Mp, E, dev)
@@ -341,15 +400,15 @@ class HeadFn(Function):
         gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw1r, out_f32=True),
              E, 9 * E, Mp, dev)
         dc1w = ops.prep_weight(4, dw1r, E, E, (E, E, 3, 3), torch.float32)
-        w1f = ops.prep_weight(3, c1w, E, E, (E, 9 * E), torch.float32)
-        dh0 = torch.empty(Mp, E, dtype=x2d.dtype, device=dev)
+        w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
+        dh0 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f), epilogue(dh0, H=h0, ldh=E), Mp, E, 9 * E, dev)
-        # expand
+        # expand (inverse depth-to-space view [T, 16E])
+        dhr, dhrt = rows(dh0, T, 16 * E, dt, ld=E, map=MAP_SHUFFLE, geo=sgeo)
         dew = torch.empty(16 * E, E, **f32)
-        gemm(operand(dh0, ld=E, orient=1, map=MAP_SHUFFLE, geo=sgeo), operand(x2d, orient=1),
-             epilogue(dew, out_f32=True), 16 * E, E, T, dev)
-        dx = torch.empty(T, E, dtype=x2d.dtype, device=dev)
-        gemm(operand(dh0, ld=E, map=MAP_SHUFFLE, geo=sgeo), operand(ew, orient=1), epilogue(dx), T, E, 16 * E, dev)
+        gemm(dhrt, operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev)
+        dx = torch.empty(T, E, dtype=dt, device=dev)
+        gemm(dhr, w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
         return (dx.view(xshape), dew, dc1w, dc1b, dc2w, dc2b, dnw, dnb, dow.view(owshape), None, None)
 
 

@@ -143,6 +143,47 @@ def test_output_maps_window_and_shuffle(ops):
         assert relmax(tc[1], ref) < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(5000, 384, 96), (20000, 288, 96), (4096, 96, 384), (3000, 96, 96), (2048, 1152, 384),
+                                   (1024, 768, 3072), (7777, 64, 32), (600, 192, 96), (4096, 96, 864)])
+def test_wgrad_mn_major(ops, shape):
+    """dW[i, j] = sum_t dY[t, i] X[t, j]: both operands MN-major for the tensor core, deterministic split-K."""
+    T, I, J = shape
+    torch.manual_seed(T + I)
+    dy = torch.randn(T, I).bfloat16().to(DEV)
+    x = torch.randn(T, J).bfloat16().to(DEV)
+
+    def go():
+        dw = torch.empty(I, J, dtype=torch.float32, device=DEV)
+        ops.gemm(ops.operand(dy, orient=1), ops.operand(x, orient=1), ops.epilogue(dw, out_f32=True), I, J, T, dy.device)
+        return dw
+
+    tc, simt = run_both(ops, go)
+    ref = dy.double().cpu().t() @ x.double().cpu()
+    assert relmax(tc, ref) < 2e-5
+    assert relmax(tc, simt) < 2e-5
+    tc2, _ = run_both(ops, go)
+    assert torch.equal(tc, tc2)  # fixed reduction order
+
+
+def test_wgrad_into_column_slice(ops):
+    """concat_back_dim weight gradient: two products written into the halves of one [C, 2C] buffer."""
+    T, C = 3000, 96
+    torch.manual_seed(1)
+    dy = torch.randn(T, C).bfloat16().to(DEV)
+    x = torch.randn(T, C).bfloat16().to(DEV)
+    s = torch.randn(T, C).bfloat16().to(DEV)
+
+    def go():
+        dw = torch.zeros(C, 2 * C, dtype=torch.float32, device=DEV)
+        ops.gemm(ops.operand(dy, orient=1), ops.operand(x, orient=1), ops.epilogue(dw, ldc=2 * C, out_f32=True), C, C, T, dy.device)
+        ops.gemm(ops.operand(dy, orient=1), ops.operand(s, orient=1), ops.epilogue(dw, ldc=2 * C, out_f32=True, offset=C), C, C, T, dy.device)
+        return dw
+
+    tc, simt = run_both(ops, go)
+    ref = dy.double().cpu().t() @ torch.cat([x, s], -1).double().cpu()
+    assert relmax(tc, ref) < 2e-5 and relmax(tc, simt) < 2e-5
+
+
 def test_gelu_grad_epilogue(ops):
     torch.manual_seed(9)
     M, N, K = 900, 384, 96
