@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the MS-UNet hot path (BASELINE.json): train img/s, fwd + DynamicLoss + bwd, T96 @ 512x512.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU cores
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract: `value` = whole-job img/s with inputs
+resident in HBM (device-timed, max over ranks); `e2e` = the same through the public API with pinned-host
+inputs copied H2D and the loss read back D2H every step; `roofline` = the dominant kernel (tcgen05 implicit
+3x3 conv) timed live with CUDA events; `cpu_baseline` = the oracle port on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_img_per_s_512x512_msunet_fwd_bwd"
+UNIT = "img/s"
+IMG, PER_GPU_BATCH = 512, 16
+T96 = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24])
+GFLOP_PER_IMG_FWD_BWD = 594.2  # BASELINE.md, T96 @ 512^2, live graph
+
+
+def synth_batch(B, S, seed):
+    """Synthetic face-shaped batch: low-frequency images in [0,1], 60 % of masks carry 1-3 elliptical blobs,
+    40 % are all-zero 'real' images."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(B, 3, S // 16, S // 16, generator=g)
+    x = torch.nn.functional.interpolate(base, size=(S, S), mode="bilinear", align_corners=False).clamp_(0, 1)
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    face = (((yy - S / 2) / (0.45 * S)) ** 2 + ((xx - S / 2) / (0.35 * S)) ** 2 < 1).float()
+    x = (0.6 * x + 0.4 * face[None, None]).contiguous()
+    y = torch.zeros(B, S, S)
+    for b in range(B):
+        if torch.rand((), generator=g) < 0.4:
+            continue
+        for _ in range(int(torch.randint(1, 4, (), generator=g))):
+            cy, cx = (torch.rand(2, generator=g) * S).tolist()
+            ry, rx = (torch.rand(2, generator=g) * 0.12 * S + 0.03 * S).tolist()
+            y[b] = torch.maximum(y[b], (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1).float())
+    return x, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step_factory(img, batch):
+    """The reference algorithm (oracle port, CPU fp32, all host threads) on a bounded sample of the workload."""
+    import torch
+    from oracle import msunet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.Cfg(img_size=img, embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24))
+    sd = O.make_weights(cfg)
+    x, y = synth_batch(batch, img, 4321)
+
+    def step():
+        _, loss, _ = O.train_step(sd, x, y, cfg)
+        return float(loss)
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 1
+    step, cores = cpu_reference_step_factory(IMG, sample_b)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    v = sample_b / dt
+    sample = f"T96 {IMG}x{IMG} fwd+DynamicLoss+bwd on {sample_b} image/step, {steps} timed steps (bounded sample of batch {PER_GPU_BATCH})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MS-UNet T96 training step {IMG}x{IMG} (reference algorithm, CPU)", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--img", type=int, default=IMG)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--drop-path", type=float, default=0.1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import semantic_segmentation_of_stylegan2_artifacts_b200 as pkg
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    B, S = args.batch, args.img
+
+    torch.manual_seed(1234)
+    model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, **T96).set_precision(args.precision).to(dev).train()
+    if world > 1:
+        from semantic_segmentation_of_stylegan2_artifacts_b200.dp import DataParallelB200
+        model = DataParallelB200(model)
+    crit = DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)
+    x_h, y_h = synth_batch(B, S, 4321 + rank)
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    params = [p for p in model.parameters()]
+
+    def step(x, y):
+        for p in params:
+            p.grad = None
+        loss = crit(model(x), y)
+        loss.backward()
+        if world > 1:
+            model.finish_gradient_sync()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up (also builds weight shadows, workspaces, func attributes)
+    for _ in range(W):
+        step(x_d, y_d)
+    barrier()
+
+    # ---------------- optional whole-step CUDA graph (fwd + loss + bwd [+ allreduce])
+    graph, g_loss = None, None
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_loss = step(x_d, y_d)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # capture is an optimisation, never a requirement
+            print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return g_loss
+        return step(x_d, y_d)
+
+    for _ in range(2):
+        run_step()
+    barrier()
+
+    # ---------------- timed region: K steps, device-timed, max over ranks
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = pkg.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        run_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = pkg.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    if graph is not None:
+        # kernels replayed from the graph are the ones captured once: count them per replay
+        n1 = pkg.launch_count()
+        step(x_d, y_d)
+        torch.cuda.synchronize()
+        launches = (pkg.launch_count() - n1) * args.steps
+
+    # ---------------- e2e: public API, pinned host -> device every step, loss read back every step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_h.to(dev, non_blocking=True)
+        yd = y_h.to(dev, non_blocking=True)
+        if graph is not None:
+            x_d.copy_(xd, non_blocking=True)
+            y_d.copy_(yd, non_blocking=True)
+            graph.replay()
+            lv = g_loss.item()
+        else:
+            lv = step(xd, yd).item()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(te.item()) / 1e3)
+    h2d = x_h.numel() * 4 + y_h.numel() * 4
+    d2h = 4
+
+    # ---------------- roofline of the dominant kernel, timed live with CUDA events on the launch stream
+    roof = None
+    if rank == 0:
+        ops.PROF = []
+        step(x_d, y_d)
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, a, b in ops.PROF:
+            d = agg.setdefault(tag, [0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += 1
+        ops.PROF = None
+        top = max(agg.items(), key=lambda kv: kv[1][0])
+        (M, N, K, kind), (tot_ms, cnt) = top
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = 2.0 * M * N * K / (tot_ms / cnt * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic, "kernel": f"{kind} M={M} N={N} K={K}", "launches_per_step": cnt,
+                "share_of_step": tot_ms / ms_per_step if graph is None else None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "gemm_ms_by_kind": {f"{k[3]}:{k[0]}x{k[1]}x{k[2]}": round(v[0], 3) for k, v in
+                                    sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, cores = cpu_reference_step_factory(S, 1)
+        cstep()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            cstep()
+        cdt = (time.perf_counter() - t0) / n
+        cpu = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"T96 {S}x{S} fwd+DynamicLoss+bwd on 1 image/step, {n} timed steps after 1 warm-up"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"MS-UNet T96 (embed 96, depths 2-2-6-2, window 7) training step fwd+DynamicLoss+bwd, "
+                                   f"{S}x{S}, batch {B}/GPU (global {B * world}), drop_path {args.drop_path}",
+                       "parallelism": f"dp{world}", "cuda_graph": graph is not None,
+                       "l2": "working set >> L2: ~10 GB of activations are written and re-read every step",
+                       "optimizer": "excluded (metric is fwd+bwd)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "model_tflops": value * GFLOP_PER_IMG_FWD_BWD / 1e3 / world,
+            "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -606,6 +606,184 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
 
 void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st);
 
+// ================================================================================================
+// 3x3 conv weight gradient on tcgen05:  dW[co, (tap, ci)] = sum_pix dZ[pix, co] * X[pix + off(tap), ci]
+// Token slabs are WB consecutive pixels of one image row; the shifted X slabs come from the same 4-D NHWC
+// tensor map with (x+dx, y+dy) coordinates (TMA zero fill = conv padding).  A CTA keeps the accumulators of
+// up to G taps in TMEM (G*BN <= 512 columns) so dZ is fetched once per tap group.
+// ================================================================================================
+struct WcParams {
+    int E, H, W, Bn;          // channels, image size, batch
+    int WB, G, BN, n_groups, splits, boxes;   // slab width, taps per CTA, N per tap, tap groups, K splits, 64-ch boxes per operand
+    int64_t slabs, slabs_per_split;
+    int stages;
+    float* ws;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, const WcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int BOX = p.WB * 128;
+    const int grp = blockIdx.x % p.n_groups;
+    const int split = blockIdx.x / p.n_groups;
+    const int tap0 = grp * p.G;
+    const int ntap = (9 - tap0) < p.G ? (9 - tap0) : p.G;
+    const int A_BYTES = p.boxes * BOX;
+    const int B_BYTES = p.G * p.boxes * BOX;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t s0 = (int64_t)split * p.slabs_per_split;
+    int64_t s1 = s0 + p.slabs_per_split;
+    if (s1 > p.slabs) s1 = p.slabs;
+    const int KB = (int)(s1 - s0);
+    const int slabs_per_row = p.W / p.WB;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                const int64_t slab = s0 + kb;
+                const int x0 = (int)(slab % slabs_per_row) * p.WB;
+                const int64_t row = slab / slabs_per_row;
+                const int y = (int)(row % p.H), b = (int)(row / p.H);
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], A_BYTES + ntap * p.boxes * BOX);
+                uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
+                uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+                for (int bx = 0; bx < p.boxes; bx++) tma_load_4d(a_dst + bx * BOX, &tmZ, &full[stage], bx * 64, x0, y, b);
+                for (int t = 0; t < ntap; t++) {
+                    const int tap = tap0 + t;
+                    for (int bx = 0; bx < p.boxes; bx++)
+                        tma_load_4d(b_dst + (t * p.boxes + bx) * BOX, &tmX, &full[stage], bx * 64, x0 + tap % 3 - 1, y + tap / 3 - 1, b);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sA + (size_t)stage * A_BYTES);
+                const uint32_t b_base = smem_u32(sB + (size_t)stage * B_BYTES);
+                for (int t = 0; t < ntap; t++) {
+                    for (int k = 0; k < p.WB / 16; k++) {
+                        const uint64_t adesc = make_desc_mnmajor_sw128(a_base + k * 2048, BOX);
+                        const uint64_t bdesc = make_desc_mnmajor_sw128(b_base + t * p.boxes * BOX + k * 2048, BOX);
+                        tc_mma_bf16(tmem_base + t * p.BN, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                }
+                tc_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tfull);
+        }
+    } else {
+        const int quad = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int J = 9 * p.E;
+        float* wsz = p.ws + (int64_t)split * p.E * J;
+        const int co = quad * 32 + lane;
+        for (int t = 0; t < ntap; t++) {
+            for (int c = 0; c < p.BN / 16; c++) {
+                float v[16];
+                tc_ld16(tmem_base + t * p.BN + c * 16 + ((uint32_t)(quad * 32) << 16), v);
+                if (co >= p.E) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int ci = c * 16 + i;
+                    if (ci >= p.E) break;
+                    wsz[(int64_t)co * J + (tap0 + t) * p.E + ci] = KB > 0 ? v[i] : 0.f;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
+// A = dZ (orient 1, plain [pix, E]); B = X (orient 1, MAP_CONV3 over NHWC [Bn,H,W,E]); out fp32 [E, 9E]
+static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
+                         float* ws, int64_t ws_elems, cudaStream_t st) {
+    const int H = B->geo[0], W = B->geo[1], Ec = B->geo[2];
+    if (I != Ec || J != 9 * (int64_t)Ec || Ec > 128 || Ec % 8 != 0 || A->ld != Ec || B->ld != Ec) return 1;
+    if (T % ((int64_t)H * W) != 0) return 1;
+    WcParams p{};
+    p.E = Ec; p.H = H; p.W = W; p.Bn = (int)(T / ((int64_t)H * W)); p.ws = ws;
+    p.WB = (W % 64 == 0) ? 64 : (W % 32 == 0 ? 32 : (W % 16 == 0 ? 16 : 0));
+    if (p.WB == 0) return 1;
+    p.BN = (Ec + 15) / 16 * 16;
+    p.boxes = (Ec + 63) / 64;
+    p.G = TC_TMEM_COLS / p.BN;
+    if (p.G > 9) p.G = 9;
+    const int BOX = p.WB * 128;
+    while (p.G > 1 && 2 * (p.boxes + p.G * p.boxes) * BOX > 200 * 1024) p.G--;
+    p.n_groups = (9 + p.G - 1) / p.G;
+    const int stage_bytes = (p.boxes + p.G * p.boxes) * BOX;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 6) p.stages = 6;
+    if (p.stages < 2) return 1;
+    p.slabs = (int64_t)p.Bn * H * (W / p.WB);
+    int splits = (2 * num_sms() + p.n_groups - 1) / p.n_groups;
+    if (splits > p.slabs) splits = (int)p.slabs;
+    while (splits > 1 && (int64_t)splits * I * J > ws_elems) splits--;
+    if ((int64_t)splits * I * J > ws_elems) return 1;
+    p.slabs_per_split = (p.slabs + splits - 1) / splits;
+    splits = (int)((p.slabs + p.slabs_per_split - 1) / p.slabs_per_split);
+    p.splits = splits;
+    CUtensorMap tmZ, tmX;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)Ec, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Bn};
+        cuuint64_t gstr[3] = {(cuuint64_t)Ec * 2, (cuuint64_t)W * Ec * 2, (cuuint64_t)H * W * Ec * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.WB, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        for (int k = 0; k < 2; k++) {
+            if (get_encode()(k ? &tmX : &tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k ? B->ptr : A->ptr), gdim, gstr,
+                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return 1;
+        }
+    }
+    const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("wgrad_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    wgrad_conv_tc_kernel<<<p.n_groups * splits, WG_THREADS, smem, st>>>(tmZ, tmX, p);
+    count_launch();
+    launch_splitk_reduce(*E, I, J, splits, ws, st);
+    return check_launch("wgrad_conv_tc");
+}
+
 static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
     return make_map_2d(tm, ptr, rows, cols, ld, 64);
 }
@@ -614,6 +792,12 @@ static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, in
 int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
              float* ws, int64_t ws_elems, cudaStream_t st) {
     if (A->dtype != MSU_BF16 || B->dtype != MSU_BF16 || !E->out_f32) return 1;
+    if (A->orient == 1 && B->orient == 1 && A->map == MSU_MAP_NONE && B->map == MSU_MAP_CONV3) {
+        if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale || !aligned16(A->ptr) || !aligned16(B->ptr)) return 1;
+        if (E->map != MSU_MAP_NONE || E->bias || E->R || E->H || E->Cpre || E->act || E->rowscale) return 1;
+        if (ws == nullptr || get_encode() == nullptr) return 1;
+        return wgrad_conv_tc(A, B, E, I, J, T, ws, ws_elems, st);
+    }
     if (A->orient != 1 || B->orient != 1 || A->map != MSU_MAP_NONE || B->map != MSU_MAP_NONE) return 1;
     if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale) return 1;
     if (E->map != MSU_MAP_NONE || E->bias || E->R || E->H || E->Cpre || E->act || E->rowscale) return 1;

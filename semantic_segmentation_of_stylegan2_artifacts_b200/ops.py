@@ -81,10 +81,21 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     return e
 
 
+PROF = None  # bench.py sets this to a list to collect (tag, start_event, end_event) per GEMM launch
+
+
 def gemm(A: MsuOperand, B: MsuOperand, E: MsuEpilogue, M: int, N: int, K: int, dev: torch.device) -> None:
     ws = workspace(dev)
+    if PROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.lib().msu_gemm(C.byref(A), C.byref(B), C.byref(E), M, N, K, ws.data_ptr(), ws.numel(), GEMM_BACKEND,
                              L.stream_ptr()), "msu_gemm")
+    if PROF is not None:
+        e1.record()
+        kind = ("wgrad" if A.orient == 1 else ("conv3x3" if A.map == MAP_CONV3 else "gemm"))
+        kind += "_tc" if L.lib().msu_last_gemm_backend() == 1 else "_simt"
+        PROF.append(((M, N, K, kind), e0, e1))
 
 
 def colsum(X: MsuOperand, M: int, N: int, dev: torch.device) -> torch.Tensor:

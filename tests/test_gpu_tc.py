@@ -165,6 +165,31 @@ def test_wgrad_mn_major(ops, shape):
     assert torch.equal(tc, tc2)  # fixed reduction order
 
 
+@pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128), (3, 48, 64)])
+def test_conv3x3_wgrad(ops, geom):
+    """dW[co,(tap ci)] = sum_pix dZ[pix,co] X[pix+off(tap),ci] with shifted NHWC slabs straight from TMA."""
+    B, S, E = geom
+    torch.manual_seed(S * 7 + E)
+    x = torch.randn(B, S, S, E).bfloat16().to(DEV)
+    dz = torch.randn(B, S, S, E).bfloat16().to(DEV)
+    Mp = B * S * S
+
+    def go():
+        dw = torch.empty(E, 9 * E, dtype=torch.float32, device=DEV)
+        ops.gemm(ops.operand(dz.view(Mp, E), orient=1), ops.operand(x.view(Mp, E), ld=E, orient=1, map=ops.MAP_CONV3, geo=[S, S, E]),
+                 ops.epilogue(dw, out_f32=True), E, 9 * E, Mp, x.device)
+        return dw
+
+    tc, simt = run_both(ops, go)
+    xr = x.float().cpu().permute(0, 3, 1, 2).double().requires_grad_(False)
+    w = torch.zeros(E, E, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(xr, w, padding=1)
+    y.backward(dz.float().cpu().permute(0, 3, 1, 2).double())
+    ref = w.grad.permute(0, 2, 3, 1).reshape(E, 9 * E)   # [co, (tap ci)]
+    assert relmax(tc, ref) < 2e-5
+    assert relmax(tc, simt) < 2e-5
+
+
 def test_wgrad_into_column_slice(ops):
     """concat_back_dim weight gradient: two products written into the halves of one [C, 2C] buffer."""
     T, C = 3000, 96
