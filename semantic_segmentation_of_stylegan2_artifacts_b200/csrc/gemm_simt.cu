@@ -191,6 +191,38 @@ __global__ void colsum_partial_kernel(MsuOperand X, int64_t M, int64_t N, int64_
     for (int64_t r = r0; r < r1; r++) s += fetch_operand(X, r, n, M, N);
     ws[(int64_t)blockIdx.y * N + n] = s;
 }
+// fast path: dense [M, N] rows, 64/128-bit loads, each block sums a row slab (HBM-bound: M*N*e bytes)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_dense_kernel(const T* __restrict__ X, int64_t M, int N, int64_t ld,
+                                                          int64_t rows_per_block, float* __restrict__ ws) {
+    __shared__ float4 sm[8][32];
+    const int vc = blockIdx.x * 32 + threadIdx.x;          // vector column (4 elements)
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = imin(M, r0 + rows_per_block);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (vc * 4 < N) {
+        int64_t r = r0 + threadIdx.y;
+        for (; r + 8 < r1; r += 16) {                       // two independent loads in flight
+            const float4 u = Vec4<T>::ld(X + r * ld + vc * 4);
+            const float4 v = Vec4<T>::ld(X + (r + 8) * ld + vc * 4);
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+        for (; r < r1; r += 8) {
+            const float4 u = Vec4<T>::ld(X + r * ld + vc * 4);
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    __syncthreads();
+    if (threadIdx.y == 0 && vc * 4 < N) {
+        float4 s = sm[0][threadIdx.x];
+#pragma unroll
+        for (int i = 1; i < 8; i++) { const float4 t = sm[i][threadIdx.x]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        *reinterpret_cast<float4*>(ws + (int64_t)blockIdx.y * N + vc * 4) = s;
+    }
+}
+
 __global__ void colsum_final_kernel(const float* ws, int parts, int64_t N, float* out, int accumulate) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -207,6 +239,20 @@ extern "C" int msu_colsum(const MsuOperand* X, int64_t M, int64_t N, float* out,
                           int64_t ws_elems, void* stream) {
     MSU_REQUIRE(X && out && ws, "msu_colsum: null pointer");
     MSU_REQUIRE(X->orient == 0, "msu_colsum: operand must be [row, col]");
+    if (X->map == MSU_MAP_NONE && X->rowscale == nullptr && X->ptr2 == nullptr && N % 4 == 0 && X->ld % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(X->ptr) & 15) == 0) {
+        int parts = (int)imin(4 * num_sms(), imax(1, M / 128));
+        while (parts > 1 && (int64_t)parts * N > ws_elems) parts--;
+        const int64_t rpb = (M + parts - 1) / parts;
+        parts = (int)((M + rpb - 1) / rpb);
+        cudaStream_t st = (cudaStream_t)stream;
+        dim3 grid((unsigned)((N / 4 + 31) / 32), (unsigned)parts), block(32, 8);
+        if (X->dtype == MSU_F32) colsum_dense_kernel<float><<<grid, block, 0, st>>>((const float*)X->ptr, M, (int)N, X->ld, rpb, ws);
+        else colsum_dense_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)X->ptr, M, (int)N, X->ld, rpb, ws);
+        colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ws, parts, N, out, accumulate);
+        count_launch(2);
+        return check_launch("msu_colsum");
+    }
     int parts = (int)imin(256, imax(1, M / 64));
     while (parts > 1 && (int64_t)parts * N > ws_elems) parts--;
     const int64_t rpb = (M + parts - 1) / parts;

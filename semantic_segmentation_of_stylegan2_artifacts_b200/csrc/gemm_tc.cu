@@ -99,14 +99,15 @@ struct TcParams {
     int mode;                 // 0 plain, 1 dual, 2 conv3x3
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
-    int stages;
+    int stages, nstg;         // operand pipeline depth, number of bf16 output staging tiles (1 or 2)
     MsuEpilogue E;
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_THREADS = 320;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_DRAIN_WARPS = 4;    // TMEM -> bf16 staging (one per TMEM lane quadrant)
+constexpr int TC_STORE_WARPS = 16;   // staging -> fused epilogue -> coalesced global stores
+constexpr int TC_THREADS = 32 * (2 + TC_DRAIN_WARPS + TC_STORE_WARPS);
 constexpr int TC_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -123,6 +124,32 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     }
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 2 MUFU + ~12 FMA-class ops instead of erff's ~45.
+// Only used by the bf16 epilogue, where it is far below the output rounding (fp32 parity mode keeps erff).
+__device__ __forceinline__ void erf_exp_fast(float x, float& erf_abs, float& e) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    e = exp2f(z * z * -1.4426950408889634f);   // exp(-x^2/2)
+    erf_abs = fmaf(-poly, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    float ea, e;
+    erf_exp_fast(x, ea, e);
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(ea, x), hx);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    float ea, e;
+    erf_exp_fast(x, ea, e);
+    const float cdf = fmaf(0.5f, copysignf(ea, x), 0.5f);
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -135,7 +162,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;   // [2]
     uint64_t* tempty = tfull + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* sfull = tempty + 2;         // [2] staging tile filled by the drain warps
+    uint64_t* sempty = sfull + 2;         // [2] staging tile consumed by the store warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
+    int64_t* sRowOut = reinterpret_cast<int64_t*>(tmem_slot + 4);   // [2][128] mapped output row of each tile row (-1: skip)
+    int64_t* sRowM = sRowOut + 2 * TC_BM;                           // [2][128] logical row m of each tile row
+    __nv_bfloat16* sStage = reinterpret_cast<__nv_bfloat16*>(sRowM + 2 * TC_BM);  // [2][128][BN + 8] bf16 output staging
+    const int pitch = p.BN + 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -143,7 +176,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_DRAIN_WARPS);
+                                      mbar_init(&sfull[a], TC_DRAIN_WARPS); mbar_init(&sempty[a], TC_STORE_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -216,110 +250,142 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {
-        // ===================== epilogue: TMEM -> registers -> global =====================
+    } else if (warp < 2 + TC_DRAIN_WARPS) {
+        // ===================== drain warps: TMEM -> registers (+bias) -> bf16 staging tile =====================
         const MsuEpilogue& E = p.E;
-        const int ew = warp - 2;              // 0..7
-        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;             // which interleaved set of 16-column chunks
+        const int ew = warp - 2;              // 0..7: TMEM lane quadrant x interleaved column half
+        const int quad = warp & 3;
+        const int half = ew >> 2;
         const int nchunks = p.BN / 16;
         int acc = 0; uint32_t acc_phase = 0;
+        int sb = 0; uint32_t sb_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            const int rl = quad * 32 + lane;
+            mbar_wait(&sempty[sb], sb_phase ^ 1);      // store warps have finished with this staging buffer
+            __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
+            if (half == 0) {
+                int64_t m;
+                if (p.mode == 2) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    const int cb = mt / per_img, r = mt % per_img;
+                    const int y = (r / p.tiles_x) * p.bmh + rl / p.bmw, x = (r % p.tiles_x) * p.bmw + rl % p.bmw;
+                    m = ((int64_t)cb * p.H + y) * p.W + x;
+                } else {
+                    m = (int64_t)mt * TC_BM + rl;
+                }
+                int64_t ro = -1;
+                if (m < p.M) {
+                    if (E.map == MSU_MAP_WINDOW) {
+                        ro = win_to_pix(make_wingeo(E.geo), m);
+                    } else if (E.map == MSU_MAP_SHUFFLE) {   // base row; (p1, p2) offsets are added per column chunk
+                        const int hw = E.geo[0] * E.geo[1], pp = E.geo[2];
+                        const int64_t b = m / hw;
+                        const int t = (int)(m - b * hw);
+                        const int hh = t / E.geo[1], ww = t - hh * E.geo[1];
+                        ro = (b * (E.geo[0] * pp) + hh * pp) * (int64_t)(E.geo[1] * pp) + ww * pp;
+                    } else {
+                        ro = m;
+                    }
+                }
+                sRowOut[sb * TC_BM + rl] = ro;
+                sRowM[sb * TC_BM + rl] = m;
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+            for (int c = half; c < nchunks; c += TC_DRAIN_WARPS / 4) {
+                float v[16];
+                tc_ld16(t_base + c * 16, v);     // warp-collective: executed by all lanes
+                const int n0 = nt * p.BN + c * 16;
+                if (E.bias != nullptr) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; g4++) {
+                        if (n0 + g4 * 4 < p.N) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(E.bias + n0 + g4 * 4);
+                            v[g4 * 4] += b0.x; v[g4 * 4 + 1] += b0.y; v[g4 * 4 + 2] += b0.z; v[g4 * 4 + 3] += b0.w;
+                        }
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)rl * pitch + c * 16);
+                dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tempty[acc]);      // TMEM buffer is free for the MMA warp again
+                mbar_arrive(&sfull[sb]);        // staging tile ready (release: smem writes of this warp are visible)
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++sb == p.nstg) { sb = 0; sb_phase ^= 1; }
+        }
+    } else {
+        // ===================== store warps: staging tile -> fused epilogue -> coalesced global stores =====================
+        const MsuEpilogue& E = p.E;
         __nv_bfloat16* Cp = reinterpret_cast<__nv_bfloat16*>(E.C);
         __nv_bfloat16* Cpre = reinterpret_cast<__nv_bfloat16*>(E.Cpre);
         const __nv_bfloat16* Rp = reinterpret_cast<const __nv_bfloat16*>(E.R);
         const __nv_bfloat16* Hp = reinterpret_cast<const __nv_bfloat16*>(E.H);
+        const int st_tid = threadIdx.x - 32 * (2 + TC_DRAIN_WARPS);
+        const int cpr = p.BN / 8;
+        const uint32_t cpr_magic = (1u << 22) / (uint32_t)cpr + 1u;   // exact id / cpr for id < 128 * cpr, cpr <= 32
+        const bool passthrough = (E.act == 0 && Hp == nullptr && E.rowscale == nullptr && Rp == nullptr);
+        int sb = 0; uint32_t sb_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
-            const int rl = quad * 32 + lane;
-            int64_t m;
-            if (p.mode == 2) {
-                const int per_img = p.tiles_x * p.tiles_y;
-                const int cb = mt / per_img, r = mt % per_img;
-                const int y = (r / p.tiles_x) * p.bmh + rl / p.bmw, x = (r % p.tiles_x) * p.bmw + rl % p.bmw;
-                m = ((int64_t)cb * p.H + y) * p.W + x;
-            } else {
-                m = (int64_t)mt * TC_BM + rl;
-            }
-            const bool row_ok = m < p.M;
-            // row part of the output map
-            int64_t row_out = m;
-            int64_t sh_b = 0; int sh_h = 0, sh_w = 0;
-            if (row_ok) {
-                if (E.map == MSU_MAP_WINDOW) {
-                    row_out = win_to_pix(make_wingeo(E.geo), m);
-                } else if (E.map == MSU_MAP_SHUFFLE) {
-                    const int hw = E.geo[0] * E.geo[1];
-                    sh_b = m / hw;
-                    const int t = (int)(m - sh_b * hw);
-                    sh_h = t / E.geo[1];
-                    sh_w = t - sh_h * E.geo[1];
+            const int nt = tile % p.num_n_tiles;
+            mbar_wait(&sfull[sb], sb_phase);
+            const __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
+            const int64_t* rowOut = sRowOut + sb * TC_BM;
+            const int64_t* rowM = sRowM + sb * TC_BM;
+            for (int id = st_tid; id < TC_BM * cpr; id += 32 * TC_STORE_WARPS) {
+                const int r = (int)(((uint32_t)id * cpr_magic) >> 22), c8 = id - r * cpr;
+                const int n = nt * p.BN + c8 * 8;
+                int64_t ro = rowOut[r];
+                if (ro < 0 || n >= p.N) continue;
+                int co = n;
+                if (E.map == MSU_MAP_SHUFFLE) {
+                    const int pp = E.geo[2], cc = E.geo[3];
+                    const int q = n / cc, p1 = q / pp, p2 = q - p1 * pp;
+                    ro += (int64_t)p1 * (E.geo[1] * pp) + p2;
+                    co = n - q * cc;
                 }
-            }
-            const bool store_ok = row_ok && row_out >= 0;
-            float rscale = 1.f;
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-            for (int c = half; c < nchunks; c += 2) {
-                float v[16];
-                tc_ld16(t_base + c * 16, v);     // warp-collective: executed by all lanes
-                const int n0 = nt * p.BN + c * 16;
-                if (!store_ok || n0 >= p.N) continue;
-#pragma unroll
-                for (int g8 = 0; g8 < 2; g8++) {
-                    const int n = n0 + g8 * 8;
-                    if (n >= p.N) break;
-                    float* w = v + g8 * 8;
-                    if (E.bias != nullptr) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(E.bias + n);
-                        const float4 b1 = *reinterpret_cast<const float4*>(E.bias + n + 4);
-                        w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
-                        w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
-                    }
-                    int64_t ro = row_out;
-                    int co = n;
-                    if (E.map == MSU_MAP_SHUFFLE) {
-                        const int pp = E.geo[2], cc = E.geo[3];
-                        const int q = n / cc, p1 = q / pp, p2 = q - p1 * pp;
-                        ro = (sh_b * (E.geo[0] * pp) + (sh_h * pp + p1)) * (int64_t)(E.geo[1] * pp) + (sh_w * pp + p2);
-                        co = n - q * cc;
-                    }
-                    const int64_t o = ro * E.ldc + co;
-                    if (Cpre != nullptr) {
-                        uint4 u = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
-                                             pack_bf16x2(w[6], w[7]));
-                        *reinterpret_cast<uint4*>(Cpre + o) = u;
-                    }
-                    if (E.act == 1) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] = gelu_f(w[i]);
-                    }
-                    if (Hp != nullptr) {
-                        float hf[8];
-                        unpack8(*reinterpret_cast<const uint4*>(Hp + m * E.ldh + n), hf);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] *= gelu_grad_f(hf[i]);
-                    }
-                    if (E.rowscale != nullptr) {
-                        rscale = E.rowscale[ro / E.rows_per_sample];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] *= rscale;
-                    }
-                    if (Rp != nullptr) {
-                        float rf[8];
-                        unpack8(*reinterpret_cast<const uint4*>(Rp + ro * E.ldr + co), rf);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] += rf[i];
-                    }
-                    uint4 u = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
-                                         pack_bf16x2(w[6], w[7]));
-                    *reinterpret_cast<uint4*>(Cp + o) = u;
+                const int64_t o = ro * E.ldc + co;
+                const uint4 raw = *reinterpret_cast<const uint4*>(stg + (size_t)r * pitch + c8 * 8);
+                if (Cpre != nullptr) *reinterpret_cast<uint4*>(Cpre + o) = raw;
+                if (passthrough) {
+                    *reinterpret_cast<uint4*>(Cp + o) = raw;
+                    continue;
                 }
+                float w[8];
+                unpack8(raw, w);
+                if (E.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = gelu_fast(w[i]);
+                }
+                if (Hp != nullptr) {
+                    float hf[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Hp + rowM[r] * E.ldh + n), hf);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] *= gelu_grad_fast(hf[i]);
+                }
+                if (E.rowscale != nullptr) {
+                    const float rscale = E.rowscale[ro / E.rows_per_sample];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] *= rscale;
+                }
+                if (Rp != nullptr) {
+                    float rf[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Rp + ro * E.ldr + co), rf);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] += rf[i];
+                }
+                *reinterpret_cast<uint4*>(Cp + o) = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
+                                                               pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
             }
-            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (lane == 0) mbar_arrive(&sempty[sb]);   // staging buffer may be refilled
+            if (++sb == p.nstg) { sb = 0; sb_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -371,12 +437,12 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* ptr, int B, int H, int W,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int pick_bn(int64_t N) {
-    // largest tile <= 256 (multiple of 16) that wastes the least of the last N tile
-    if (N <= 256) return (int)((N + 15) / 16 * 16);
-    int best = 256;
-    int64_t best_waste = (N + 255) / 256 * 256 - N;
-    for (int bn = 256; bn >= 96; bn -= 16) {
+static int pick_bn(int64_t N, int cap = 256) {
+    // largest tile <= cap (multiple of 16) that wastes the least of the last N tile
+    if (N <= cap) return (int)((N + 15) / 16 * 16);
+    int best = cap;
+    int64_t best_waste = (N + cap - 1) / cap * cap - N;
+    for (int bn = cap; bn >= 96; bn -= 16) {
         const int64_t waste = (N + bn - 1) / bn * bn - N;
         if (waste < best_waste) { best = bn; best_waste = waste; }
     }
@@ -404,7 +470,10 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
 
     TcParams p{};
     p.M = M; p.N = (int)N;
-    p.BN = pick_bn(N);
+    // memory-bound shapes: <=192 columns and two staging tiles (drain and store overlap);
+    // compute-bound shapes (long K): 256 columns, one staging tile, deeper operand pipeline
+    p.nstg = (K >= 512 && N >= 256) ? 1 : 2;
+    p.BN = pick_bn(N, p.nstg == 1 ? 256 : 192);
     p.num_n_tiles = (int)((N + p.BN - 1) / p.BN);
     p.E = *E;
     CUtensorMap tmA, tmA2, tmB;
@@ -445,10 +514,11 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
 
     const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
-    p.stages = (200 * 1024) / stage_bytes;
+    const int fixed_bytes = (2 * 8 + 8) * 8 + 16 + 4 * TC_BM * 8 + p.nstg * TC_BM * (p.BN + 8) * 2 + 1024;
+    p.stages = (226 * 1024 - fixed_bytes) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return 1;
-    const int smem = p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+    const int smem = p.stages * stage_bytes + fixed_bytes;
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -824,7 +894,7 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return 1;
     const int base_ctas = p.n_super * p.n_q_tiles;
-    int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
+    int splits = (num_sms() + base_ctas - 1) / base_ctas;
     const int64_t max_splits_t = (T + 511) / 512;
     if (splits > max_splits_t) splits = (int)max_splits_t;
     while (splits > 1 && (int64_t)splits * I * J > ws_elems) splits--;

@@ -253,7 +253,15 @@ __global__ void relbias_expand_kernel(const float* __restrict__ table, float* __
     const int dy = i / WS - j / WS + WS - 1, dx = i % WS - j % WS + WS - 1;
     bias[idx] = table[(dy * (2 * WS - 1) + dx) * nH + h];
 }
-// dtable[t,h] = sum over CTAs, over (i,j) with rel_index(i,j)=t of dbias_partial[cta,h,i,j]; fixed order.
+// part[0][h][e] = sum_c part[c][h][e]  (in place, fixed order; each thread touches only its own column)
+__global__ void relbias_sum_kernel(float* __restrict__ part, int grid, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < grid; c++) s += part[(int64_t)c * n + idx];
+    part[idx] = s;
+}
+// dtable[t,h] = sum over (i,j) with rel_index(i,j)=t of the CTA-summed d(bias)[h,i,j]; fixed order.
 __global__ void relbias_reduce_kernel(const float* __restrict__ part, int grid, int nH, float* __restrict__ dtable,
                                       int accumulate) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,7 +277,7 @@ __global__ void relbias_reduce_kernel(const float* __restrict__ part, int grid, 
             const int xj = xi - dx;
             if (xj < 0 || xj >= WS) continue;
             const int e = (yi * WS + xi) * WT + (yj * WS + xj);
-            for (int c = 0; c < grid; c++) s += part[((int64_t)c * nH + h) * (WT * WT) + e];
+            s += part[(int64_t)h * (WT * WT) + e];   // slot 0 holds the sum over CTAs (relbias_sum_kernel)
         }
     }
     dtable[idx] = accumulate ? dtable[idx] + s : s;
@@ -352,7 +360,9 @@ extern "C" int msu_relbias_reduce(const float* dbias_partial, int32_t grid, int3
                                   void* stream) {
     MSU_REQUIRE(dbias_partial && dtable && grid > 0 && nH > 0, "msu_relbias_reduce: bad arguments");
     const int n = 169 * nH;
+    const int ne = nH * WT * WT;
+    relbias_sum_kernel<<<(ne + 255) / 256, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(dbias_partial), grid, ne);
     relbias_reduce_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dbias_partial, grid, nH, dtable, accumulate);
-    count_launch();
+    count_launch(2);
     return check_launch("msu_relbias_reduce");
 }
