@@ -111,9 +111,11 @@ int msu_ln_param_reduce(const float* partial, int32_t partial_rows, int32_t C, f
  * Replaces TV:models/swin_transformer.py:181-214. */
 int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
                     const int32_t* geo, void* stream);
+/* 0 = auto (tcgen05 kernels for bf16), 1 = force the SIMT fp32-FMA kernels (parity checks of the tensor-core path). */
+int msu_set_attn_backend(int backend);
 /* Backward (recomputes P from qkv; O is the forward output): dqkv [.,3C];
- * dbias_partial fp32 [msu_winattn_bwd_grid(n_windows,nH), nH, 2401], reduced by msu_relbias_reduce. */
-int msu_winattn_bwd_grid(int64_t n_windows, int32_t nH);
+ * dbias_partial fp32 [msu_winattn_bwd_grid(dtype,n_windows,nH), nH, 2401], reduced by msu_relbias_reduce. */
+int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH);
 int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
                     float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, void* stream);
 /* bias[h,i,j] = table[index(i,j), h]  (TV:...:49-56) and its deterministic transpose-reduction. */

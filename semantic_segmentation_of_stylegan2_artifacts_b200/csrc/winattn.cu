@@ -295,7 +295,17 @@ static int attn_grid(int64_t n_windows, int nH) {
 
 }  // namespace msu
 
+namespace msu {
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, cudaStream_t st);
+int winattn_bwd_tc_grid(int64_t n_windows, int nH);
+int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
+                   int nH, const WinGeo& g, cudaStream_t st);
+static int g_attn_backend = 0;  // 0 auto (tcgen05 for bf16), 1 force the SIMT kernels
+}
+
 using namespace msu;
+
+extern "C" int msu_set_attn_backend(int backend) { g_attn_backend = backend; return 0; }
 
 extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
                                const int32_t* geo, void* stream) {
@@ -305,6 +315,10 @@ extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, vo
     WinGeo g = make_wingeo(geo);
     dim3 grid(attn_grid(n_windows, nH), nH);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MSU_BF16 && g_attn_backend == 0) {
+        const int rc = winattn_fwd_tc(qkv, bias, O, n_windows, nH, g, st);
+        if (rc != 1) return rc;
+    }
     if (dtype == MSU_F32) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr = true; }
@@ -320,7 +334,10 @@ extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, vo
     return check_launch("msu_winattn_fwd");
 }
 
-extern "C" int msu_winattn_bwd_grid(int64_t n_windows, int32_t nH) { return attn_grid(n_windows, nH); }
+extern "C" int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH) {
+    if (dtype == MSU_BF16 && g_attn_backend == 0) return 2 * winattn_bwd_tc_grid(n_windows, nH);
+    return attn_grid(n_windows, nH);
+}
 
 // O (the forward output) supplies delta_i = dO_i . O_i without a second P.V product.
 extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
@@ -330,6 +347,11 @@ extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, co
     const int gx = attn_grid(n_windows, nH);
     dim3 grid(gx, nH);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MSU_BF16 && g_attn_backend == 0) {
+        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, st);
+        if (rc != 1) return rc;
+        MSU_REQUIRE(false, "msu_winattn_bwd: tcgen05 path unavailable for these pointers (workspace was sized for it)");
+    }
     if (dtype == MSU_F32) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr = true; }

@@ -1,0 +1,509 @@
+// Shifted-window attention core on tcgen05 (bf16): S = Q K^T and O = P V run on the 5th-gen tensor cores with
+// TMEM accumulators; the softmax (scale, relative-position bias, -100 shift mask, fp32 statistics) runs on
+// the TMEM lanes: one thread owns one query row.  TV:models/swin_transformer.py:181-214.
+//
+// Tiny-tile strategy (49 tokens x head-dim 32): two windows are packed into one M=128 MMA.
+//   MMA 1:  S[128 x 128] = [Q_a; Q_b] [K_a; K_b]^T      (K = 32; the two off-diagonal 64x64 blocks are unused)
+//   softmax per row on its own 64-column block -> P (bf16) written block-diagonally into a 128B-swizzled
+//           K-major tile [128 rows x 128 keys] (off-diagonal blocks stay zero)
+//   MMA 2:  O[128 x 32] = P V, V read MN-major straight from its TMA tile (no transpose)
+// Q/K/V tiles are [64 rows x 32] bf16 TMA boxes (64B swizzle) taken directly from the window-ordered qkv rows
+// (rows 49..63 of a box belong to the next window: finite values that meet exact zeros in P).
+// The Q/K boxes alias the two diagonal blocks of the P tile, so a CTA needs 40 KB of shared memory and
+// 128 TMEM columns: four CTAs per SM overlap each other's TMA / MMA / softmax phases.
+#include "tc_common.cuh"
+
+namespace msu {
+
+constexpr float ATT_SCALE = 0.17677669529663687f;   // 32^-1/2
+constexpr float LOG2E = 1.4426950408889634f;
+
+// K-major, 64B-swizzled descriptor (rows of 32 bf16 = 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+    return d;
+}
+// MN-major, 64B-swizzled descriptor for a [k rows x 32] tile: one 64 B chunk along MN, 8-row k groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // LBO unused: a single MN chunk
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+struct MaskInfoTc { int any, ty, tx; };
+__device__ __forceinline__ MaskInfoTc mask_info_tc(const WinGeo& g, int w) {
+    MaskInfoTc m;
+    const int wy = w / g.nwx(), wx = w % g.nwx();
+    m.ty = (g.sh > 0 && wy == g.Ph / WS - 1) ? WS - g.sh : WS;
+    m.tx = (g.sw > 0 && wx == g.Pw / WS - 1) ? WS - g.sw : WS;
+    m.any = (m.ty < WS) || (m.tx < WS);
+    return m;
+}
+__device__ __forceinline__ int region_tc(const MaskInfoTc& m, int t) {
+    const int a = t / WS, b = t - a * WS;
+    return (a >= m.ty ? 2 : 0) + (b >= m.tx ? 1 : 0);
+}
+
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr int AT_P_BYTES = 32 * 1024;   // P tile: two [128 x 128 B] swizzle atoms
+constexpr int AT_V_BYTES = 8 * 1024;
+constexpr int AT_BIAS_BYTES = 2404 * 4;  // this head's [49,49] bias, pre-multiplied by log2(e)
+constexpr int AT_SMEM = AT_P_BYTES + AT_V_BYTES + AT_BIAS_BYTES + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 4)
+winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ bias, __nv_bfloat16* __restrict__ O,
+                      int64_t n_windows, int nH, WinGeo g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sP = smem;                       // atom 0 = keys 0..63, atom 1 = keys 64..127
+    uint8_t* sQ = smem;                       // aliases P atom 0 rows 0..63   (data block of window a)
+    uint8_t* sK = smem + 24 * 1024;           // aliases P atom 1 rows 64..127 (data block of window b)
+    uint8_t* sV = smem + AT_P_BYTES;
+    float* sBias = reinterpret_cast<float*>(sV + AT_V_BYTES);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sV + AT_V_BYTES + AT_BIAS_BYTES);
+    uint64_t* bar_mma = bar_load + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int C = nH * HD;
+    const int h = blockIdx.y;
+    for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
+
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // the two off-diagonal blocks of P are zero for the whole kernel: [8K, 24K)
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem + 8 * 1024);
+        for (int i = tid; i < 16 * 1024 / 16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int64_t n_pairs = (n_windows + 1) / 2;
+    const int nwin_img = g.nwin();
+    const int half = tid >> 6;             // which window of the pair this row belongs to
+    const int i = tid & 63;                // token index inside the window (valid if < 49)
+    const uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc2 = make_idesc_bf16(128, 32, 0, 1);
+    uint32_t ph_load = 0, ph_mma = 0;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int64_t win = pair * 2 + half;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar_load, 6 * 4096);
+            const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
+            tma_load_2d(sQ, &tm, bar_load, h * HD, r0);
+            tma_load_2d(sQ + 4096, &tm, bar_load, h * HD, r1);
+            tma_load_2d(sK, &tm, bar_load, C + h * HD, r0);
+            tma_load_2d(sK + 4096, &tm, bar_load, C + h * HD, r1);
+            tma_load_2d(sV, &tm, bar_load, 2 * C + h * HD, r0);
+            tma_load_2d(sV + 4096, &tm, bar_load, 2 * C + h * HD, r1);
+            mbar_wait(bar_load, ph_load);
+            tc_fence_after();
+            const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
+            tc_mma_bf16(tmem, qd, kd, idesc1, 0);
+            tc_mma_bf16(tmem, qd + 2, kd + 2, idesc1, 1);   // +32 B: second K=16 slice of the 64 B rows
+            tc_commit(bar_mma);
+        }
+        ph_load ^= 1;
+        // ---- softmax on this thread's row
+        const bool row_ok = (i < WT) && (win < n_windows);
+        const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
+        const int ri = region_tc(mi, i);
+        const float* brow = sBias + i * WT;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        float s[64];
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
+        tc_ld16(trow, s);
+        tc_ld16(trow + 16, s + 16);
+        tc_ld16(trow + 32, s + 32);
+        tc_ld16(trow + 48, s + 48);
+        float inv = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) pk[j] = 0u;
+        if (row_ok) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < WT; j++) {
+                s[j] = fmaf(s[j], ATT_SCALE * LOG2E, brow[j]);    // log2-domain logits
+                if (mi.any && region_tc(mi, j) != ri) s[j] += -100.0f * LOG2E;
+                mx = fmaxf(mx, s[j]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < WT; j += 2) {
+                const float p0 = ex2_fast(s[j] - mx);
+                const float p1 = (j + 1 < WT) ? ex2_fast(s[j + 1] - mx) : 0.f;
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                const float2 back = __bfloat1622float2(b2);      // normalise by what the tensor core will actually sum
+                sum += back.x + back.y;
+            }
+            inv = 1.0f / sum;
+        }
+        // all TMEM reads of S are done before MMA 2 overwrites columns 0..31; all Q/K smem reads (MMA 1) completed
+        // P row -> its diagonal block: atom `half`, row tid, 8 x 16 B chunks, 128B swizzle (chunk ^ (row & 7))
+        {
+            uint8_t* prow = sP + half * 16 * 1024 + tid * 128;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {   // 128 keys = 8 K-steps: 4 per swizzle atom (+32 B each), V advances 16 rows = 1 KB
+                const uint64_t ad = make_desc_kmajor_sw128(pa + (k >> 2) * 16 * 1024 + (k & 3) * 32);
+                const uint64_t bd = make_desc_mnmajor_sw64(va + k * 1024);
+                tc_mma_bf16(tmem, ad, bd, idesc2, k != 0);
+            }
+            tc_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        float o[32];
+        const uint32_t orow = tmem + ((uint32_t)(warp * 32) << 16);
+        tc_ld16(orow, o);
+        tc_ld16(orow + 16, o + 16);
+        if (row_ok) {
+            __nv_bfloat16* dst = O + (win * WT + i) * (int64_t)C + h * HD;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint4 v;
+                v.x = pk2(o[8 * c] * inv, o[8 * c + 1] * inv);
+                v.y = pk2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+                v.z = pk2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+                v.w = pk2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+                *reinterpret_cast<uint4*>(dst + 8 * c) = v;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // TMEM columns and the Q/K/V/P tiles are free for the next unit
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    }
+}
+
+// returns 0 launched, 1 unsupported
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, cudaStream_t st) {
+    if (tc_get_encode() == nullptr) return 1;
+    const int C = nH * HD;
+    if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15)) return 1;
+    const int64_t rows = n_windows * WT;
+    CUtensorMap tm;
+    cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
+    cuuint32_t box[2] = {32, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (tc_get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(winattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+        if (e != cudaSuccess) { set_error("winattn_fwd_tc: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    const int64_t pairs = (n_windows + 1) / 2;
+    const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 4 + nH - 1) / nH));
+    dim3 grid(gx, nH);
+    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, bias, reinterpret_cast<__nv_bfloat16*>(O), n_windows, nH, g);
+    count_launch();
+    return check_launch("winattn_fwd_tc");
+}
+
+// ================================================================================================
+// Backward on tcgen05.  Per unit (two windows x one head), P is recomputed (nothing of size 49x49 is saved):
+//   MMA a: S  = [Q_a;Q_b] [K_a;K_b]^T            -> TMEM cols [0,128)
+//   MMA b: dP = [dO_a;dO_b] [V_a;V_b]^T          -> TMEM cols [128,256)
+//   rows : P = softmax(S*s + bias + mask), delta = sum_j P dP, dS = P (dP - delta), d(bias) += dS (registers)
+//          P and dS rows (bf16) go to two compact [128 rows x 64 own-window keys] 128B-swizzled tiles
+//   MMA c/d: dV_w = P_w^T dO_w, dK_w = dS_w^T Q_w (A read MN-major from the same tiles, contraction over the 64
+//            rows of window w; key-indexed results land in TMEM lanes 0..63 for both windows)
+//   MMA e:   dQ_w = dS K_w (A = all 128 rows K-major; lanes of the other window hold unused values)
+// dQ and dK are scaled by 32^-1/2 in the epilogue (S = s Q K^T).  d(bias) partial sums stay in registers over
+// all units of the CTA and are written once: partial[2*blockIdx.x + half][h][49*49] (fixed order => deterministic).
+// ================================================================================================
+constexpr int AB_TILE = 8 * 1024;          // one [128 x 32] bf16 operand tile (two 64-row boxes)
+constexpr int AB_X = 16 * 1024;            // one [128 x 64] bf16 P / dS tile
+// + one spare tile: the M=128 MN-major A descriptors of dV / dK read a second 64-key chunk `AB_X` bytes after the
+// real one (its products land in TMEM lanes 64..127, which nobody reads) and must stay inside the allocation.
+constexpr int AB_SMEM = 4 * AB_TILE + 3 * AB_X + AT_BIAS_BYTES + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_partial,
+                      int64_t n_windows, int nH, WinGeo g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + AB_TILE;
+    uint8_t* sV = sK + AB_TILE;
+    uint8_t* sD = sV + AB_TILE;                 // dO
+    uint8_t* sXP = sD + AB_TILE;                // P rows
+    uint8_t* sXS = sXP + AB_X;                  // dS rows
+    float* sBias = reinterpret_cast<float*>(sXS + 2 * AB_X);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);
+    uint64_t* bar_mma = bar_load + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int C = nH * HD;
+    const int h = blockIdx.y;
+    for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int64_t n_pairs = (n_windows + 1) / 2;
+    const int nwin_img = g.nwin();
+    const int half = tid >> 6, i = tid & 63;
+    const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
+    const uint32_t id_kv = make_idesc_bf16(128, 32, 1, 1);     // dV, dK: A MN-major, B MN-major
+    const uint32_t id_q = make_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
+    uint32_t ph_load = 0, ph_mma = 0;
+    float acc[WT];
+#pragma unroll
+    for (int j = 0; j < WT; j++) acc[j] = 0.f;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int64_t win = pair * 2 + half;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar_load, 8 * 4096);
+            const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
+            tma_load_2d(sQ, &tmQKV, bar_load, h * HD, r0);
+            tma_load_2d(sQ + 4096, &tmQKV, bar_load, h * HD, r1);
+            tma_load_2d(sK, &tmQKV, bar_load, C + h * HD, r0);
+            tma_load_2d(sK + 4096, &tmQKV, bar_load, C + h * HD, r1);
+            tma_load_2d(sV, &tmQKV, bar_load, 2 * C + h * HD, r0);
+            tma_load_2d(sV + 4096, &tmQKV, bar_load, 2 * C + h * HD, r1);
+            tma_load_2d(sD, &tmDO, bar_load, h * HD, r0);
+            tma_load_2d(sD + 4096, &tmDO, bar_load, h * HD, r1);
+            mbar_wait(bar_load, ph_load);
+            tc_fence_after();
+            const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
+            const uint64_t vd = make_desc_kmajor_sw64(smem_u32(sV)), dd = make_desc_kmajor_sw64(smem_u32(sD));
+            tc_mma_bf16(tmem, qd, kd, id_s, 0);
+            tc_mma_bf16(tmem, qd + 2, kd + 2, id_s, 1);
+            tc_mma_bf16(tmem + 128, dd, vd, id_s, 0);
+            tc_mma_bf16(tmem + 128, dd + 2, vd + 2, id_s, 1);
+            tc_commit(bar_mma);
+        }
+        ph_load ^= 1;
+        const bool row_ok = (i < WT) && (win < n_windows);
+        const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
+        const int ri = region_tc(mi, i);
+        const float* brow = sBias + i * WT;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        uint32_t pk[32], dk_[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) { pk[j] = 0u; dk_[j] = 0u; }
+        {
+            float s[64], dp[64];
+            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
+            tc_ld16(trow, s); tc_ld16(trow + 16, s + 16); tc_ld16(trow + 32, s + 32); tc_ld16(trow + 48, s + 48);
+            tc_ld16(trow + 128, dp); tc_ld16(trow + 144, dp + 16); tc_ld16(trow + 160, dp + 32); tc_ld16(trow + 176, dp + 48);
+            if (row_ok) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < WT; j++) {
+                    s[j] = fmaf(s[j], ATT_SCALE * LOG2E, brow[j]);
+                    if (mi.any && region_tc(mi, j) != ri) s[j] += -100.0f * LOG2E;
+                    mx = fmaxf(mx, s[j]);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < WT; j++) { s[j] = ex2_fast(s[j] - mx); sum += s[j]; }
+                const float inv = 1.0f / sum;
+                float delta = 0.f;
+#pragma unroll
+                for (int j = 0; j < WT; j++) { s[j] *= inv; delta = fmaf(s[j], dp[j], delta); }
+#pragma unroll
+                for (int j = 0; j < WT; j++) {
+                    dp[j] = s[j] * (dp[j] - delta);   // dS
+                    acc[j] += dp[j];
+                }
+#pragma unroll
+                for (int j = 0; j < WT; j += 2) {
+                    pk[j >> 1] = pk2(s[j], (j + 1 < WT) ? s[j + 1] : 0.f);
+                    dk_[j >> 1] = pk2(dp[j], (j + 1 < WT) ? dp[j + 1] : 0.f);
+                }
+            }
+        }
+        {   // row tid of both compact tiles (zeros for padding rows: they are contracted over in dV / dK)
+            uint8_t* prow = sXP + tid * 128;
+            uint8_t* srow = sXS + tid * 128;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int sw = (c ^ (tid & 7)) << 4;
+                *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                *reinterpret_cast<uint4*>(srow + sw) = make_uint4(dk_[4 * c], dk_[4 * c + 1], dk_[4 * c + 2], dk_[4 * c + 3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t xp = smem_u32(sXP), xs = smem_u32(sXS);
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sD);
+            for (int w = 0; w < 2; w++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {   // contraction over the 64 rows of window w, 16 rows (2 KB of X, 1 KB of B) per step
+                    const uint64_t ap = make_desc_mnmajor_sw128(xp + w * 8192 + k * 2048, AB_X);
+                    const uint64_t as = make_desc_mnmajor_sw128(xs + w * 8192 + k * 2048, AB_X);
+                    tc_mma_bf16(tmem + w * 32, ap, make_desc_mnmajor_sw64(da + w * 4096 + k * 1024), id_kv, k != 0);       // dV_w
+                    tc_mma_bf16(tmem + 64 + w * 32, as, make_desc_mnmajor_sw64(qa + w * 4096 + k * 1024), id_kv, k != 0);  // dK_w
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {   // contraction over the 64 keys of window w: +32 B per step inside the 128 B rows
+                    const uint64_t as = make_desc_kmajor_sw128(xs + k * 32);
+                    tc_mma_bf16(tmem + 128 + w * 32, as, make_desc_mnmajor_sw64(ka + w * 4096 + k * 1024), id_q, k != 0);  // dQ_w
+                }
+            }
+            tc_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        {
+            float o[32];
+            const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+            // dQ: own row
+            tc_ld16(lane_base + 128 + half * 32, o);
+            tc_ld16(lane_base + 128 + half * 32 + 16, o + 16);
+            if (row_ok) {
+                __nv_bfloat16* dst = dqkv + (win * WT + i) * (int64_t)(3 * C) + h * HD;
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pk2(o[8 * c] * ATT_SCALE, o[8 * c + 1] * ATT_SCALE),
+                        pk2(o[8 * c + 2] * ATT_SCALE, o[8 * c + 3] * ATT_SCALE), pk2(o[8 * c + 4] * ATT_SCALE, o[8 * c + 5] * ATT_SCALE),
+                        pk2(o[8 * c + 6] * ATT_SCALE, o[8 * c + 7] * ATT_SCALE));
+            }
+            // dK / dV: key-indexed results of BOTH windows live in lanes 0..63 -> warps 0,1 store them
+            if (warp < 2) {
+                for (int w = 0; w < 2; w++) {
+                    const int64_t wn = pair * 2 + w;
+                    const bool ok = (i < WT) && (wn < n_windows);
+                    __nv_bfloat16* dst = dqkv + (wn * WT + i) * (int64_t)(3 * C) + h * HD;
+                    tc_ld16(lane_base + 64 + w * 32, o);
+                    tc_ld16(lane_base + 64 + w * 32 + 16, o + 16);
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4*>(dst + C + 8 * c) = make_uint4(pk2(o[8 * c] * ATT_SCALE, o[8 * c + 1] * ATT_SCALE),
+                                pk2(o[8 * c + 2] * ATT_SCALE, o[8 * c + 3] * ATT_SCALE), pk2(o[8 * c + 4] * ATT_SCALE, o[8 * c + 5] * ATT_SCALE),
+                                pk2(o[8 * c + 6] * ATT_SCALE, o[8 * c + 7] * ATT_SCALE));
+                    }
+                    tc_ld16(lane_base + w * 32, o);
+                    tc_ld16(lane_base + w * 32 + 16, o + 16);
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4*>(dst + 2 * C + 8 * c) = make_uint4(pk2(o[8 * c], o[8 * c + 1]), pk2(o[8 * c + 2], o[8 * c + 3]),
+                                pk2(o[8 * c + 4], o[8 * c + 5]), pk2(o[8 * c + 6], o[8 * c + 7]));
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i
+    if (i < WT) {
+        float* out = dbias_partial + (((int64_t)blockIdx.x * 2 + half) * nH + h) * (WT * WT) + i * WT;
+#pragma unroll
+        for (int j = 0; j < WT; j++) out[j] = acc[j];
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    }
+}
+
+static bool make_attn_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {32, 64};
+    cuuint32_t estr[2] = {1, 1};
+    return tc_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
+    const int64_t pairs = (n_windows + 1) / 2;
+    return (int)imax(1, imin(pairs, ((int64_t)num_sms() * 2 + nH - 1) / nH));
+}
+
+// returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
+int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
+                   int nH, const WinGeo& g, cudaStream_t st) {
+    if (tc_get_encode() == nullptr) return 1;
+    const int C = nH * HD;
+    if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15)) return 1;
+    CUtensorMap tmQKV, tmDO;
+    if (!make_attn_map(&tmQKV, qkv, n_windows * WT, 3 * C) || !make_attn_map(&tmDO, dO, n_windows * WT, C)) return 1;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(winattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e != cudaSuccess) { set_error("winattn_bwd_tc: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    dim3 grid(winattn_bwd_tc_grid(n_windows, nH), nH);
+    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, bias, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_partial,
+                                                    n_windows, nH, g);
+    count_launch();
+    return check_launch("winattn_bwd_tc");
+}
+
+}  // namespace msu

@@ -163,7 +163,7 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
     """Returns (dqkv, dtable[169, nH])."""
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
-    gx = L.lib().msu_winattn_bwd_grid(n_windows, nH)
+    gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
     part = torch.empty(gx * nH * 2401, dtype=torch.float32, device=dev)
     g = L.geo6(geo)
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),

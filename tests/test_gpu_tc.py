@@ -209,6 +209,93 @@ def test_wgrad_into_column_slice(ops):
     assert relmax(tc, ref) < 2e-5 and relmax(tc, simt) < 2e-5
 
 
+@pytest.mark.parametrize("geom", [(2, 14, 14, 3, 1), (3, 16, 16, 3, 2), (1, 16, 16, 0, 3), (5, 7, 7, 3, 1), (2, 35, 35, 3, 12),
+                                  (1, 10, 12, 3, 6), (16, 21, 21, 3, 24)])
+def test_window_attention_fwd_tcgen05(ops, geom):
+    """tcgen05 attention core (two windows per M=128 MMA, P staged block-diagonally) vs the fp32-FMA kernel and
+    vs an fp64 softmax(QK^T*s + bias + mask) V on the same bf16 inputs."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    from semantic_segmentation_of_stylegan2_artifacts_b200.functional import window_geo
+    B, H, W, shift, nH = geom
+    C = nH * 32
+    geo = window_geo(H, W, shift)
+    nW = (geo[2] // 7) * (geo[3] // 7)
+    nwin = B * nW
+    torch.manual_seed(H * 13 + nH)
+    qkv = (torch.randn(nwin * 49, 3 * C) * 1.5).bfloat16().to(DEV)
+    table = (torch.randn(169, nH) * 0.5).to(DEV)
+    bias = ops.relbias_expand(table, nH)
+    lib = _lib.lib()
+    lib.msu_set_attn_backend(0)
+    o_tc = ops.winattn_fwd(qkv, bias, nwin, nH, geo).float().cpu()
+    lib.msu_set_attn_backend(1)
+    o_simt = ops.winattn_fwd(qkv, bias, nwin, nH, geo).float().cpu()
+    lib.msu_set_attn_backend(0)
+    # fp64 reference with the mask rebuilt from the geometry (oracle.window_geometry)
+    from oracle import msunet_oracle as O
+    _, _, sh, sw, _, region = O.window_geometry(H, W, shift)
+    x = qkv.double().cpu().view(B, nW, 49, 3, nH, 32).permute(3, 0, 1, 4, 2, 5)
+    q, k, v = x[0] * 32 ** -0.5, x[1], x[2]
+    att = q @ k.transpose(-1, -2) + bias.double().cpu()[None, None]
+    if sh + sw > 0:
+        reg = region.view(nW, 49)
+        att = att + torch.where(reg[:, :, None] != reg[:, None, :], -100.0, 0.0).double()[None, :, None]
+    ref = (att.softmax(-1) @ v).permute(0, 1, 3, 2, 4).reshape(nwin * 49, C)
+    assert relmax(o_simt, ref) < 1.2e-2
+    assert relmax(o_tc, ref) < 1.5e-2
+    assert float((o_tc.double() - ref).norm() / ref.norm()) < 6e-3
+
+
+@pytest.mark.parametrize("geom", [(2, 14, 14, 3, 1), (3, 16, 16, 3, 2), (1, 16, 16, 0, 3), (5, 7, 7, 3, 1), (2, 35, 35, 3, 12),
+                                  (1, 10, 12, 3, 6), (16, 21, 21, 3, 24)])
+def test_window_attention_bwd_tcgen05(ops, geom):
+    """tcgen05 attention backward (5 tensor-core products, P recomputed) vs autograd through an fp64 reference."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    from semantic_segmentation_of_stylegan2_artifacts_b200.functional import window_geo
+    from oracle import msunet_oracle as O
+    B, H, W, shift, nH = geom
+    C = nH * 32
+    geo = window_geo(H, W, shift)
+    nW = (geo[2] // 7) * (geo[3] // 7)
+    nwin = B * nW
+    torch.manual_seed(H * 17 + nH)
+    qkv = (torch.randn(nwin * 49, 3 * C) * 1.2).bfloat16().to(DEV)
+    do = torch.randn(nwin * 49, C).bfloat16().to(DEV)
+    table = (torch.randn(169, nH) * 0.5).to(DEV)
+    bias = ops.relbias_expand(table, nH)
+    lib = _lib.lib()
+    res = {}
+    for name, be in (("tc", 0), ("simt", 1)):
+        lib.msu_set_attn_backend(be)
+        o = ops.winattn_fwd(qkv, bias, nwin, nH, geo)
+        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, nwin, nH, geo)
+        res[name] = (dqkv.float().cpu(), dtable.cpu())
+    lib.msu_set_attn_backend(0)
+    dq2, dt2 = ops.winattn_bwd(qkv, bias, ops.winattn_fwd(qkv, bias, nwin, nH, geo), do, nwin, nH, geo)
+    assert torch.equal(dt2.cpu(), res["tc"][1]) and torch.equal(dq2.float().cpu(), res["tc"][0])   # deterministic
+    # fp64 autograd reference
+    _, _, sh, sw, _, region = O.window_geometry(H, W, shift)
+    x = qkv.double().cpu().requires_grad_(True)
+    tb = table.double().cpu().requires_grad_(True)
+    xx = x.view(B, nW, 49, 3, nH, 32).permute(3, 0, 1, 4, 2, 5)
+    q, k, v = xx[0] * 32 ** -0.5, xx[1], xx[2]
+    bexp = tb[O.relative_position_index()].view(49, 49, nH).permute(2, 0, 1)
+    att = q @ k.transpose(-1, -2) + bexp[None, None]
+    if sh + sw > 0:
+        reg = region.view(nW, 49)
+        att = att + torch.where(reg[:, :, None] != reg[:, None, :], -100.0, 0.0).double()[None, :, None]
+    out = (att.softmax(-1) @ v).permute(0, 1, 3, 2, 4).reshape(nwin * 49, C)
+    out.backward(do.double().cpu())
+
+    def rl2(a, b):
+        return float((a.double() - b).norm() / b.norm())
+
+    assert rl2(res["simt"][0], x.grad) < 6e-3 and rl2(res["simt"][1], tb.grad) < 2e-3
+    assert rl2(res["tc"][0], x.grad) < 1.2e-2, rl2(res["tc"][0], x.grad)
+    assert rl2(res["tc"][1], tb.grad) < 6e-3, rl2(res["tc"][1], tb.grad)
+    assert relmax(res["tc"][0], x.grad) < 4e-2
+
+
 def test_gelu_grad_epilogue(ops):
     torch.manual_seed(9)
     M, N, K = 900, 384, 96
