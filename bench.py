@@ -156,7 +156,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     W = max(3, args.warmup)
     B, S = args.batch, args.img
 
@@ -268,10 +269,10 @@ def main():
 
     # ---------------- roofline of the dominant kernel, timed live with CUDA events on the launch stream
     roof = None
+    ops.PROF = [] if rank == 0 else None
+    step(x_d, y_d)          # every rank runs it (the step contains collectives); only rank 0 records events
+    barrier()
     if rank == 0:
-        ops.PROF = []
-        step(x_d, y_d)
-        torch.cuda.synchronize()
         agg = {}
         for tag, a, b in ops.PROF:
             d = agg.setdefault(tag, [0.0, 0])

@@ -109,3 +109,17 @@ def test_encoder_key_remap():
     assert _remap("features.6.reduction.weight", "features.") == "layers.2.downsample.reduction.weight"
     assert _remap("features.7.0.norm1.weight", "features.") == "layers.3.blocks.0.norm1.weight"
     assert _remap("features.9.x", "features.") is None
+
+
+def test_dropin_overlay_resolves_reference_imports(built):
+    """With dropin/ ahead on PYTHONPATH the reference's own import lines (train.py:10, trainer.py:27,29) bind to this repo."""
+    import subprocess
+    import sys
+    code = ("from network.MSUNet import MSUNet; from loss.DynamicLoss import DynamicLoss; "
+            "from scripts.validation_functions import calculate_metrics, validation_loss; "
+            "import network.model_parts as mp; "
+            "print(MSUNet.__module__, DynamicLoss.__module__, calculate_metrics.__module__, mp.MSUNetSys.__module__)")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, PKG, "dropin"), ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert all(m.startswith(PKG + ".") for m in out.stdout.split()), out.stdout
