@@ -330,7 +330,16 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:
-        dist.destroy_process_group()
+        # tear down without ever hanging the launcher: captured graphs hold NCCL work, so give the orderly
+        # shutdown a few seconds and then leave
+        sys.stdout.flush()
+        threading.Timer(8.0, lambda: os._exit(0)).start()
+        try:
+            barrier()
+            del graph
+            dist.destroy_process_group()
+        finally:
+            os._exit(0)
 
 
 if __name__ == "__main__":

@@ -40,6 +40,9 @@ extern "C" {
 #define MSU_MAP_MERGE 4    /* 2x2 neighbourhood concat: logical [(b,h/2,w/2), (q c)] -> memory [(b,2h'+q%2,2w'+q/2), c]; \
                               geo = {H, W, C}. network/model_parts.py:87-92                                  */
 
+#define MSU_MAP_UNSHUFFLE 5 /* inverse depth-to-space (backward of MSU_MAP_SHUFFLE): logical [(b,h*p+p1,w*p+p2), c] ->      \
+                              memory [token(b,h,w), (p1 p2 c)]; geo = {H, W, p, c}                                 */
+
 typedef struct {
     const void* ptr;        /* base pointer                                                              */
     const void* ptr2;       /* second source for logical columns >= k_split (skip concat), or NULL       */
@@ -64,7 +67,7 @@ typedef struct {
     const float* rowscale;  /* per-sample scale of the branch before the residual add                     */
     int32_t rows_per_sample;
     int32_t act;            /* 0 none, 1 exact (erf) GELU                                                  */
-    int32_t map;            /* MSU_MAP_NONE / WINDOW / SHUFFLE on the output                              */
+    int32_t map;            /* MSU_MAP_NONE / WINDOW / SHUFFLE / UNSHUFFLE on the output                  */
     int32_t dtype;          /* dtype of C, Cpre, R, H                                                     */
     int32_t geo[6];
     int32_t out_f32;        /* 1: C is fp32 regardless of dtype (weight gradients)                        */
@@ -94,10 +97,10 @@ int msu_ln_fwd(int dtype, const void* X, const float* gamma, const float* beta, 
                const float* dotw, void* stream);
 
 /* LayerNorm backward.  dY is read through `dy_map` (NONE, or WINDOW: gradient rows live in window order),
- * dX written through `dx_map` (NONE or MERGE scatter).  dX = LN'(dY) + dRes (dRes optional).
- * partial: fp32 workspace [msu_ln_bwd_partial_rows(rows,C), 3, C] for deterministic dgamma/dbeta/(ddotw) reduction, finished by
+ * dX written through `dx_map` (NONE, MERGE scatter, or UNSHUFFLE: inverse depth-to-space).  dX = LN'(dY) + dRes (dRes optional).
+ * partial: fp32 workspace [msu_ln_bwd_partial_rows(dtype,rows,C), 3, C] for deterministic dgamma/dbeta/(ddotw) reduction, finished by
  * msu_ln_param_reduce.  If dotw != NULL, dY is a per-row scalar (d logits) times dotw. */
-int msu_ln_bwd_partial_rows(int64_t rows, int32_t C);
+int msu_ln_bwd_partial_rows(int dtype, int64_t rows, int32_t C);
 int msu_ln_bwd(int dtype, const void* dY, const void* X, const float* gamma, const float* beta,
                const float* mean, const float* rstd, const void* dRes, void* dX, int64_t rows, int32_t C,
                int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsunet_sm100.so")
 
 F32, BF16, F16 = 0, 1, 2
-MAP_NONE, MAP_WINDOW, MAP_SHUFFLE, MAP_CONV3, MAP_MERGE = 0, 1, 2, 3, 4
+MAP_NONE, MAP_WINDOW, MAP_SHUFFLE, MAP_CONV3, MAP_MERGE, MAP_UNSHUFFLE = 0, 1, 2, 3, 4, 5
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -50,7 +50,7 @@ _SIGS = {
                  C.c_int, _P],
     "msu_colsum": [C.POINTER(MsuOperand), _I64, _I64, _P, C.c_int, _P, _I64, _P],
     "msu_ln_fwd": [C.c_int, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
-    "msu_ln_bwd_partial_rows": [_I64, _I32],
+    "msu_ln_bwd_partial_rows": [C.c_int, _I64, _I32],
     "msu_ln_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
     "msu_ln_param_reduce": [_P, _I32, _I32, _P, _P, _P, C.c_int, _P],
     "msu_winattn_fwd": [C.c_int, _P, _P, _P, _I64, _I32, _P, _P],

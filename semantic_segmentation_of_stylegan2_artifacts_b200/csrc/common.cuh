@@ -143,6 +143,15 @@ __device__ __forceinline__ RowCol map_rc(int map, const int32_t* geo, int64_t r,
             const int h = t / W, w = t - h * W;
             return RowCol{(b * (H * p) + (h * p + p1)) * (int64_t)(W * p) + (w * p + p2), c - q * cc};
         }
+        case MSU_MAP_UNSHUFFLE: {  // geo = {H, W, p, cc}: r walks the shuffled map [(b, h*p+p1, w*p+p2)]
+            const int H = geo[0], W = geo[1], p = geo[2], cc = geo[3];
+            const int Wp = W * p, HWp = H * p * Wp;
+            const int64_t b = r / HWp;
+            const int t = (int)(r - b * HWp);
+            const int y = t / Wp, x = t - y * Wp;
+            const int h = y / p, p1 = y - h * p, w = x / p, p2 = x - w * p;
+            return RowCol{(b * H + h) * (int64_t)W + w, (p1 * p + p2) * cc + c};
+        }
         case MSU_MAP_CONV3: {  // geo = {H, W, C}
             const int H = geo[0], W = geo[1], C = geo[2];
             const int tap = c / C, ci = c - tap * C;

@@ -223,12 +223,21 @@ __global__ void __launch_bounds__(256) colsum_dense_kernel(const T* __restrict__
     }
 }
 
-__global__ void colsum_final_kernel(const float* ws, int parts, int64_t N, float* out, int accumulate) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// out[n] = sum_p ws[p][n]: 32 columns x 8 partial-row lanes per block, fixed-order combine (deterministic)
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* ws, int parts, int64_t N, float* out, int accumulate) {
+    __shared__ float sm[8][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int p = 0; p < parts; p++) s += ws[(int64_t)p * N + n];
-    out[n] = accumulate ? out[n] + s : s;
+    if (n < N)
+        for (int p = threadIdx.y; p < parts; p += 8) s += ws[(int64_t)p * N + n];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += sm[i][threadIdx.x];
+        out[n] = accumulate ? out[n] + t : t;
+    }
 }
 
 }  // namespace msu
@@ -249,7 +258,7 @@ extern "C" int msu_colsum(const MsuOperand* X, int64_t M, int64_t N, float* out,
         dim3 grid((unsigned)((N / 4 + 31) / 32), (unsigned)parts), block(32, 8);
         if (X->dtype == MSU_F32) colsum_dense_kernel<float><<<grid, block, 0, st>>>((const float*)X->ptr, M, (int)N, X->ld, rpb, ws);
         else colsum_dense_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)X->ptr, M, (int)N, X->ld, rpb, ws);
-        colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ws, parts, N, out, accumulate);
+        colsum_final_kernel<<<(unsigned)((N + 31) / 32), dim3(32, 8), 0, st>>>(ws, parts, N, out, accumulate);
         count_launch(2);
         return check_launch("msu_colsum");
     }
@@ -260,7 +269,7 @@ extern "C" int msu_colsum(const MsuOperand* X, int64_t M, int64_t N, float* out,
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)parts);
     colsum_partial_kernel<<<grid, 128, 0, st>>>(*X, M, N, rpb, ws);
-    colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ws, parts, N, out, accumulate);
+    colsum_final_kernel<<<(unsigned)((N + 31) / 32), dim3(32, 8), 0, st>>>(ws, parts, N, out, accumulate);
     count_launch(2);
     return check_launch("msu_colsum");
 }

@@ -93,7 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
     int64_t* sRowOut = reinterpret_cast<int64_t*>(tmem_slot + 4);   // [2][128] mapped output row of each tile row (-1: skip)
     int64_t* sRowM = sRowOut + 2 * TC_BM;                           // [2][128] logical row m of each tile row
-    __nv_bfloat16* sStage = reinterpret_cast<__nv_bfloat16*>(sRowM + 2 * TC_BM);  // [2][128][BN + 8] bf16 output staging
+    int32_t* sColOff = reinterpret_cast<int32_t*>(sRowM + 2 * TC_BM);  // [2][128] column offset of the row (UNSHUFFLE map)
+    __nv_bfloat16* sStage = reinterpret_cast<__nv_bfloat16*>(sColOff + 2 * TC_BM);  // [2][128][BN + 8] bf16 output staging
     const int pitch = p.BN + 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,9 +202,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     m = (int64_t)mt * TC_BM + rl;
                 }
                 int64_t ro = -1;
+                int coff = 0;
                 if (m < p.M) {
                     if (E.map == MSU_MAP_WINDOW) {
                         ro = win_to_pix(make_wingeo(E.geo), m);
+                    } else if (E.map == MSU_MAP_UNSHUFFLE) {
+                        const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, E.geo, m, 0);
+                        ro = rc.row;
+                        coff = rc.col;
                     } else if (E.map == MSU_MAP_SHUFFLE) {   // base row; (p1, p2) offsets are added per column chunk
                         const int hw = E.geo[0] * E.geo[1], pp = E.geo[2];
                         const int64_t b = m / hw;
@@ -216,6 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 sRowOut[sb * TC_BM + rl] = ro;
                 sRowM[sb * TC_BM + rl] = m;
+                sColOff[sb * TC_BM + rl] = coff;
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -264,12 +271,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
             const int64_t* rowOut = sRowOut + sb * TC_BM;
             const int64_t* rowM = sRowM + sb * TC_BM;
+            const int32_t* colOff = sColOff + sb * TC_BM;
             for (int id = st_tid; id < TC_BM * cpr; id += 32 * TC_STORE_WARPS) {
                 const int r = (int)(((uint32_t)id * cpr_magic) >> 22), c8 = id - r * cpr;
                 const int n = nt * p.BN + c8 * 8;
                 int64_t ro = rowOut[r];
                 if (ro < 0 || n >= p.N) continue;
-                int co = n;
+                int co = n + colOff[r];
                 if (E.map == MSU_MAP_SHUFFLE) {
                     const int pp = E.geo[2], cc = E.geo[3];
                     const int q = n / cc, p1 = q / pp, p2 = q - p1 * pp;
@@ -385,9 +393,9 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (A->orient != 0 || B->orient != 0 || B->map != MSU_MAP_NONE || B->ptr2 != nullptr) return 1;
     if (A->rowscale != nullptr || B->rowscale != nullptr) return 1;
     if (!(A->map == MSU_MAP_NONE || A->map == MSU_MAP_CONV3)) return 1;
-    if (!(E->map == MSU_MAP_NONE || E->map == MSU_MAP_WINDOW || E->map == MSU_MAP_SHUFFLE)) return 1;
+    if (!(E->map == MSU_MAP_NONE || E->map == MSU_MAP_WINDOW || E->map == MSU_MAP_SHUFFLE || E->map == MSU_MAP_UNSHUFFLE)) return 1;
     if (N % 8 != 0 || (E->ldc % 8) != 0 || (E->R && E->ldr % 8 != 0) || (E->H && E->ldh % 8 != 0)) return 1;
-    if (E->map == MSU_MAP_SHUFFLE && E->geo[3] % 8 != 0) return 1;
+    if ((E->map == MSU_MAP_SHUFFLE || E->map == MSU_MAP_UNSHUFFLE) && E->geo[3] % 8 != 0) return 1;
     if ((A->ld % 8) != 0 || (B->ld % 8) != 0 || !aligned16(A->ptr) || !aligned16(B->ptr) || !aligned16(E->C)) return 1;
     if ((E->Cpre && !aligned16(E->Cpre)) || (E->R && !aligned16(E->R)) || (E->H && !aligned16(E->H))) return 1;
     if (E->bias && !aligned16(E->bias)) return 1;
@@ -440,7 +448,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
 
     const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
-    const int fixed_bytes = (2 * 8 + 8) * 8 + 16 + 4 * TC_BM * 8 + p.nstg * TC_BM * (p.BN + 8) * 2 + 1024;
+    const int fixed_bytes = (2 * 8 + 8) * 8 + 16 + 4 * TC_BM * 8 + 2 * TC_BM * 4 + p.nstg * TC_BM * (p.BN + 8) * 2 + 1024;
     p.stages = (226 * 1024 - fixed_bytes) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return 1;
@@ -796,11 +804,20 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     const MsuOperand* Q = p.swap ? A : B;
     p.Pn = p.swap ? (int)J : (int)I;
     p.Qn = p.swap ? (int)I : (int)J;
-    p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn);
+    const int m_tiles = (p.Pn + 127) / 128;
+    // Long token axis (stage 0/1): activation reads dominate -> wide N tile and several M accumulators per CTA so
+    // that each activation element is fetched once.  Short token axis with a large output (stage 2/3): many
+    // output tiles, few splits -> small deterministic split-K partial traffic.
+    const bool out_heavy = (int64_t)I * J * 8 > T * (I + J);
+    if (out_heavy) {
+        p.BN = p.Qn <= 128 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 128);
+        p.MT = 1;
+    } else {
+        p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn);
+        p.MT = m_tiles < 4 ? m_tiles : 4;
+    }
     p.n_q_tiles = (p.Qn + p.BN - 1) / p.BN;
     p.qboxes = (p.BN + 63) / 64;
-    const int m_tiles = (p.Pn + 127) / 128;
-    p.MT = m_tiles < 4 ? m_tiles : 4;
     while (p.MT > 1 && p.MT * p.BN > TC_TMEM_COLS) p.MT--;
     // keep at least 2 pipeline stages in 200 KB
     while (p.MT > 1 && 2 * (p.MT * 2 + p.qboxes) * WG_BOX_BYTES > 200 * 1024) p.MT--;

@@ -15,6 +15,44 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
     return v;
 }
 
+// 16-byte vectors: 4 floats or 8 bf16
+template <typename T> struct VecW;
+template <> struct VecW<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void ld(const float* p, float* o) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* o) {
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+};
+template <> struct VecW<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+        const uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 f = __bfloat1622float2(h[i]);
+            o[2 * i] = f.x; o[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* o) {
+        uint4 r;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = r;
+    }
+};
+__device__ __forceinline__ void ldf(const float* p, float* o, int n) {
+    for (int i = 0; i < n; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        o[i] = v.x; o[i + 1] = v.y; o[i + 2] = v.z; o[i + 3] = v.w;
+    }
+}
+
 struct MergeGeo { int H, W; };
 // source offset (in elements) of logical column c of LayerNorm row lr when the row is a 2x2 neighbourhood concat
 __device__ __forceinline__ int64_t merge_off(const MergeGeo& mg, int64_t lr, int c, int Cin) {
@@ -43,27 +81,30 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restri
         pad = lr < 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
     }
     const bool live = in_range && !pad;
+    constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
-    float4 x[NV];
+    float x[NV][VW];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * 4;
-        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = (l + lpr * j) * VW;
+#pragma unroll
+        for (int e = 0; e < VW; e++) x[j][e] = 0.f;
         if (live && c < C) {
             const T* p = (in_map == MSU_MAP_MERGE) ? X + merge_off(mg, lr, c, Cin) : X + lr * C + c;
-            x[j] = Vec4<T>::ld(p);
-            s += x[j].x + x[j].y + x[j].z + x[j].w;
+            VecW<T>::ld(p, x[j]);
+#pragma unroll
+            for (int e = 0; e < VW; e++) s += x[j][e];
         }
     }
     const float mu = group_sum(s, lpr) / C;
     float v = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * 4;
+        const int c = (l + lpr * j) * VW;
         if (c < C) {
-            const float a = x[j].x - mu, b = x[j].y - mu, cc = x[j].z - mu, d = x[j].w - mu;
-            v += a * a + b * b + cc * cc + d * d;
+#pragma unroll
+            for (int e = 0; e < VW; e++) { const float a = x[j][e] - mu; v = fmaf(a, a, v); }
         }
     }
     const float rs = 1.0f / sqrtf(group_sum(v, lpr) / C + LN_EPS);
@@ -74,22 +115,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restri
     float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * 4;
+        const int c = (l + lpr * j) * VW;
         if (in_range && c < C) {
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            float y[VW];
+#pragma unroll
+            for (int e = 0; e < VW; e++) y[e] = 0.f;
             if (!pad) {
-                const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-                const float4 b = *reinterpret_cast<const float4*>(beta + c);
-                y.x = (x[j].x - mu) * rs * g.x + b.x;
-                y.y = (x[j].y - mu) * rs * g.y + b.y;
-                y.z = (x[j].z - mu) * rs * g.z + b.z;
-                y.w = (x[j].w - mu) * rs * g.w + b.w;
+                float g[VW], b[VW];
+                ldf(gamma + c, g, VW);
+                ldf(beta + c, b, VW);
+#pragma unroll
+                for (int e = 0; e < VW; e++) y[e] = (x[j][e] - mu) * rs * g[e] + b[e];
             }
             if (dotw != nullptr) {
-                const float4 w = *reinterpret_cast<const float4*>(dotw + c);
-                dot += y.x * w.x + y.y * w.y + y.z * w.z + y.w * w.w;
+                float w[VW];
+                ldf(dotw + c, w, VW);
+#pragma unroll
+                for (int e = 0; e < VW; e++) dot = fmaf(y[e], w[e], dot);
             } else {
-                Vec4<T>::st(Y + r * C + c, y);
+                VecW<T>::st(Y + r * C + c, y);
             }
         }
     }
@@ -101,26 +145,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restri
 
 // Backward: warp w walks row groups  w, w + P, ...  (P = number of warps) and keeps the per-column parameter-gradient
 // partial sums in registers; partial[w][3][C] is reduced afterwards in a fixed order (deterministic).
-template <typename T, int NV>
+template <typename T, int NV, bool DOT>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ X,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const T* __restrict__ dRes, T* __restrict__ dX, int64_t rows,
                                                               int C, int lpr, int dy_map, int dx_map, WinGeo wg, MergeGeo mg,
-                                                              const float* __restrict__ dotw, float* __restrict__ partial) {
+                                                              const float* __restrict__ dotw, float* __restrict__ partial,
+                                                              MsuOperand ug) {
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
     const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int64_t P = (int64_t)gridDim.x * LN_WARPS;
+    constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
-    float4 ag[NV], ab[NV], aw[NV];
-#pragma unroll
-    for (int j = 0; j < NV; j++) ag[j] = ab[j] = aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 gm[NV];
+    float ag[NV][VW], ab[NV][VW], aw[DOT ? NV : 1][VW], gm[NV][VW];
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * 4;
-        gm[j] = (c < C) ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = (l + lpr * j) * VW;
+#pragma unroll
+        for (int e = 0; e < VW; e++) ag[j][e] = ab[j][e] = aw[DOT ? j : 0][e] = gm[j][e] = 0.f;
+        if (c < C) ldf(gamma + c, gm[j], VW);
     }
 
     for (int64_t g0 = wid * rpw; g0 < rows; g0 += P * rpw) {
@@ -128,52 +173,66 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
         const bool live = lr < rows;
         const float mu = live ? mean[lr] : 0.f, rs = live ? rstd[lr] : 0.f;
         const int64_t dyr = (live && dy_map == MSU_MAP_WINDOW) ? pix_to_win(wg, lr) : lr;
-        const float dl = (live && dotw != nullptr) ? to_f<T>(dY[lr]) : 0.f;
-        float4 x[NV], dy[NV];
+        const float dl = (DOT && live) ? to_f<T>(dY[lr]) : 0.f;
+        float x[NV][VW], dy[NV][VW];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            const int c = (l + lpr * j) * 4;
-            x[j] = dy[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c = (l + lpr * j) * VW;
+#pragma unroll
+            for (int e = 0; e < VW; e++) x[j][e] = dy[j][e] = 0.f;
             if (live && c < C) {
                 const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : lr * C + c;
-                x[j] = Vec4<T>::ld(X + xo);
-                if (dotw != nullptr) {
-                    const float4 w = *reinterpret_cast<const float4*>(dotw + c);
-                    dy[j] = make_float4(dl * w.x, dl * w.y, dl * w.z, dl * w.w);
+                VecW<T>::ld(X + xo, x[j]);
+                if (DOT) {
+                    float w[VW];
+                    ldf(dotw + c, w, VW);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) dy[j][e] = dl * w[e];
                 } else {
-                    dy[j] = Vec4<T>::ld(dY + dyr * C + c);
+                    VecW<T>::ld(dY + dyr * C + c, dy[j]);
                 }
-                // x <- normalised x-hat
-                x[j].x = (x[j].x - mu) * rs; x[j].y = (x[j].y - mu) * rs; x[j].z = (x[j].z - mu) * rs; x[j].w = (x[j].w - mu) * rs;
-                const float g0_ = dy[j].x * gm[j].x, g1_ = dy[j].y * gm[j].y, g2_ = dy[j].z * gm[j].z, g3_ = dy[j].w * gm[j].w;
-                s1 += g0_ + g1_ + g2_ + g3_;
-                s2 += g0_ * x[j].x + g1_ * x[j].y + g2_ * x[j].z + g3_ * x[j].w;
+#pragma unroll
+                for (int e = 0; e < VW; e++) {
+                    x[j][e] = (x[j][e] - mu) * rs;          // x-hat
+                    const float g = dy[j][e] * gm[j][e];
+                    s1 += g;
+                    s2 = fmaf(g, x[j][e], s2);
+                }
             }
         }
         s1 = group_sum(s1, lpr) / C;
         s2 = group_sum(s2, lpr) / C;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            const int c = (l + lpr * j) * 4;
+            const int c = (l + lpr * j) * VW;
             if (live && c < C) {
                 const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : lr * C + c;
-                float4 dx;
-                dx.x = rs * (dy[j].x * gm[j].x - s1 - x[j].x * s2);
-                dx.y = rs * (dy[j].y * gm[j].y - s1 - x[j].y * s2);
-                dx.z = rs * (dy[j].z * gm[j].z - s1 - x[j].z * s2);
-                dx.w = rs * (dy[j].w * gm[j].w - s1 - x[j].w * s2);
+                float dx[VW];
+#pragma unroll
+                for (int e = 0; e < VW; e++) dx[e] = rs * (dy[j][e] * gm[j][e] - s1 - x[j][e] * s2);
                 if (dRes != nullptr) {
-                    const float4 d = Vec4<T>::ld(dRes + xo);
-                    dx.x += d.x; dx.y += d.y; dx.z += d.z; dx.w += d.w;
+                    float d[VW];
+                    VecW<T>::ld(dRes + xo, d);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) dx[e] += d[e];
                 }
-                Vec4<T>::st(dX + xo, dx);
-                ag[j].x += dy[j].x * x[j].x; ag[j].y += dy[j].y * x[j].y; ag[j].z += dy[j].z * x[j].z; ag[j].w += dy[j].w * x[j].w;
-                ab[j].x += dy[j].x; ab[j].y += dy[j].y; ab[j].z += dy[j].z; ab[j].w += dy[j].w;
-                if (dotw != nullptr) {
-                    const float4 b = *reinterpret_cast<const float4*>(beta + c);
-                    aw[j].x += dl * (x[j].x * gm[j].x + b.x); aw[j].y += dl * (x[j].y * gm[j].y + b.y);
-                    aw[j].z += dl * (x[j].z * gm[j].z + b.z); aw[j].w += dl * (x[j].w * gm[j].w + b.w);
+                int64_t wo = xo;
+                if (dx_map == MSU_MAP_UNSHUFFLE) {   // gradient written straight in the inverse depth-to-space layout
+                    const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, ug.geo, lr, c);
+                    wo = rc.row * (int64_t)(ug.geo[2] * ug.geo[2] * ug.geo[3]) + rc.col;
+                }
+                VecW<T>::st(dX + wo, dx);
+#pragma unroll
+                for (int e = 0; e < VW; e++) {
+                    ag[j][e] = fmaf(dy[j][e], x[j][e], ag[j][e]);
+                    ab[j][e] += dy[j][e];
+                }
+                if (DOT) {
+                    float b[VW];
+                    ldf(beta + c, b, VW);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) aw[DOT ? j : 0][e] = fmaf(dl, x[j][e] * gm[j][e] + b[e], aw[DOT ? j : 0][e]);
                 }
             }
         }
@@ -183,20 +242,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < NV; j++) {
         for (int o = lpr; o < 32; o <<= 1) {
-            ag[j].x += __shfl_xor_sync(0xffffffffu, ag[j].x, o); ag[j].y += __shfl_xor_sync(0xffffffffu, ag[j].y, o);
-            ag[j].z += __shfl_xor_sync(0xffffffffu, ag[j].z, o); ag[j].w += __shfl_xor_sync(0xffffffffu, ag[j].w, o);
-            ab[j].x += __shfl_xor_sync(0xffffffffu, ab[j].x, o); ab[j].y += __shfl_xor_sync(0xffffffffu, ab[j].y, o);
-            ab[j].z += __shfl_xor_sync(0xffffffffu, ab[j].z, o); ab[j].w += __shfl_xor_sync(0xffffffffu, ab[j].w, o);
-            if (dotw != nullptr) {
-                aw[j].x += __shfl_xor_sync(0xffffffffu, aw[j].x, o); aw[j].y += __shfl_xor_sync(0xffffffffu, aw[j].y, o);
-                aw[j].z += __shfl_xor_sync(0xffffffffu, aw[j].z, o); aw[j].w += __shfl_xor_sync(0xffffffffu, aw[j].w, o);
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+                ag[j][e] += __shfl_xor_sync(0xffffffffu, ag[j][e], o);
+                ab[j][e] += __shfl_xor_sync(0xffffffffu, ab[j][e], o);
+                if (DOT) aw[DOT ? j : 0][e] += __shfl_xor_sync(0xffffffffu, aw[DOT ? j : 0][e], o);
             }
         }
-        const int c = (l + lpr * j) * 4;
+        const int c = (l + lpr * j) * VW;
         if (sub == 0 && c < C) {
-            *reinterpret_cast<float4*>(pg + c) = ag[j];
-            *reinterpret_cast<float4*>(pg + C + c) = ab[j];
-            *reinterpret_cast<float4*>(pg + 2 * C + c) = aw[j];
+#pragma unroll
+            for (int e = 0; e < VW; e += 4) {
+                *reinterpret_cast<float4*>(pg + c + e) = make_float4(ag[j][e], ag[j][e + 1], ag[j][e + 2], ag[j][e + 3]);
+                *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(ab[j][e], ab[j][e + 1], ab[j][e + 2], ab[j][e + 3]);
+                if (DOT) *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(aw[DOT ? j : 0][e], aw[DOT ? j : 0][e + 1], aw[DOT ? j : 0][e + 2], aw[DOT ? j : 0][e + 3]);
+            }
         }
     }
 }
@@ -223,8 +283,8 @@ __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __re
 }
 
 // lanes per row: power of two in [4, 32] giving about 3-4 vectors (of 4 elements) per lane
-static int pick_lpr(int C) {
-    const int nvec = C / 4;
+static int pick_lpr(int C, int vw) {
+    const int nvec = (C + vw - 1) / vw;
     int lpr = 4;
     while (lpr < 32 && lpr * 4 < nvec) lpr <<= 1;
     return lpr;
@@ -254,16 +314,24 @@ static int launch_bwd(const void* dY, const void* X, const float* gamma, const f
     MergeGeo mg{0, 0};
     if (dy_map == MSU_MAP_WINDOW) wg = make_wingeo(geo);
     if (dx_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
-    ln_bwd_kernel<T, NV><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,
-                                                        (const T*)dRes, (T*)dX, rows, C, lpr, dy_map, dx_map, wg, mg,
-                                                        dotw, partial);
+    MsuOperand ug{};
+    if (dx_map == MSU_MAP_UNSHUFFLE) for (int k = 0; k < 4; k++) ug.geo[k] = geo[k];
+    if (dotw != nullptr)
+        ln_bwd_kernel<T, NV, true><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,
+                                                                  (const T*)dRes, (T*)dX, rows, C, lpr, dy_map, dx_map, wg, mg,
+                                                                  dotw, partial, ug);
+    else
+        ln_bwd_kernel<T, NV, false><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,
+                                                                   (const T*)dRes, (T*)dX, rows, C, lpr, dy_map, dx_map, wg, mg,
+                                                                   dotw, partial, ug);
     count_launch();
     return check_launch("msu_ln_bwd");
 }
 
 #define LN_DISPATCH_NV(FN, T, ...)                                         \
     do {                                                                   \
-        const int nv = (C / 4 + pick_lpr(C) - 1) / pick_lpr(C);            \
+        const int vw_ = VecW<T>::N;                                        \
+        const int nv = ((C + vw_ - 1) / vw_ + pick_lpr(C, vw_) - 1) / pick_lpr(C, vw_); \
         if (nv <= 1) return FN<T, 1>(__VA_ARGS__);                         \
         if (nv <= 2) return FN<T, 2>(__VA_ARGS__);                         \
         if (nv <= 3) return FN<T, 3>(__VA_ARGS__);                         \
@@ -284,22 +352,23 @@ extern "C" int msu_ln_fwd(int dtype, const void* X, const float* gamma, const fl
                           float* rstd, int64_t rows, int32_t C, int32_t in_map, int32_t out_map, const int32_t* geo,
                           const float* dotw, void* stream) {
     MSU_REQUIRE(X && gamma && beta && Y && mean && rstd, "msu_ln_fwd: null pointer");
-    MSU_REQUIRE(C % 4 == 0 && C > 0, "msu_ln_fwd: C=%d must be a positive multiple of 4", C);
+    MSU_REQUIRE(C > 0 && C % (dtype == MSU_F32 ? 4 : 8) == 0, "msu_ln_fwd: C=%d must be a positive multiple of the 16-byte vector width", C);
     MSU_REQUIRE(in_map == MSU_MAP_NONE || in_map == MSU_MAP_MERGE, "msu_ln_fwd: bad in_map %d", in_map);
     MSU_REQUIRE(out_map == MSU_MAP_NONE || out_map == MSU_MAP_WINDOW, "msu_ln_fwd: bad out_map %d", out_map);
     MSU_REQUIRE((in_map == 0 && out_map == 0) || geo != nullptr, "msu_ln_fwd: geo required for mapped rows");
     if (rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_fwd, float, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C), in_map, out_map, geo, dotw, st);
-    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_fwd, __nv_bfloat16, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C), in_map, out_map, geo, dotw, st);
+    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_fwd, float, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, st);
+    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_fwd, __nv_bfloat16, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, st);
     MSU_REQUIRE(false, "msu_ln_fwd: unsupported dtype %d", dtype);
 }
 
 // number of partial rows P = grid*8 warps: enough warps to cover the SMs, bounded by a 32 MiB workspace
-extern "C" int msu_ln_bwd_partial_rows(int64_t rows, int32_t C) {
-    const int rpw = 32 / pick_lpr(C);
+extern "C" int msu_ln_bwd_partial_rows(int dtype, int64_t rows, int32_t C) {
+    const int rpw = 32 / pick_lpr(C, dtype == MSU_F32 ? 4 : 8);
     int64_t P = imin((rows + rpw - 1) / rpw, (int64_t)num_sms() * 32);
     P = imin(P, (8ll << 20) / (3ll * C));
+    P = imin(P, imax(LN_WARPS, rows / 16));   // keep the fp32 partial rows (3*C floats each) small next to the row data
     const int grid = (int)imax(1, (P + LN_WARPS - 1) / LN_WARPS);
     return grid * LN_WARPS;
 }
@@ -309,13 +378,14 @@ extern "C" int msu_ln_bwd(int dtype, const void* dY, const void* X, const float*
                           int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,
                           void* stream) {
     MSU_REQUIRE(dY && X && gamma && beta && mean && rstd && dX && partial, "msu_ln_bwd: null pointer");
-    MSU_REQUIRE(C % 4 == 0 && C > 0, "msu_ln_bwd: C=%d must be a positive multiple of 4", C);
+    MSU_REQUIRE(C > 0 && C % (dtype == MSU_F32 ? 4 : 8) == 0, "msu_ln_bwd: C=%d must be a positive multiple of the 16-byte vector width", C);
     MSU_REQUIRE(dy_map == MSU_MAP_NONE || dy_map == MSU_MAP_WINDOW, "msu_ln_bwd: bad dy_map %d", dy_map);
-    MSU_REQUIRE(dx_map == MSU_MAP_NONE || dx_map == MSU_MAP_MERGE, "msu_ln_bwd: bad dx_map %d", dx_map);
-    const int grid = msu_ln_bwd_partial_rows(rows, C) / LN_WARPS;
+    MSU_REQUIRE(dx_map == MSU_MAP_NONE || dx_map == MSU_MAP_MERGE || dx_map == MSU_MAP_UNSHUFFLE, "msu_ln_bwd: bad dx_map %d", dx_map);
+    MSU_REQUIRE(dx_map != MSU_MAP_UNSHUFFLE || (geo != nullptr && geo[3] % (dtype == MSU_F32 ? 4 : 8) == 0), "msu_ln_bwd: UNSHUFFLE needs geo with a vector-aligned chunk width");
+    const int grid = msu_ln_bwd_partial_rows(dtype, rows, C) / LN_WARPS;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_bwd, float, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C), dy_map, dx_map, geo, dotw, partial, grid, st);
-    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_bwd, __nv_bfloat16, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C), dy_map, dx_map, geo, dotw, partial, grid, st);
+    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_bwd, float, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st);
+    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_bwd, __nv_bfloat16, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st);
     MSU_REQUIRE(false, "msu_ln_bwd: unsupported dtype %d", dtype);
 }
 

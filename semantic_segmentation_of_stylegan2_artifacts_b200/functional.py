@@ -21,7 +21,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import ops
-from .ops import MAP_CONV3, MAP_MERGE, MAP_SHUFFLE, MAP_WINDOW, epilogue, gemm, operand
+from .ops import MAP_CONV3, MAP_MERGE, MAP_SHUFFLE, MAP_UNSHUFFLE, MAP_WINDOW, epilogue, gemm, operand
 
 WS = 7
 BF16 = torch.bfloat16
@@ -268,12 +268,13 @@ class PatchExpandFn(Function):
         T, Cd = x2d.shape
         c2 = Cd // 2
         dout = _c(dout).view(4 * T, c2)
-        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2)
-        dyr, dyrt = rows(dy, T, 2 * Cd, dt, ld=c2, map=MAP_SHUFFLE, geo=geo)   # inverse depth-to-space view [T, 2C]
+        # LayerNorm backward writes its result straight in the inverse depth-to-space layout [T, 2C]
+        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2, dx_map=MAP_UNSHUFFLE, geo=geo,
+                                     dx_shape=(T, 2 * Cd))
         dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
-        gemm(dyrt, operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
+        gemm(operand(dy, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
         dx = torch.empty(T, Cd, dtype=dt, device=dev)
-        gemm(dyr, w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
+        gemm(operand(dy), w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
         return dx.view(xshape), dew, dnw, dnb, None, None, None
 
 
@@ -401,14 +402,14 @@ class HeadFn(Function):
              E, 9 * E, Mp, dev)
         dc1w = ops.prep_weight(4, dw1r, E, E, (E, E, 3, 3), torch.float32)
         w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
-        dh0 = torch.empty(Mp, E, dtype=dt, device=dev)
-        gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f), epilogue(dh0, H=h0, ldh=E), Mp, E, 9 * E, dev)
-        # expand (inverse depth-to-space view [T, 16E])
-        dhr, dhrt = rows(dh0, T, 16 * E, dt, ld=E, map=MAP_SHUFFLE, geo=sgeo)
+        # conv1 dgrad (x gelu'(h0)) written by the GEMM epilogue in the inverse depth-to-space layout [T, 16E]
+        dh0 = torch.empty(T, 16 * E, dtype=dt, device=dev)
+        gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f),
+             epilogue(dh0, ldc=16 * E, H=h0, ldh=E, map=MAP_UNSHUFFLE, geo=sgeo), Mp, E, 9 * E, dev)
         dew = torch.empty(16 * E, E, **f32)
-        gemm(dhrt, operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev)
+        gemm(operand(dh0, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev)
         dx = torch.empty(T, E, dtype=dt, device=dev)
-        gemm(dhr, w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
+        gemm(operand(dh0), w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
         return (dx.view(xshape), dew, dc1w, dc1b, dc2w, dc2b, dnw, dnb, dow.view(owshape), None, None)
 
 

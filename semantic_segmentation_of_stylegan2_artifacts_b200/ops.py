@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib as L
-from ._lib import (BF16, F16, F32, MAP_CONV3, MAP_MERGE, MAP_NONE, MAP_SHUFFLE, MAP_WINDOW,  # noqa: F401
+from ._lib import (BF16, F16, F32, MAP_CONV3, MAP_MERGE, MAP_NONE, MAP_SHUFFLE, MAP_UNSHUFFLE, MAP_WINDOW,  # noqa: F401
                    MsuEpilogue, MsuOperand)
 
 _ws_cache: dict = {}
@@ -130,7 +130,7 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     """Returns (dx, dgamma, dbeta, ddotw|None); rows = number of LayerNorm rows."""
     dev = x.device
     dx = torch.empty(x.shape if dx_shape is None else dx_shape, dtype=x.dtype, device=dev)
-    P = L.lib().msu_ln_bwd_partial_rows(rows, Cdim)
+    P = L.lib().msu_ln_bwd_partial_rows(L.dt(x), rows, Cdim)
     part = torch.empty(P * 3 * Cdim, dtype=torch.float32, device=dev)
     g = _geo_arr(geo)
     L.check(L.lib().msu_ln_bwd(L.dt(x), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
