@@ -12,6 +12,8 @@
 //             padding; network/model_parts.py:468-471)
 // B is always a K-major [N, K] bf16 weight shadow.  K tails are zero-filled by TMA (out-of-bounds).
 // Every output map / fused epilogue of MsuEpilogue is honoured (each epilogue thread owns one output row).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 #include "common.cuh"
@@ -21,11 +23,12 @@ namespace msu {
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     int64_t M;
-    int N, BN, num_m_tiles, num_n_tiles;
+    int N, K, BN, num_m_tiles, num_n_tiles;
     int mode;                 // 0 plain, 1 dual, 2 conv3x3
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
     int stages, nstg;         // operand pipeline depth, number of bf16 output staging tiles (1 or 2)
+    int a_stage, b_stage;     // bytes per pipeline stage of the A / B operand rings
     MsuEpilogue E;
 };
 
@@ -83,8 +86,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int B_BYTES = p.BN * TC_BK * 2;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)p.stages * TC_A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
+    uint8_t* sB = smem + (size_t)p.stages * p.a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_stage);
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;   // [2]
     uint64_t* tempty = tfull + 2;         // [2]
@@ -123,7 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
                 int cb = 0, cy = 0, cx = 0;
-                if (p.mode == 2) {
+                if (p.mode >= 2) {
                     const int per_img = p.tiles_x * p.tiles_y;
                     cb = mt / per_img;
                     const int r = mt % per_img;
@@ -132,9 +135,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* a_dst = sA + (size_t)stage * p.a_stage;
+                    uint8_t* b_dst = sB + (size_t)stage * p.b_stage;
+                    if (p.mode == 3) {
+                        // halo row: 130 pixels x 64 channels once per (dy, channel block); the three dx taps are
+                        // row-shifted views of it.  Three weight tiles ride in the same stage.
+                        const int dyi = kb / p.cblocks, c0 = (kb % p.cblocks) * TC_BK;
+                        mbar_arrive_expect_tx(&full[stage], 130 * 128 + 3 * B_BYTES);
+                        tma_load_4d(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
+                        for (int dx = 0; dx < 3; dx++)
+                            tma_load_2d(b_dst + dx * B_BYTES, &tmB, &full[stage], (dyi * 3 + dx) * p.C + c0, nt * p.BN);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[stage], TC_A_BYTES + B_BYTES);
-                    void* a_dst = sA + (size_t)stage * TC_A_BYTES;
-                    void* b_dst = sB + (size_t)stage * B_BYTES;
                     int bk;
                     if (p.mode == 2) {
                         const int tap = kb / p.cblocks, c0 = (kb % p.cblocks) * TC_BK;
@@ -165,11 +179,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
-                    const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
+                    const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage);
+                    if (p.mode == 3) {
+                        for (int dx = 0; dx < 3; dx++) {
+                            // A rows shifted by dx pixels = start address + dx*128 B.  The 128B swizzle is a function of
+                            // the shared-memory address bits (measured: base-offset field must stay 0), so a row-shifted
+                            // view of the TMA-written halo tile is read back consistently.
+                            const uint64_t adesc = make_desc_kmajor_sw128(a_addr + dx * 128);
+                            const uint64_t bdesc = make_desc_kmajor_sw128(b_addr + dx * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle row
-                        tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < TC_BK / 16; k++)
+                                tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | dx | k) != 0);
+                        }
+                    } else {
+                        const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+                        const uint64_t bdesc = make_desc_kmajor_sw128(b_addr);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle row
+                            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     tc_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -193,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
             if (half == 0) {
                 int64_t m;
-                if (p.mode == 2) {
+                if (p.mode >= 2) {
                     const int per_img = p.tiles_x * p.tiles_y;
                     const int cb = mt / per_img, r = mt % per_img;
                     const int y = (r / p.tiles_x) * p.bmh + rl / p.bmw, x = (r % p.tiles_x) * p.bmw + rl % p.bmw;
@@ -403,7 +432,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (get_encode() == nullptr) return 1;
 
     TcParams p{};
-    p.M = M; p.N = (int)N;
+    p.M = M; p.N = (int)N; p.K = (int)K;
     // memory-bound shapes: <=192 columns and two staging tiles (drain and store overlap);
     // compute-bound shapes (long K): 256 columns, one staging tile, deeper operand pipeline
     p.nstg = (K >= 512 && N >= 256) ? 1 : 2;
@@ -427,7 +456,13 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         p.tiles_x = W / bmw; p.tiles_y = H / bmh;
         p.num_m_tiles = Bn * p.tiles_x * p.tiles_y;
         p.kb1 = 9 * p.cblocks; p.kb2 = 0; p.k_split = 0;
-        if (!make_map_nhwc(&tmA, A->ptr, Bn, H, W, C, bmw, bmh)) return 1;
+        static const int halo_off = getenv("MSU_CONV_HALO") ? (atoi(getenv("MSU_CONV_HALO")) == 0) : 0;
+        if (!halo_off && bmw == 128) {
+            // one 130-pixel halo row per (dy, channel block) instead of nine shifted 128-pixel boxes: 2.9x less A traffic
+            p.mode = 3;
+            p.kb1 = 3 * p.cblocks;
+            if (!make_map_nhwc(&tmA, A->ptr, Bn, H, W, C, 130, 1)) return 1;
+        } else if (!make_map_nhwc(&tmA, A->ptr, Bn, H, W, C, bmw, bmh)) return 1;
         tmA2 = tmA;
     } else {
         p.mode = A->ptr2 ? 1 : 0;
@@ -447,7 +482,9 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     }
     if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
 
-    const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
+    p.a_stage = p.mode == 3 ? 17 * 1024 : TC_A_BYTES;
+    p.b_stage = (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
+    const int stage_bytes = p.a_stage + p.b_stage;
     const int fixed_bytes = (2 * 8 + 8) * 8 + 16 + 4 * TC_BM * 8 + 2 * TC_BM * 4 + p.nstg * TC_BM * (p.BN + 8) * 2 + 1024;
     p.stages = (226 * 1024 - fixed_bytes) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
@@ -611,6 +648,7 @@ struct WcParams {
     int WB, G, BN, n_groups, splits, boxes;   // slab width, taps per CTA, N per tap, tap groups, K splits, 64-ch boxes per operand
     int64_t slabs, slabs_per_split;
     int stages;
+    int halo;                 // 1: one (WB+2)-pixel halo slab per dy, the three dx taps are row-shifted views of it
     float* ws;
 };
 
@@ -624,7 +662,8 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int tap0 = grp * p.G;
     const int ntap = (9 - tap0) < p.G ? (9 - tap0) : p.G;
     const int A_BYTES = p.boxes * BOX;
-    const int B_BYTES = p.G * p.boxes * BOX;
+    const int XBOX = p.halo ? ((p.WB + 2) * 128 + 1023) / 1024 * 1024 : BOX;   // halo slab box, 1 KB aligned
+    const int B_BYTES = p.halo ? p.boxes * XBOX : p.G * p.boxes * BOX;
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
@@ -661,11 +700,15 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 const int64_t row = slab / slabs_per_row;
                 const int y = (int)(row % p.H), b = (int)(row / p.H);
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], A_BYTES + ntap * p.boxes * BOX);
+                mbar_arrive_expect_tx(&full[stage], p.halo ? A_BYTES + p.boxes * (p.WB + 2) * 128 : A_BYTES + ntap * p.boxes * BOX);
                 uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
                 uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
                 for (int bx = 0; bx < p.boxes; bx++) tma_load_4d(a_dst + bx * BOX, &tmZ, &full[stage], bx * 64, x0, y, b);
-                for (int t = 0; t < ntap; t++) {
+                if (p.halo) {   // group = dy; pixels x0-1 .. x0+WB of row y+dy-1 (zero fill outside the image)
+                    for (int bx = 0; bx < p.boxes; bx++)
+                        tma_load_4d(b_dst + bx * XBOX, &tmX, &full[stage], bx * 64, x0 - 1, y + grp - 1, b);
+                }
+                for (int t = 0; t < (p.halo ? 0 : ntap); t++) {
                     const int tap = tap0 + t;
                     for (int bx = 0; bx < p.boxes; bx++)
                         tma_load_4d(b_dst + (t * p.boxes + bx) * BOX, &tmX, &full[stage], bx * 64, x0 + tap % 3 - 1, y + tap / 3 - 1, b);
@@ -685,7 +728,9 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 for (int t = 0; t < ntap; t++) {
                     for (int k = 0; k < p.WB / 16; k++) {
                         const uint64_t adesc = make_desc_mnmajor_sw128(a_base + k * 2048, BOX);
-                        const uint64_t bdesc = make_desc_mnmajor_sw128(b_base + t * p.boxes * BOX + k * 2048, BOX);
+                        // halo: tap t = dx is the slab shifted by t pixel rows (+128 B); swizzle is address based
+                        const uint64_t bdesc = p.halo ? make_desc_mnmajor_sw128(b_base + t * 128 + k * 2048, XBOX)
+                                                      : make_desc_mnmajor_sw128(b_base + t * p.boxes * BOX + k * 2048, BOX);
                         tc_mma_bf16(tmem_base + t * p.BN, adesc, bdesc, idesc, (kb | k) != 0);
                     }
                 }
@@ -740,7 +785,15 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     const int BOX = p.WB * 128;
     while (p.G > 1 && 2 * (p.boxes + p.G * p.boxes) * BOX > 200 * 1024) p.G--;
     p.n_groups = (9 + p.G - 1) / p.G;
-    const int stage_bytes = (p.boxes + p.G * p.boxes) * BOX;
+    int stage_bytes = (p.boxes + p.G * p.boxes) * BOX;
+    // measured slower than the 5+4 tap grouping on B200 (3.8 vs 2.6 ms per step): opt-in only
+    static const int halo_on = getenv("MSU_WGRAD_HALO") ? atoi(getenv("MSU_WGRAD_HALO")) : 0;
+    p.halo = (halo_on && p.WB == 64 && 3 * p.BN <= TC_TMEM_COLS) ? 1 : 0;
+    if (p.halo) {   // taps grouped by dy: 3 accumulators per CTA, dZ read 3x but X read once per dy (1.8x less L2 traffic)
+        p.G = 3;
+        p.n_groups = 3;
+        stage_bytes = p.boxes * BOX + p.boxes * (((p.WB + 2) * 128 + 1023) / 1024 * 1024);
+    }
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return 1;
@@ -759,6 +812,7 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
         cuuint32_t box[4] = {64, (cuuint32_t)p.WB, 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         for (int k = 0; k < 2; k++) {
+            box[1] = (cuuint32_t)((k == 1 && p.halo) ? p.WB + 2 : p.WB);
             if (get_encode()(k ? &tmX : &tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k ? B->ptr : A->ptr), gdim, gstr,
                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -79,7 +79,8 @@ def test_dual_source_concat(ops):
         assert relmax(tc, ref) < 1e-2 and relmax(tc, simt) < 8e-3
 
 
-@pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128)])
+@pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128), (2, 256, 96),
+                                  (1, 128, 64), (1, 128, 128)])
 def test_conv3x3_implicit(ops, geom):
     B, S, E = geom
     torch.manual_seed(S + E)
