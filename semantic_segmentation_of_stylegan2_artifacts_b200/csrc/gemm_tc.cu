@@ -1,9 +1,15 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a: C[m,n] = epilogue(sum_k A(m,k) B(n,k)), bf16 operands, fp32 accumulate.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer (+TMEM
-// alloc), warps 2..9 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).  Operands are staged
-// in 128B-swizzled shared memory by cp.async.bulk.tensor; accumulators live in TMEM (2 x 256 columns so
-// the epilogue of tile i overlaps the MMAs of tile i+1).  UMMA shape M=128, N=BN (16..256), K=16.
+// alloc), warps 2..2+EPW = self-contained epilogue warps: each takes 32-row x 32-column blocks of the
+// accumulator (its TMEM lane quadrant, column chunks round-robin among the warps of the quadrant):
+// tcgen05.ld -> +bias -> bf16 -> a private 2.5 KB shared-memory transpose -> fused epilogue -> coalesced
+// 16 B global stores (8 rows x 64 B per instruction).  No barrier between epilogue warps; the residual /
+// GELU' operands are requested before the TMEM load is waited for.  Operands are staged in 128B-swizzled
+// shared memory by cp.async.bulk.tensor; accumulators live in TMEM (2 x 256 columns so the epilogue of
+// tile i overlaps the MMAs of tile i+1).  UMMA shape M=128, N=BN (16..256), K=16.  The epilogue scratch is
+// only EPW x 2.5 KB, which leaves room for 4-5 operand stages: measured TMA round trips are ~1700 cycles
+// under load, so mainloop throughput = operand bytes in flight / latency.
 //
 // A-operand modes (all K-major, i.e. contraction index contiguous in memory):
 //   plain   : [M, K] rows                              (2-D tensor map)
@@ -12,6 +18,7 @@
 //             padding; network/model_parts.py:468-471)
 // B is always a K-major [N, K] bf16 weight shadow.  K tails are zero-filled by TMA (out-of-bounds).
 // Every output map / fused epilogue of MsuEpilogue is honoured (each epilogue thread owns one output row).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -27,17 +34,23 @@ struct TcParams {
     int mode;                 // 0 plain, 1 dual, 2 conv3x3
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
-    int stages, nstg;         // operand pipeline depth, number of bf16 output staging tiles (1 or 2)
+    int stages;               // operand pipeline depth
+    int epi_tma;              // 1: unmapped output -> per-warp swizzled slabs + TMA stores (Cpre out / R or H in through TMA too)
+    int epi_bytes;            // shared memory per epilogue warp
     int a_stage, b_stage;     // bytes per pipeline stage of the A / B operand rings
+    long long* trace;         // debug (MSU_TC_TRACE=1): clock64 stamps [cta][tile < 8][16 events]
     MsuEpilogue E;
 };
+#define TC_TRACE(ev) do { if (p.trace != nullptr && lane == 0 && it < 8) p.trace[((size_t)blockIdx.x * 8 + it) * 16 + (ev)] = clock64(); } while (0)
 
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_DRAIN_WARPS = 4;    // TMEM -> bf16 staging (one per TMEM lane quadrant)
-constexpr int TC_STORE_WARPS = 16;   // staging -> fused epilogue -> coalesced global stores
-constexpr int TC_THREADS = 32 * (2 + TC_DRAIN_WARPS + TC_STORE_WARPS);
+constexpr int TC_EPI_WARPS = 12;     // epilogue warps (multiple of 4: warp % 4 selects the TMEM lane quadrant)
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_CW = 32;                          // epilogue chunk width (columns)
+constexpr int TC_CPITCH_B = (TC_CW + 8) * 2;       // 80 B scratch row pitch: 16 B accesses of 32 lanes are conflict free
+constexpr int TC_SCRATCH_BYTES = 32 * TC_CPITCH_B; // per epilogue warp
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -53,35 +66,45 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     }
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 2 MUFU + ~12 FMA-class ops instead of erff's ~45.
-// Only used by the bf16 epilogue, where it is far below the output rounding (fp32 parity mode keeps erff).
-__device__ __forceinline__ void erf_exp_fast(float x, float& erf_abs, float& e) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    e = exp2f(z * z * -1.4426950408889634f);   // exp(-x^2/2)
-    erf_abs = fmaf(-poly, e, 1.0f);
+// GELU(x) = x * Phi(x) for the bf16 epilogues.  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as
+// sigmoid(2 x (c0 + c1 x^2 + c2 x^4)) with minimax-fitted c (|Phi error| <= 5.1e-5, |GELU error| <= 6.5e-5 absolute,
+// 60x below the bf16 rounding of an O(1) output; tails keep their relative accuracy because 1 / (1 + 2^v) is
+// exact in the limit).  9 issue slots per element (2 MUFU) instead of erff's ~45: the store warps of the
+// short-K GEMMs are ALU-bound.  The fp32 parity mode keeps erff (common.cuh).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float phi_cdf_fast(float x, float& x2c) {
+    x2c = fminf(x * x, 50.0f);                     // beyond |x| = 7.07 Phi is 0 / 1 to fp32 precision
+    float p = fmaf(1.070594816e-03f, x2c, -1.070108842e-01f);
+    p = fmaf(p, x2c, -2.301264832e+00f);           // -2 log2(e) (c0 + c1 x^2 + c2 x^4)
+    return rcp_approx(1.0f + ex2_approx(x * p));
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-    float ea, e;
-    erf_exp_fast(x, ea, e);
-    const float hx = 0.5f * x;
-    return fmaf(hx, copysignf(ea, x), hx);
+    float x2c;
+    return x * phi_cdf_fast(x, x2c);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-    float ea, e;
-    erf_exp_fast(x, ea, e);
-    const float cdf = fmaf(0.5f, copysignf(ea, x), 0.5f);
+    float x2c;
+    const float cdf = phi_cdf_fast(x, x2c);
+    const float e = ex2_approx(x2c * -0.72134752044448170368f);   // exp(-x^2 / 2)
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// 16 B chunk g of row `row` inside a [32 rows x 64 B] SWIZZLE_64B slab (1 KB aligned): chunk ^= (row / 2) % 4
+__device__ __forceinline__ uint32_t slab_off(int row, int g) { return (uint32_t)(row * 64 + ((g ^ ((row >> 1) & 3)) << 4)); }
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int B_BYTES = p.BN * TC_BK * 2;
@@ -91,14 +114,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;   // [2]
     uint64_t* tempty = tfull + 2;         // [2]
-    uint64_t* sfull = tempty + 2;         // [2] staging tile filled by the drain warps
-    uint64_t* sempty = sfull + 2;         // [2] staging tile consumed by the store warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
-    int64_t* sRowOut = reinterpret_cast<int64_t*>(tmem_slot + 4);   // [2][128] mapped output row of each tile row (-1: skip)
-    int64_t* sRowM = sRowOut + 2 * TC_BM;                           // [2][128] logical row m of each tile row
-    int32_t* sColOff = reinterpret_cast<int32_t*>(sRowM + 2 * TC_BM);  // [2][128] column offset of the row (UNSHUFFLE map)
-    __nv_bfloat16* sStage = reinterpret_cast<__nv_bfloat16*>(sColOff + 2 * TC_BM);  // [2][128][BN + 8] bf16 output staging
-    const int pitch = p.BN + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* auxbar = reinterpret_cast<uint64_t*>(tmem_slot + 4);   // [TC_EPI_WARPS][2] aux-in slab landed (TMA path)
+    uint8_t* sScratch = smem + (size_t)p.stages * (p.a_stage + p.b_stage) + 1024;   // [TC_EPI_WARPS][epi_bytes], 1 KB aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -106,8 +124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_DRAIN_WARPS);
-                                      mbar_init(&sfull[a], TC_DRAIN_WARPS); mbar_init(&sempty[a], TC_STORE_WARPS); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2 * TC_EPI_WARPS; a++) mbar_init(&auxbar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -123,9 +141,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
                 const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
                 int cb = 0, cy = 0, cx = 0;
+                TC_TRACE(0);
                 if (p.mode >= 2) {
                     const int per_img = p.tiles_x * p.tiles_y;
                     cb = mt / per_img;
@@ -164,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(b_dst, &tmB, &full[stage], bk, nt * p.BN);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                TC_TRACE(1);
             }
         }
     } else if (warp == 1) {
@@ -172,13 +193,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
+                TC_TRACE(2);
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) TC_TRACE(3);
                     const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage);
                     const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage);
                     if (p.mode == 3) {
@@ -203,152 +227,320 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[acc]);                  // accumulator ready for the epilogue
+                TC_TRACE(4);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp < 2 + TC_DRAIN_WARPS) {
-        // ===================== drain warps: TMEM -> registers (+bias) -> bf16 staging tile =====================
+    } else if (p.epi_tma) {
+        // ===================== epilogue warps, unmapped output: TMEM -> fused epilogue in registers -> swizzled slab -> TMA store ==========
+        // Each lane owns one accumulator row (32 columns per chunk).  The residual / GELU' operand arrives as a TMA-loaded
+        // [32 x 32] slab one chunk ahead; the result (and the pre-activation copy) leave as TMA box stores, so there is no
+        // per-row address arithmetic and no transposition.
         const MsuEpilogue& E = p.E;
-        const int ew = warp - 2;              // 0..7: TMEM lane quadrant x interleaved column half
         const int quad = warp & 3;
-        const int half = ew >> 2;
-        const int nchunks = p.BN / 16;
+        const int sub = (warp - 2) >> 2;
+        constexpr int NSUB = TC_EPI_WARPS / 4;
+        const int nchunks = p.BN / TC_CW;               // BN is a multiple of 32 on this path
+        uint8_t* slab_out = sScratch + (size_t)(warp - 2) * p.epi_bytes;
+        uint8_t* slab_aux = slab_out + 2048;            // Cpre staging (out) or R/H operand (in, 2 slabs)
+        uint64_t* abar = auxbar + 2 * (warp - 2);
+        const bool aux_in = (E.R != nullptr || E.H != nullptr);
+        uint32_t aux_phase[2] = {0, 0};
+        int aux_buf = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        int sb = 0; uint32_t sb_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
-            const int rl = quad * 32 + lane;
-            mbar_wait(&sempty[sb], sb_phase ^ 1);      // store warps have finished with this staging buffer
-            __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
-            if (half == 0) {
-                int64_t m;
-                if (p.mode >= 2) {
-                    const int per_img = p.tiles_x * p.tiles_y;
-                    const int cb = mt / per_img, r = mt % per_img;
-                    const int y = (r / p.tiles_x) * p.bmh + rl / p.bmw, x = (r % p.tiles_x) * p.bmw + rl % p.bmw;
-                    m = ((int64_t)cb * p.H + y) * p.W + x;
-                } else {
-                    m = (int64_t)mt * TC_BM + rl;
-                }
-                int64_t ro = -1;
-                int coff = 0;
-                if (m < p.M) {
-                    if (E.map == MSU_MAP_WINDOW) {
-                        ro = win_to_pix(make_wingeo(E.geo), m);
-                    } else if (E.map == MSU_MAP_UNSHUFFLE) {
-                        const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, E.geo, m, 0);
-                        ro = rc.row;
-                        coff = rc.col;
-                    } else if (E.map == MSU_MAP_SHUFFLE) {   // base row; (p1, p2) offsets are added per column chunk
-                        const int hw = E.geo[0] * E.geo[1], pp = E.geo[2];
-                        const int64_t b = m / hw;
-                        const int t = (int)(m - b * hw);
-                        const int hh = t / E.geo[1], ww = t - hh * E.geo[1];
-                        ro = (b * (E.geo[0] * pp) + hh * pp) * (int64_t)(E.geo[1] * pp) + ww * pp;
-                    } else {
-                        ro = m;
-                    }
-                }
-                sRowOut[sb * TC_BM + rl] = ro;
-                sRowM[sb * TC_BM + rl] = m;
-                sColOff[sb * TC_BM + rl] = coff;
+            int64_t m0;                                   // first logical row of the tile (rows are consecutive on this path)
+            if (p.mode >= 2) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int cb = mt / per_img, rr = mt % per_img;
+                m0 = ((int64_t)cb * p.H + (rr / p.tiles_x) * p.bmh) * p.W + (rr % p.tiles_x) * p.bmw;
+            } else {
+                m0 = (int64_t)mt * TC_BM;
             }
+            const int row0 = (int)(m0 + quad * 32);       // first row of this warp's slab
+            float rs = 1.0f;
+            if (E.rowscale != nullptr) {
+                const int64_t m_own = m0 + quad * 32 + lane;
+                rs = m_own < p.M ? E.rowscale[m_own / E.rows_per_sample] : 0.0f;
+            }
+            const int c_first = (sub + it) % NSUB;
+            if (aux_in && c_first < nchunks && lane == 0) {   // operand slab of the first chunk
+                mbar_arrive_expect_tx(&abar[aux_buf], 2048);
+                tma_load_2d(slab_aux + aux_buf * 2048, &tmAux, &abar[aux_buf], nt * p.BN + c_first * TC_CW, row0);
+            }
+            if (warp == 2) TC_TRACE(5);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (warp == 2) TC_TRACE(6);
             const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-            for (int c = half; c < nchunks; c += TC_DRAIN_WARPS / 4) {
-                float v[16];
-                tc_ld16(t_base + c * 16, v);     // warp-collective: executed by all lanes
-                const int n0 = nt * p.BN + c * 16;
+            bool released = false;
+            bool first = true;
+            for (int c = c_first; c < nchunks; c += NSUB) {
+                uint32_t raw[TC_CW];
+                tc_ld32_nowait(t_base + c * TC_CW, raw);
+                const int n0 = nt * p.BN + c * TC_CW;
+                if (aux_in && c + NSUB < nchunks && lane == 0) {   // next chunk's operand slab (its buffer was drained a chunk ago)
+                    mbar_arrive_expect_tx(&abar[aux_buf ^ 1], 2048);
+                    tma_load_2d(slab_aux + (aux_buf ^ 1) * 2048, &tmAux, &abar[aux_buf ^ 1], n0 + NSUB * TC_CW, row0);
+                }
+                tc_ld_wait();
+                if (warp == 2 && first) TC_TRACE(10);
+                if (c + NSUB >= nchunks) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    released = true;
+                }
+                float v[TC_CW];
+#pragma unroll
+                for (int i = 0; i < TC_CW; i++) v[i] = __uint_as_float(raw[i]);
                 if (E.bias != nullptr) {
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; g4++) {
+                    for (int g4 = 0; g4 < TC_CW / 4; g4++) {
                         if (n0 + g4 * 4 < p.N) {
                             const float4 b0 = *reinterpret_cast<const float4*>(E.bias + n0 + g4 * 4);
                             v[g4 * 4] += b0.x; v[g4 * 4 + 1] += b0.y; v[g4 * 4 + 2] += b0.z; v[g4 * 4 + 3] += b0.w;
                         }
                     }
                 }
-                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)rl * pitch + c * 16);
-                dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                // the previous chunk's stores must have finished reading the slabs before they are overwritten
+                if (lane == 0) tma_store_wait_read0();
+                __syncwarp();
+                if (E.Cpre != nullptr) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        *reinterpret_cast<uint4*>(slab_aux + slab_off(lane, g)) =
+                            make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                    // the activation sees the bf16-rounded pre-activation, exactly like a separate GELU pass over Cpre
+#pragma unroll
+                    for (int i = 0; i < TC_CW; i++) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+                }
+                if (E.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < TC_CW; i++) v[i] = gelu_fast(v[i]);
+                }
+                if (aux_in) {
+                    mbar_wait(&abar[aux_buf], aux_phase[aux_buf]);
+                    aux_phase[aux_buf] ^= 1;
+                    const uint8_t* ab = slab_aux + aux_buf * 2048;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        float f[8];
+                        unpack8(*reinterpret_cast<const uint4*>(ab + slab_off(lane, g)), f);
+                        if (E.H != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[g * 8 + i] *= gelu_grad_fast(f[i]);
+                            if (E.rowscale != nullptr) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) v[g * 8 + i] *= rs;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[g * 8 + i] = fmaf(v[g * 8 + i], rs, f[i]);
+                        }
+                    }
+                    aux_buf ^= 1;
+                } else if (E.rowscale != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < TC_CW; i++) v[i] *= rs;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    *reinterpret_cast<uint4*>(slab_out + slab_off(lane, g)) =
+                        make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (warp == 2 && first) TC_TRACE(8);
+                if (lane == 0) {
+                    tma_store_2d(slab_out, &tmC, n0, row0);
+                    if (E.Cpre != nullptr) tma_store_2d(slab_aux, &tmAux, n0, row0);
+                    tma_store_commit();
+                }
+                if (warp == 2 && first) TC_TRACE(9);
+                first = false;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty[acc]);      // TMEM buffer is free for the MMA warp again
-                mbar_arrive(&sfull[sb]);        // staging tile ready (release: smem writes of this warp are visible)
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
             }
+            if (warp == 2) TC_TRACE(7);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (++sb == p.nstg) { sb = 0; sb_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();               // global writes complete before the CTA retires its shared memory
     } else {
-        // ===================== store warps: staging tile -> fused epilogue -> coalesced global stores =====================
+        // ===================== epilogue warps: TMEM -> (+bias) -> private transpose -> fused epilogue -> global =====================
         const MsuEpilogue& E = p.E;
         __nv_bfloat16* Cp = reinterpret_cast<__nv_bfloat16*>(E.C);
         __nv_bfloat16* Cpre = reinterpret_cast<__nv_bfloat16*>(E.Cpre);
         const __nv_bfloat16* Rp = reinterpret_cast<const __nv_bfloat16*>(E.R);
         const __nv_bfloat16* Hp = reinterpret_cast<const __nv_bfloat16*>(E.H);
-        const int st_tid = threadIdx.x - 32 * (2 + TC_DRAIN_WARPS);
-        const int cpr = p.BN / 8;
-        const uint32_t cpr_magic = (1u << 22) / (uint32_t)cpr + 1u;   // exact id / cpr for id < 128 * cpr, cpr <= 32
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
+        const int sub = (warp - 2) >> 2;                // index among the warps of the quadrant
+        constexpr int NSUB = TC_EPI_WARPS / 4;
+        const int nchunks = (p.BN + TC_CW - 1) / TC_CW;
+        const int rsub = lane >> 2, q = lane & 3;       // store phase: rows rsub + 8 j (j < 4), 16 B quarter q of the 64 B row
+        uint8_t* scr = sScratch + (size_t)(warp - 2) * TC_SCRATCH_BYTES;
         const bool passthrough = (E.act == 0 && Hp == nullptr && E.rowscale == nullptr && Rp == nullptr);
-        int sb = 0; uint32_t sb_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int nt = tile % p.num_n_tiles;
-            mbar_wait(&sfull[sb], sb_phase);
-            const __nv_bfloat16* stg = sStage + (size_t)sb * TC_BM * pitch;
-            const int64_t* rowOut = sRowOut + sb * TC_BM;
-            const int64_t* rowM = sRowM + sb * TC_BM;
-            const int32_t* colOff = sColOff + sb * TC_BM;
-            for (int id = st_tid; id < TC_BM * cpr; id += 32 * TC_STORE_WARPS) {
-                const int r = (int)(((uint32_t)id * cpr_magic) >> 22), c8 = id - r * cpr;
-                const int n = nt * p.BN + c8 * 8;
-                int64_t ro = rowOut[r];
-                if (ro < 0 || n >= p.N) continue;
-                int co = n + colOff[r];
-                if (E.map == MSU_MAP_SHUFFLE) {
-                    const int pp = E.geo[2], cc = E.geo[3];
-                    const int q = n / cc, p1 = q / pp, p2 = q - p1 * pp;
-                    ro += (int64_t)p1 * (E.geo[1] * pp) + p2;
-                    co = n - q * cc;
+        int acc = 0; uint32_t acc_phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            // ---- output row of accumulator lane (quad, lane), computed once per tile by its owner lane
+            int64_t m_own, ro_own = -1;
+            int coff_own = 0;
+            float rs_own = 1.0f;
+            {
+                const int rl = quad * 32 + lane;
+                if (p.mode >= 2) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    const int cb = mt / per_img, rr = mt % per_img;
+                    const int y = (rr / p.tiles_x) * p.bmh + rl / p.bmw, x = (rr % p.tiles_x) * p.bmw + rl % p.bmw;
+                    m_own = ((int64_t)cb * p.H + y) * p.W + x;
+                } else {
+                    m_own = (int64_t)mt * TC_BM + rl;
                 }
-                const int64_t o = ro * E.ldc + co;
-                const uint4 raw = *reinterpret_cast<const uint4*>(stg + (size_t)r * pitch + c8 * 8);
-                if (Cpre != nullptr) *reinterpret_cast<uint4*>(Cpre + o) = raw;
-                if (passthrough) {
-                    *reinterpret_cast<uint4*>(Cp + o) = raw;
-                    continue;
+                if (m_own < p.M) {
+                    if (E.map == MSU_MAP_WINDOW) {
+                        ro_own = win_to_pix(make_wingeo(E.geo), m_own);
+                    } else if (E.map == MSU_MAP_UNSHUFFLE) {
+                        const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, E.geo, m_own, 0);
+                        ro_own = rc.row;
+                        coff_own = rc.col;
+                    } else if (E.map == MSU_MAP_SHUFFLE) {   // base row; (p1, p2) offsets are added per column chunk
+                        const int hw = E.geo[0] * E.geo[1], pp = E.geo[2];
+                        const int64_t b = m_own / hw;
+                        const int t = (int)(m_own - b * hw);
+                        const int hh = t / E.geo[1], ww = t - hh * E.geo[1];
+                        ro_own = (b * (E.geo[0] * pp) + hh * pp) * (int64_t)(E.geo[1] * pp) + ww * pp;
+                    } else {
+                        ro_own = m_own;
+                    }
                 }
-                float w[8];
-                unpack8(raw, w);
-                if (E.act == 1) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] = gelu_fast(w[i]);
-                }
-                if (Hp != nullptr) {
-                    float hf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(Hp + rowM[r] * E.ldh + n), hf);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] *= gelu_grad_fast(hf[i]);
-                }
-                if (E.rowscale != nullptr) {
-                    const float rscale = E.rowscale[ro / E.rows_per_sample];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] *= rscale;
-                }
-                if (Rp != nullptr) {
-                    float rf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(Rp + ro * E.ldr + co), rf);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] += rf[i];
-                }
-                *reinterpret_cast<uint4*>(Cp + o) = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
-                                                               pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+                if (E.rowscale != nullptr && ro_own >= 0) rs_own = E.rowscale[ro_own / E.rows_per_sample];   // shuffle offsets stay inside the sample
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[sb]);   // staging buffer may be refilled
-            if (++sb == p.nstg) { sb = 0; sb_phase ^= 1; }
+            // rows this lane stores: hand the owner lanes' maps over
+            int64_t m_r[4], ro_r[4];
+            int coff_r[4];
+            float rs_r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int src = rsub + 8 * j;
+                m_r[j] = __shfl_sync(0xffffffffu, m_own, src);
+                ro_r[j] = __shfl_sync(0xffffffffu, ro_own, src);
+                coff_r[j] = __shfl_sync(0xffffffffu, coff_own, src);
+                rs_r[j] = __shfl_sync(0xffffffffu, rs_own, src);
+            }
+            if (warp == 2) TC_TRACE(5);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            if (warp == 2) TC_TRACE(6);
+            const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+            bool released = false;
+            bool first = true;
+            for (int c = (sub + it) % NSUB; c < nchunks; c += NSUB) {
+                const int cols = p.BN - c * TC_CW >= TC_CW ? TC_CW : 16;   // BN is a multiple of 16
+                uint32_t raw[TC_CW];
+                if (cols == TC_CW) tc_ld32_nowait(t_base + c * TC_CW, raw);
+                else tc_ld16_nowait(t_base + c * TC_CW, raw);
+                // ---- addresses and operand prefetch of the 4 (row, quarter) vectors this lane stores
+                const int n0 = nt * p.BN + c * TC_CW;
+                const int n = n0 + q * 8;
+                int64_t o[4];
+                uint4 hraw[4], rraw[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    o[j] = -1;
+                    if (ro_r[j] < 0 || n >= p.N || q * 8 >= cols) continue;
+                    int64_t rw = ro_r[j];
+                    int co = n + coff_r[j];
+                    if (E.map == MSU_MAP_SHUFFLE) {
+                        const int pp = E.geo[2], cc = E.geo[3];
+                        const int qq = n / cc, p1 = qq / pp, p2 = qq - p1 * pp;
+                        rw += (int64_t)p1 * (E.geo[1] * pp) + p2;
+                        co = n - qq * cc;
+                    }
+                    o[j] = rw * E.ldc + co;
+                    if (Hp != nullptr) hraw[j] = *reinterpret_cast<const uint4*>(Hp + m_r[j] * E.ldh + n);
+                    if (Rp != nullptr) rraw[j] = *reinterpret_cast<const uint4*>(Rp + rw * E.ldr + co);
+                }
+                tc_ld_wait();
+                if (warp == 2 && first) TC_TRACE(10);
+                if (c + NSUB >= nchunks) {                 // this warp's last read of the accumulator: hand TMEM back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    released = true;
+                }
+                // ---- own accumulator row -> bf16 -> scratch (row = lane)
+#pragma unroll
+                for (int g8 = 0; g8 < TC_CW / 8; g8++) {
+                    if (g8 * 8 < cols) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(raw[g8 * 8 + i]);
+                        if (E.bias != nullptr && n0 + g8 * 8 < p.N) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(E.bias + n0 + g8 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(E.bias + n0 + g8 * 8 + 4);
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        }
+                        *reinterpret_cast<uint4*>(scr + lane * TC_CPITCH_B + g8 * 16) =
+                            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    }
+                }
+                __syncwarp();
+                if (warp == 2 && first) TC_TRACE(8);
+                // ---- transposed read: 8 rows x 64 B per instruction -> fused epilogue -> coalesced stores
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (o[j] < 0) continue;
+                    const uint4 tv = *reinterpret_cast<const uint4*>(scr + (rsub + 8 * j) * TC_CPITCH_B + q * 16);
+                    if (Cpre != nullptr) *reinterpret_cast<uint4*>(Cpre + o[j]) = tv;
+                    if (passthrough) {
+                        *reinterpret_cast<uint4*>(Cp + o[j]) = tv;
+                        continue;
+                    }
+                    float w[8];
+                    unpack8(tv, w);
+                    if (E.act == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] = gelu_fast(w[i]);
+                    }
+                    if (Hp != nullptr) {
+                        float hf[8];
+                        unpack8(hraw[j], hf);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] *= gelu_grad_fast(hf[i]);
+                    }
+                    if (E.rowscale != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] *= rs_r[j];
+                    }
+                    if (Rp != nullptr) {
+                        float rf[8];
+                        unpack8(rraw[j], rf);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] += rf[i];
+                    }
+                    *reinterpret_cast<uint4*>(Cp + o[j]) = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
+                                                                      pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+                }
+                __syncwarp();                              // scratch is rewritten by the next chunk
+                if (warp == 2 && first) TC_TRACE(9);
+                first = false;
+            }
+            if (!released) {                               // no chunk of this tile fell to this warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            if (warp == 2) TC_TRACE(7);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -400,12 +592,23 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* ptr, int B, int H, int W,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int pick_bn(int64_t N, int cap = 256) {
-    // largest tile <= cap (multiple of 16) that wastes the least of the last N tile
-    if (N <= cap) return (int)((N + 15) / 16 * 16);
+// [rows, cols] bf16 output / epilogue operand, box = [32 rows, 32 cols] (one epilogue warp's chunk), 64B swizzle
+static bool make_map_slab(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_CW, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int pick_bn(int64_t N, int cap = 256, int step = 16) {
+    // largest tile <= cap (multiple of step) that wastes the least of the last N tile
+    if (N <= cap) return (int)((N + step - 1) / step * step);
     int best = cap;
     int64_t best_waste = (N + cap - 1) / cap * cap - N;
-    for (int bn = cap; bn >= 96; bn -= 16) {
+    for (int bn = cap; bn >= 96; bn -= step) {
         const int64_t waste = (N + bn - 1) / bn * bn - N;
         if (waste < best_waste) { best = bn; best_waste = waste; }
     }
@@ -433,10 +636,17 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
 
     TcParams p{};
     p.M = M; p.N = (int)N; p.K = (int)K;
-    // memory-bound shapes: <=192 columns and two staging tiles (drain and store overlap);
-    // compute-bound shapes (long K): 256 columns, one staging tile, deeper operand pipeline
-    p.nstg = (K >= 512 && N >= 256) ? 1 : 2;
-    p.BN = pick_bn(N, p.nstg == 1 ? 256 : 192);
+    static const int env_bn = getenv("MSU_TC_BN") ? atoi(getenv("MSU_TC_BN")) : 0;
+    static const int env_stages = getenv("MSU_TC_STAGES") ? atoi(getenv("MSU_TC_STAGES")) : 0;
+    static const int env_epi = getenv("MSU_TC_EPI") ? atoi(getenv("MSU_TC_EPI")) : 0;   // 1: force the generic epilogue
+    // unmapped outputs whose tile rows are consecutive leave through TMA stores (conv tiles: whole-row tiles only)
+    bool epi_tma = env_epi != 1 && E->map == MSU_MAP_NONE && !(E->R && E->H) && !(E->Cpre && (E->R || E->H)) &&
+                   E->ldr == E->ldc;
+    if (A->map == MSU_MAP_CONV3 && A->geo[1] % 128 != 0) epi_tma = false;
+    const int naux = E->Cpre ? 1 : ((E->R || E->H) ? 2 : 0);
+    p.epi_tma = epi_tma ? 1 : 0;
+    p.epi_bytes = epi_tma ? 2048 * (1 + naux) : ((TC_SCRATCH_BYTES + 1023) / 1024) * 1024;
+    p.BN = pick_bn(N, env_bn ? env_bn : 256, epi_tma ? 32 : 16);
     p.num_n_tiles = (int)((N + p.BN - 1) / p.BN);
     p.E = *E;
     CUtensorMap tmA, tmA2, tmB;
@@ -485,11 +695,33 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     p.a_stage = p.mode == 3 ? 17 * 1024 : TC_A_BYTES;
     p.b_stage = (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
     const int stage_bytes = p.a_stage + p.b_stage;
-    const int fixed_bytes = (2 * 8 + 8) * 8 + 16 + 4 * TC_BM * 8 + 2 * TC_BM * 4 + p.nstg * TC_BM * (p.BN + 8) * 2 + 1024;
-    p.stages = (226 * 1024 - fixed_bytes) / stage_bytes;
-    if (p.stages > 8) p.stages = 8;
+    // [operand stages][1 KB: barriers, TMEM slot][epilogue slabs] + 1 KB alignment slack
+    auto stages_for = [&](int sb) { int s_ = (227 * 1024 - 2048 - TC_EPI_WARPS * p.epi_bytes) / sb; return s_ > 8 ? 8 : s_; };
+    p.stages = stages_for(stage_bytes);
+    if (p.mode != 3 && p.BN > 192 && p.stages < 4 && !env_bn) {
+        // operand bytes in flight bound the mainloop: a narrower N tile that buys the 4th stage wins
+        const int bn2 = pick_bn(N, 192, epi_tma ? 32 : 16);
+        const int sb2 = p.a_stage + bn2 * TC_BK * 2;
+        if (stages_for(sb2) >= 4) {
+            p.BN = bn2;
+            p.num_n_tiles = (int)((N + p.BN - 1) / p.BN);
+            p.b_stage = p.BN * TC_BK * 2;
+            if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
+            p.stages = stages_for(sb2);
+        }
+    }
+    const int stage_bytes_final = p.a_stage + p.b_stage;
+    const int fixed_bytes = 2048 + TC_EPI_WARPS * p.epi_bytes;
+    if (env_stages && p.stages > env_stages) p.stages = env_stages;
     if (p.stages < 2) return 1;
-    const int smem = p.stages * stage_bytes + fixed_bytes;
+    const int smem = p.stages * stage_bytes_final + fixed_bytes;
+    CUtensorMap tmC = tmB, tmAux = tmB;
+    if (epi_tma) {
+        if (!make_map_slab(&tmC, E->C, M, N, E->ldc)) return 1;
+        const void* aux = E->Cpre ? E->Cpre : (E->R ? E->R : E->H);
+        const int64_t ldaux = E->Cpre ? E->ldc : (E->R ? E->ldr : E->ldh);
+        if (aux != nullptr && !make_map_slab(&tmAux, aux, M, N, ldaux)) return 1;
+    }
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -498,8 +730,35 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, p);
+    static const int trace_on = getenv("MSU_TC_TRACE") ? atoi(getenv("MSU_TC_TRACE")) : 0;
+    static long long* trace_buf = nullptr;
+    if (trace_on) {
+        if (trace_buf == nullptr) cudaMalloc(&trace_buf, 148 * 8 * 16 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 148 * 8 * 16 * sizeof(long long), st);
+        p.trace = trace_buf;
+    }
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     count_launch();
+    if (trace_on) {   // debug only: synchronous dump of the per-tile role timeline of two CTAs
+        static long long host[148 * 8 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost);
+        static const char* names[11] = {"prod_start", "prod_end", "mma_tempty", "mma_full0", "mma_commit", "epi_mapped",
+                                        "epi_tfull", "epi_done", "epi_c0_scratch", "epi_c0_stored", "epi_c0_ldtm"};
+        for (int cta : {0, 100}) {
+            if (cta >= grid) continue;
+            const long long t0 = host[(size_t)cta * 8 * 16];
+            fprintf(stderr, "[tc trace] M=%lld N=%d K=%d BN=%d stages=%d epw=%d cta %d\n", (long long)M, (int)N, (int)K, p.BN, p.stages, TC_EPI_WARPS, cta);
+            for (int it = 0; it < 8; it++) {
+                fprintf(stderr, "  tile %d:", it);
+                for (int ev = 0; ev < 11; ev++) {
+                    const long long v = host[((size_t)cta * 8 + it) * 16 + ev];
+                    fprintf(stderr, " %s=%lld", names[ev], v ? v - t0 : -1);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     return check_launch("gemm_tc");
 }
 

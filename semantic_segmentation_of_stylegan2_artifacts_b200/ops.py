@@ -81,28 +81,52 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     return e
 
 
-PROF = None  # bench.py sets this to a list to collect (tag, start_event, end_event) per GEMM launch
+PROF = None  # bench.py / tools set this to a list to collect (tag, start_event, end_event, bytes, flops) per launch
+
+
+def _p0():
+    if PROF is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _p1(e0, tag, nbytes=0, flops=0):
+    """tag = (M, N, K, kind); nbytes = algorithmic HBM bytes of the launch."""
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROF.append((tag, e0, e1, nbytes, flops))
 
 
 def gemm(A: MsuOperand, B: MsuOperand, E: MsuEpilogue, M: int, N: int, K: int, dev: torch.device) -> None:
     ws = workspace(dev)
-    if PROF is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    e0 = _p0()
     L.check(L.lib().msu_gemm(C.byref(A), C.byref(B), C.byref(E), M, N, K, ws.data_ptr(), ws.numel(), GEMM_BACKEND,
                              L.stream_ptr()), "msu_gemm")
-    if PROF is not None:
-        e1.record()
-        kind = ("wgrad" if A.orient == 1 else ("conv3x3" if A.map == MAP_CONV3 else "gemm"))
+    if e0 is not None:
+        es = 2 if A.dtype == BF16 else 4
+        if A.orient == 1:      # weight gradient: both [tokens, channels] operands read once, fp32 output
+            kind = "wgrad"
+            nb = K * (M + (N // 9 if B.map == MAP_CONV3 else N)) * es + M * N * 4
+        else:
+            kind = "conv3x3" if A.map == MAP_CONV3 else "gemm"
+            a_cols = K // 9 if A.map == MAP_CONV3 else K
+            outs = 1 + (E.Cpre is not None) + (E.R is not None) + (E.H is not None)
+            nb = (M * a_cols + N * K + outs * M * N) * es
         kind += "_tc" if L.lib().msu_last_gemm_backend() == 1 else "_simt"
-        PROF.append(((M, N, K, kind), e0, e1))
+        _p1(e0, (M, N, K, kind), nb, 2 * M * N * K)
 
 
 def colsum(X: MsuOperand, M: int, N: int, dev: torch.device) -> torch.Tensor:
     out = torch.empty(N, dtype=torch.float32, device=dev)
     ws = workspace(dev)
+    e0 = _p0()
     L.check(L.lib().msu_colsum(C.byref(X), M, N, out.data_ptr(), 0, ws.data_ptr(), ws.numel(), L.stream_ptr()),
             "msu_colsum")
+    _p1(e0, (M, N, 0, "colsum"), M * N * (2 if X.dtype == BF16 else 4))
     return out
 
 
@@ -119,9 +143,12 @@ def ln_fwd(x: torch.Tensor, gamma, beta, rows: int, Cdim: int, *, in_map=MAP_NON
     mean = torch.empty(ns, dtype=torch.float32, device=x.device)
     rstd = torch.empty(ns, dtype=torch.float32, device=x.device)
     g = _geo_arr(geo)
+    e0 = _p0()
     L.check(L.lib().msu_ln_fwd(L.dt(x), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
                                mean.data_ptr(), rstd.data_ptr(), rows, Cdim, in_map, out_map,
                                None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), L.stream_ptr()), "msu_ln_fwd")
+    _p1(e0, (rows, Cdim, 0, "ln_fwd" + ("_dot" if dotw is not None else "")),
+        (ns * Cdim + y.numel()) * x.element_size())
     return y, mean, rstd
 
 
@@ -133,6 +160,7 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     P = L.lib().msu_ln_bwd_partial_rows(L.dt(x), rows, Cdim)
     part = torch.empty(P * 3 * Cdim, dtype=torch.float32, device=dev)
     g = _geo_arr(geo)
+    e0 = _p0()
     L.check(L.lib().msu_ln_bwd(L.dt(x), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                mean.data_ptr(), rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), rows, Cdim, dy_map,
                                dx_map, None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), part.data_ptr(),
@@ -142,6 +170,8 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     dw = torch.empty(Cdim, dtype=torch.float32, device=dev) if dotw is not None else None
     L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), L.ptr(dw), 0,
                                         L.stream_ptr()), "msu_ln_param_reduce")
+    _p1(e0, (rows, Cdim, 0, "ln_bwd" + ("_dot" if dotw is not None else "") + ("_res" if dres is not None else "")),
+        (dy.numel() + (2 + (dres is not None)) * rows * Cdim) * x.element_size())
     return dx, dg, db, dw
 
 
@@ -154,8 +184,11 @@ def relbias_expand(table: torch.Tensor, nH: int) -> torch.Tensor:
 def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, geo) -> torch.Tensor:
     o = torch.empty(n_windows * 49, nH * 32, dtype=qkv.dtype, device=qkv.device)
     g = L.geo6(geo)
+    e0 = _p0()
     L.check(L.lib().msu_winattn_fwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), n_windows, nH,
                                     C.cast(g, C.c_void_p), L.stream_ptr()), "msu_winattn_fwd")
+    _p1(e0, (n_windows, nH, 0, "winattn_fwd"), (qkv.numel() + o.numel()) * qkv.element_size(),
+        2 * 2 * n_windows * nH * 49 * 49 * 32)
     return o
 
 
@@ -166,12 +199,15 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
     gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
     part = torch.empty(gx * nH * 2401, dtype=torch.float32, device=dev)
     g = L.geo6(geo)
+    e0 = _p0()
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
                                     dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p),
                                     L.stream_ptr()), "msu_winattn_bwd")
     dtable = torch.empty(169, nH, dtype=torch.float32, device=dev)
     L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
             "msu_relbias_reduce")
+    _p1(e0, (n_windows, nH, 0, "winattn_bwd"), (2 * qkv.numel() + 2 * o.numel()) * qkv.element_size(),
+        5 * 2 * n_windows * nH * 49 * 49 * 32)
     return dqkv, dtable
 
 
@@ -192,7 +228,9 @@ def patchify4(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 def gather_rows(src: MsuOperand, M: int, N: int, like: torch.Tensor) -> torch.Tensor:
     """Dense [M, N] copy of a mapped / scaled operand (same dtype as `like`)."""
     out = torch.empty(M, N, dtype=like.dtype, device=like.device)
+    e0 = _p0()
     L.check(L.lib().msu_gather_rows(C.byref(src), out.data_ptr(), M, N, L.stream_ptr()), "msu_gather_rows")
+    _p1(e0, (M, N, 0, "gather_rows"), 2 * M * N * like.element_size())
     return out
 
 

@@ -1,4 +1,5 @@
-"""Run a few representative tcgen05 GEMM launches (for ncu / timing). Usage: gemm_case.py [reps]"""
+"""Time representative tcgen05 GEMM launches of the training step (CUDA-graph of `reps` launches, device timed).
+Usage: gemm_case.py [reps] [case-name-substring ...]   (ncu: run with reps=1 and a case filter)"""
 import os
 import sys
 
@@ -8,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semantic_segmentation_of_stylegan2_artifacts_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+filt = sys.argv[2:]
 bf = torch.bfloat16
 
 
@@ -18,14 +20,35 @@ def fc1(M, N, K):
     b = torch.randn(N, device=dev)
     y = torch.empty(M, N, dtype=bf, device=dev)
     pre = torch.empty(M, N, dtype=bf, device=dev)
-    return lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=b, act=1), M, N, K, dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=b, act=1), M, N, K, dev),
+            2 * M * N * K, (M * K + 2 * M * N) * 2)
 
 
 def plain(M, N, K):
     a = torch.randn(M, K, device=dev).to(bf)
     w = (torch.randn(N, K, device=dev) * 0.1).to(bf)
     y = torch.empty(M, N, dtype=bf, device=dev)
-    return lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y), M, N, K, dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y), M, N, K, dev),
+            2 * M * N * K, (M * K + M * N) * 2)
+
+
+def resid(M, N, K):
+    a = torch.randn(M, K, device=dev).to(bf)
+    w = (torch.randn(N, K, device=dev) * 0.1).to(bf)
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).to(bf)
+    y = torch.empty(M, N, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, bias=b, R=r), M, N, K, dev),
+            2 * M * N * K, (M * K + 2 * M * N) * 2)
+
+
+def dgelu(M, N, K):
+    a = torch.randn(M, K, device=dev).to(bf)
+    w = (torch.randn(N, K, device=dev) * 0.1).to(bf)
+    h = torch.randn(M, N, device=dev).to(bf)
+    y = torch.empty(M, N, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, H=h, ldh=N), M, N, K, dev),
+            2 * M * N * K, (M * K + 2 * M * N) * 2)
 
 
 def conv(B, S, E):
@@ -33,24 +56,41 @@ def conv(B, S, E):
     w = (torch.randn(E, 9 * E, device=dev) * 0.05).to(bf)
     b = torch.randn(E, device=dev)
     y = torch.empty(B * S * S, E, dtype=bf, device=dev)
-    return lambda: ops.gemm(ops.operand(x, ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(w), ops.epilogue(y, bias=b),
-                            B * S * S, E, 9 * E, dev)
+    return (lambda: ops.gemm(ops.operand(x, ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(w), ops.epilogue(y, bias=b),
+                             B * S * S, E, 9 * E, dev), 2 * B * S * S * E * 9 * E, 2 * B * S * S * E * 2)
 
 
-cases = {"fc1_s0": (fc1(262144, 384, 96), 2 * 262144 * 384 * 96, (262144 * 96 + 2 * 262144 * 384) * 2),
-         "plain_s0": (plain(262144, 384, 96), 2 * 262144 * 384 * 96, (262144 * 96 + 262144 * 384) * 2),
-         "fc1_s2": (fc1(16384, 1536, 384), 2 * 16384 * 1536 * 384, (16384 * 384 + 2 * 16384 * 1536) * 2),
-         "plain_big": (plain(8192, 4096, 4096), 2 * 8192 * 4096 * 4096, 0),
-         "conv_b4": (conv(4, 512, 96), 2 * 4 * 512 * 512 * 96 * 864, 2 * 4 * 512 * 512 * 96 * 2)}
-for name, (fn, flops, byts) in cases.items():
+cases = {
+    "fc1_s0": lambda: fc1(262144, 384, 96), "fc2_s0": lambda: resid(262144, 96, 384),
+    "dh_s0": lambda: dgelu(262144, 384, 96), "qkv_s0": lambda: plain(283024, 288, 96),
+    "fc1_s1": lambda: fc1(65536, 768, 192), "fc2_s1": lambda: resid(65536, 192, 768),
+    "fc1_s2": lambda: fc1(16384, 1536, 384), "plain_s2": lambda: plain(16384, 1536, 384),
+    "dh_s2": lambda: dgelu(16384, 1536, 384), "fc2_s2": lambda: resid(16384, 384, 1536),
+    "dxn_s2": lambda: plain(16384, 384, 1536), "qkv_s2": lambda: plain(19600, 1152, 384),
+    "proj_s2": lambda: plain(19600, 384, 384), "fc1_s3": lambda: fc1(4096, 3072, 768),
+    "plain_big": lambda: plain(8192, 4096, 4096), "conv_b16": lambda: conv(16, 512, 96),
+}
+for name, mk in cases.items():
+    if filt and not any(f in name for f in filt):
+        continue
+    fn, flops, byts = mk()
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
+    if reps > 1:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
+    if reps > 1:
+        g.replay()
+    else:
         fn()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"{name:10s} {ms * 1e3:9.1f} us  {flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s")
+    print(f"{name:10s} {ms * 1e3:9.1f} us  {flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s", flush=True)
