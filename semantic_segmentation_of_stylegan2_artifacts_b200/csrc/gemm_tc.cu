@@ -787,7 +787,8 @@ constexpr int WG_THREADS = 192;
 
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
+                const __grid_constant__ CUtensorMap tmW, const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int A_BYTES = p.MT * 2 * WG_BOX_BYTES;
@@ -798,6 +799,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint8_t* sSlab = smem + (size_t)p.stages * (A_BYTES + B_BYTES) + 1024;   // [4 warps][2][4 KB] fp32 output slabs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // work decomposition: blockIdx.x = (split * n_super + sup) * n_q_tiles + qt
@@ -862,29 +864,52 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
             tc_commit(tfull);
         }
     } else {
+        // epilogue: TMEM -> fp32 [32 x 32] slab (128B swizzle) -> TMA store into this split's partial [I, J]
+        // (coalesced 128 B rows, out-of-range rows / columns clipped by the tensor map)
         const int quad = warp & 3;
+        uint8_t* slab = sSlab + (size_t)(warp - 2) * 2 * 4096;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        float* wsz = p.ws + (int64_t)split * p.I * p.J;
+        int nb = 0;
         for (int mt = 0; mt < p.MT; mt++) {
-            const int pr = p0 + mt * 128 + quad * 32 + lane;   // M-side channel of this thread
-            for (int c = 0; c < p.BN / 16; c++) {
-                float v[16];
-                tc_ld16(tmem_base + mt * p.BN + c * 16 + ((uint32_t)(quad * 32) << 16), v);
+            const int prow0 = p0 + mt * 128 + quad * 32;       // first M-side channel of this warp's slab
+            for (int c = 0; c < (p.BN + 31) / 32; c++) {
+                const int cols = p.BN - c * 32 >= 32 ? 32 : 16;
+                uint32_t raw[32];
+                if (cols == 32) tc_ld32_nowait(tmem_base + mt * p.BN + c * 32 + ((uint32_t)(quad * 32) << 16), raw);
+                else tc_ld16_nowait(tmem_base + mt * p.BN + c * 32 + ((uint32_t)(quad * 32) << 16), raw);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab nb was stored two chunks ago
+                __syncwarp();
+                tc_ld_wait();
+                if (prow0 >= p.Pn) continue;                   // warp-uniform: the whole slab is out of range
+                uint8_t* sl = slab + nb * 4096;
                 if (KB == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    for (int i = 0; i < 32; i++) raw[i] = 0u;
                 }
-                if (pr >= p.Pn) continue;
+                if (!p.swap) {          // slab[row = lane (i)][col = j]: 8 x 16 B per lane
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int qc = q0 + c * 16 + i;
-                    if (qc >= p.Qn) break;
-                    if (p.swap) wsz[(int64_t)qc * p.J + pr] = v[i];
-                    else wsz[(int64_t)pr * p.J + qc] = v[i];
+                    for (int g = 0; g < 8; g++)
+                        if (g * 4 < cols)
+                            *reinterpret_cast<uint4*>(sl + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                                make_uint4(raw[g * 4], raw[g * 4 + 1], raw[g * 4 + 2], raw[g * 4 + 3]);
+                } else {                // transposed: slab[row = q (i)][col = lane (j)]
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (i < cols)
+                            *reinterpret_cast<uint32_t*>(sl + i * 128 + (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4) = raw[i];
                 }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!p.swap) tma_store_3d(sl, &tmW, q0 + c * 32, prow0, split);
+                    else tma_store_3d(sl, &tmW, prow0, q0 + c * 32, split);
+                    tma_store_commit();
+                }
+                nb ^= 1;
             }
         }
+        if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -1123,10 +1148,10 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     // output tiles, few splits -> small deterministic split-K partial traffic.
     const bool out_heavy = (int64_t)I * J * 8 > T * (I + J);
     if (out_heavy) {
-        p.BN = p.Qn <= 128 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 128);
+        p.BN = p.Qn <= 128 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 128, 32);   // several q tiles: whole 32-column store boxes
         p.MT = 1;
     } else {
-        p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn);
+        p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 256, 32);
         p.MT = m_tiles < 4 ? m_tiles : 4;
     }
     p.n_q_tiles = (p.Qn + p.BN - 1) / p.BN;
@@ -1136,7 +1161,7 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     while (p.MT > 1 && 2 * (p.MT * 2 + p.qboxes) * WG_BOX_BYTES > 200 * 1024) p.MT--;
     p.n_super = (m_tiles + p.MT - 1) / p.MT;
     const int stage_bytes = (p.MT * 2 + p.qboxes) * WG_BOX_BYTES;
-    p.stages = (200 * 1024) / stage_bytes;
+    p.stages = (193 * 1024) / stage_bytes;
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return 1;
     const int base_ctas = p.n_super * p.n_q_tiles;
@@ -1152,14 +1177,25 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     CUtensorMap tmP, tmQ;
     if (!make_map_2d_box64(&tmP, P->ptr, T, p.Pn, P->ld)) return 1;
     if (!make_map_2d_box64(&tmQ, Q->ptr, T, p.Qn, Q->ld)) return 1;
-    const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+    // partials ws[split][I][J] fp32 as a 3-D map, box = [32 cols, 32 rows, 1], 128B swizzle
+    CUtensorMap tmW;
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)J, (cuuint64_t)I, (cuuint64_t)splits};
+        cuuint64_t gstr[2] = {(cuuint64_t)J * 4, (cuuint64_t)I * J * 4};
+        cuuint32_t box[3] = {32, 32, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (get_encode()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    }
+    const int smem = p.stages * stage_bytes + 1024 + 4 * 2 * 4096 + 1024;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
-    wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, p);
+    wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, tmW, p);
     count_launch();
     launch_splitk_reduce(*E, I, J, splits, ws, st);
     return check_launch("wgrad_tc");

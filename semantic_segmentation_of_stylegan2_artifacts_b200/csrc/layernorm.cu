@@ -46,6 +46,19 @@ template <> struct VecW<__nv_bfloat16> {
         *reinterpret_cast<uint4*>(p) = r;
     }
 };
+// raw 16 B vector (kept packed in registers) and its conversion
+template <typename T> __device__ __forceinline__ void cvt_raw(const uint4& r, float* o);
+template <> __device__ __forceinline__ void cvt_raw<float>(const uint4& r, float* o) {
+    o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void cvt_raw<__nv_bfloat16>(const uint4& r, float* o) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __bfloat1622float2(h[i]);
+        o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+}
 __device__ __forceinline__ void ldf(const float* p, float* o, int n) {
     for (int i = 0; i < n; i += 4) {
         const float4 v = *reinterpret_cast<const float4*>(p + i);
@@ -64,89 +77,111 @@ __device__ __forceinline__ int64_t merge_off(const MergeGeo& mg, int64_t lr, int
     return (b * (int64_t)(mg.H * mg.W) + y * mg.W + x) * Cin + ci;
 }
 
+// Forward: every warp owns LN_RG row groups (rpw rows each) whose 16 B loads are all issued before the first
+// reduction, so ~2x the bytes are in flight per warp (the one-group version topped out at 3.4 TB/s).
+constexpr int LN_RG = 2;
 template <typename T, int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ Y,
                                                               float* __restrict__ mean, float* __restrict__ rstd,
                                                               int64_t rows, int C, int lpr, int in_map, int out_map,
                                                               WinGeo wg, MergeGeo mg, const float* __restrict__ dotw) {
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
-    const int64_t r = ((int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * rpw + sub;
-    const bool in_range = r < rows;
-    int64_t lr = r;  // LayerNorm row (statistics index)
-    bool pad = false;
-    if (in_range && out_map == MSU_MAP_WINDOW) {
-        lr = win_to_pix(wg, r);
-        pad = lr < 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
-    }
-    const bool live = in_range && !pad;
     constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
-    float x[NV][VW];
-    float s = 0.f;
+    const int64_t wbase = ((int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_RG;
+    int64_t r[LN_RG], lr[LN_RG];
+    bool in_range[LN_RG], pad[LN_RG];
+    uint4 xr[LN_RG][NV];
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * VW;
-#pragma unroll
-        for (int e = 0; e < VW; e++) x[j][e] = 0.f;
-        if (live && c < C) {
-            const T* p = (in_map == MSU_MAP_MERGE) ? X + merge_off(mg, lr, c, Cin) : X + lr * C + c;
-            VecW<T>::ld(p, x[j]);
-#pragma unroll
-            for (int e = 0; e < VW; e++) s += x[j][e];
+    for (int g = 0; g < LN_RG; g++) {
+        r[g] = (wbase + g) * rpw + sub;
+        in_range[g] = r[g] < rows;
+        lr[g] = r[g];       // LayerNorm row (statistics index)
+        pad[g] = false;
+        if (in_range[g] && out_map == MSU_MAP_WINDOW) {
+            lr[g] = win_to_pix(wg, r[g]);
+            pad[g] = lr[g] < 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
         }
-    }
-    const float mu = group_sum(s, lpr) / C;
-    float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * VW;
-        if (c < C) {
-#pragma unroll
-            for (int e = 0; e < VW; e++) { const float a = x[j][e] - mu; v = fmaf(a, a, v); }
-        }
-    }
-    const float rs = 1.0f / sqrtf(group_sum(v, lpr) / C + LN_EPS);
-    if (live && l == 0) {
-        mean[lr] = mu;
-        rstd[lr] = rs;
-    }
-    float dot = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * VW;
-        if (in_range && c < C) {
-            float y[VW];
-#pragma unroll
-            for (int e = 0; e < VW; e++) y[e] = 0.f;
-            if (!pad) {
-                float g[VW], b[VW];
-                ldf(gamma + c, g, VW);
-                ldf(beta + c, b, VW);
-#pragma unroll
-                for (int e = 0; e < VW; e++) y[e] = (x[j][e] - mu) * rs * g[e] + b[e];
-            }
-            if (dotw != nullptr) {
-                float w[VW];
-                ldf(dotw + c, w, VW);
-#pragma unroll
-                for (int e = 0; e < VW; e++) dot = fmaf(y[e], w[e], dot);
-            } else {
-                VecW<T>::st(Y + r * C + c, y);
+        for (int j = 0; j < NV; j++) {
+            const int c = (l + lpr * j) * VW;
+            xr[g][j] = make_uint4(0, 0, 0, 0);
+            if (in_range[g] && !pad[g] && c < C) {
+                const T* p = (in_map == MSU_MAP_MERGE) ? X + merge_off(mg, lr[g], c, Cin) : X + lr[g] * C + c;
+                xr[g][j] = *reinterpret_cast<const uint4*>(p);
             }
         }
     }
-    if (dotw != nullptr) {
-        dot = group_sum(dot, lpr);
-        if (in_range && l == 0) Y[r] = from_f<T>(dot);
+#pragma unroll
+    for (int g = 0; g < LN_RG; g++) {
+        const bool live = in_range[g] && !pad[g];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            float x[VW];
+            cvt_raw<T>(xr[g][j], x);
+#pragma unroll
+            for (int e = 0; e < VW; e++) s += x[e];
+        }
+        const float mu = group_sum(s, lpr) / C;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c = (l + lpr * j) * VW;
+            if (c < C) {
+                float x[VW];
+                cvt_raw<T>(xr[g][j], x);
+#pragma unroll
+                for (int e = 0; e < VW; e++) { const float a = x[e] - mu; v = fmaf(a, a, v); }
+            }
+        }
+        const float rs = 1.0f / sqrtf(group_sum(v, lpr) / C + LN_EPS);
+        if (live && l == 0) {
+            mean[lr[g]] = mu;
+            rstd[lr[g]] = rs;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c = (l + lpr * j) * VW;
+            if (in_range[g] && c < C) {
+                float y[VW];
+#pragma unroll
+                for (int e = 0; e < VW; e++) y[e] = 0.f;
+                if (!pad[g]) {
+                    float x[VW], gm[VW], b[VW];
+                    cvt_raw<T>(xr[g][j], x);
+                    ldf(gamma + c, gm, VW);
+                    ldf(beta + c, b, VW);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) y[e] = (x[e] - mu) * rs * gm[e] + b[e];
+                }
+                if (dotw != nullptr) {
+                    float w[VW];
+                    ldf(dotw + c, w, VW);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) dot = fmaf(y[e], w[e], dot);
+                } else {
+                    VecW<T>::st(Y + r[g] * C + c, y);
+                }
+            }
+        }
+        if (dotw != nullptr) {
+            dot = group_sum(dot, lpr);
+            if (in_range[g] && l == 0) Y[r[g]] = from_f<T>(dot);
+        }
     }
 }
 
 // Backward: warp w walks row groups  w, w + P, ...  (P = number of warps) and keeps the per-column parameter-gradient
 // partial sums in registers; partial[w][3][C] is reduced afterwards in a fixed order (deterministic).
+// Operands stay packed (16 B) in registers between the two passes over a row and the residual gradient is requested
+// together with x and dy, so a row group costs ONE memory round trip and the kernel fits 2 blocks (16 warps) per SM:
+// ~75 KB of loads in flight per SM instead of 24 KB (the first version ran at 8 warps/SM and ~1.4 TB/s).
 template <typename T, int NV, bool DOT>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ X,
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ X,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const T* __restrict__ dRes, T* __restrict__ dX, int64_t rows,
@@ -159,103 +194,136 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
     const int64_t P = (int64_t)gridDim.x * LN_WARPS;
     constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
-    float ag[NV][VW], ab[NV][VW], aw[DOT ? NV : 1][VW], gm[NV][VW];
+    // ag = sum dy * x-hat (DOT: sum dl * x-hat), ab = sum dy (DOT: the scalar sum dl lives in ab[0][0])
+    float ag[NV][VW], ab[DOT ? 1 : NV][DOT ? 1 : VW];
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int c = (l + lpr * j) * VW;
 #pragma unroll
-        for (int e = 0; e < VW; e++) ag[j][e] = ab[j][e] = aw[DOT ? j : 0][e] = gm[j][e] = 0.f;
-        if (c < C) ldf(gamma + c, gm[j], VW);
+        for (int e = 0; e < VW; e++) {
+            ag[j][e] = 0.f;
+            if (!DOT) ab[DOT ? 0 : j][DOT ? 0 : e] = 0.f;
+        }
     }
+    if (DOT) ab[0][0] = 0.f;
 
     for (int64_t g0 = wid * rpw; g0 < rows; g0 += P * rpw) {
         const int64_t lr = g0 + sub;
         const bool live = lr < rows;
         const float mu = live ? mean[lr] : 0.f, rs = live ? rstd[lr] : 0.f;
+        const float nmr = -mu * rs;
         const int64_t dyr = (live && dy_map == MSU_MAP_WINDOW) ? pix_to_win(wg, lr) : lr;
         const float dl = (DOT && live) ? to_f<T>(dY[lr]) : 0.f;
-        float x[NV][VW], dy[NV][VW];
+        const int64_t rowoff = lr * C;
+        uint4 xr[NV], yr[DOT ? 1 : NV], rr[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c = (l + lpr * j) * VW;
+            if (live && c < C) {
+                const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
+                xr[j] = *reinterpret_cast<const uint4*>(X + xo);
+                if (!DOT) yr[DOT ? 0 : j] = *reinterpret_cast<const uint4*>(dY + dyr * C + c);
+                if (dRes != nullptr) rr[j] = *reinterpret_cast<const uint4*>(dRes + xo);
+            }
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
-#pragma unroll
-            for (int e = 0; e < VW; e++) x[j][e] = dy[j][e] = 0.f;
             if (live && c < C) {
-                const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : lr * C + c;
-                VecW<T>::ld(X + xo, x[j]);
+                float x[VW], dy[VW], gm[VW];
+                cvt_raw<T>(xr[j], x);
+                ldf(gamma + c, gm, VW);
                 if (DOT) {
-                    float w[VW];
-                    ldf(dotw + c, w, VW);
+                    ldf(dotw + c, dy, VW);
 #pragma unroll
-                    for (int e = 0; e < VW; e++) dy[j][e] = dl * w[e];
+                    for (int e = 0; e < VW; e++) dy[e] *= dl;
                 } else {
-                    VecW<T>::ld(dY + dyr * C + c, dy[j]);
+                    cvt_raw<T>(yr[DOT ? 0 : j], dy);
                 }
 #pragma unroll
                 for (int e = 0; e < VW; e++) {
-                    x[j][e] = (x[j][e] - mu) * rs;          // x-hat
-                    const float g = dy[j][e] * gm[j][e];
+                    const float g = dy[e] * gm[e];
                     s1 += g;
-                    s2 = fmaf(g, x[j][e], s2);
+                    s2 = fmaf(g, fmaf(x[e], rs, nmr), s2);
                 }
             }
         }
         s1 = group_sum(s1, lpr) / C;
         s2 = group_sum(s2, lpr) / C;
+        const float k1 = -s1 * rs;
+        if (DOT) ab[0][0] += dl;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
             if (live && c < C) {
-                const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : lr * C + c;
-                float dx[VW];
+                float x[VW], dy[VW], gm[VW], dx[VW];
+                cvt_raw<T>(xr[j], x);
+                ldf(gamma + c, gm, VW);
+                if (DOT) {
+                    ldf(dotw + c, dy, VW);
 #pragma unroll
-                for (int e = 0; e < VW; e++) dx[e] = rs * (dy[j][e] * gm[j][e] - s1 - x[j][e] * s2);
-                if (dRes != nullptr) {
-                    float d[VW];
-                    VecW<T>::ld(dRes + xo, d);
-#pragma unroll
-                    for (int e = 0; e < VW; e++) dx[e] += d[e];
+                    for (int e = 0; e < VW; e++) dy[e] *= dl;
+                } else {
+                    cvt_raw<T>(yr[DOT ? 0 : j], dy);
                 }
-                int64_t wo = xo;
+                if (dRes != nullptr) cvt_raw<T>(rr[j], dx);
+                else {
+#pragma unroll
+                    for (int e = 0; e < VW; e++) dx[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < VW; e++) {
+                    const float xh = fmaf(x[e], rs, nmr);                 // x-hat
+                    // dx = rs * (dy*gamma - s1 - xh*s2) + dres
+                    dx[e] += fmaf(dy[e] * gm[e], rs, fmaf(-xh * s2, rs, k1));
+                    ag[j][e] = fmaf(DOT ? dl : dy[e], xh, ag[j][e]);
+                    if (!DOT) ab[DOT ? 0 : j][DOT ? 0 : e] += dy[e];
+                }
+                int64_t wo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
                 if (dx_map == MSU_MAP_UNSHUFFLE) {   // gradient written straight in the inverse depth-to-space layout
                     const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, ug.geo, lr, c);
                     wo = rc.row * (int64_t)(ug.geo[2] * ug.geo[2] * ug.geo[3]) + rc.col;
                 }
                 VecW<T>::st(dX + wo, dx);
-#pragma unroll
-                for (int e = 0; e < VW; e++) {
-                    ag[j][e] = fmaf(dy[j][e], x[j][e], ag[j][e]);
-                    ab[j][e] += dy[j][e];
-                }
-                if (DOT) {
-                    float b[VW];
-                    ldf(beta + c, b, VW);
-#pragma unroll
-                    for (int e = 0; e < VW; e++) aw[DOT ? j : 0][e] = fmaf(dl, x[j][e] * gm[j][e] + b[e], aw[DOT ? j : 0][e]);
-                }
             }
         }
     }
     // fold the row groups of this warp (lanes l, l+lpr, ...) in a fixed order, then one partial row per warp
     float* pg = partial + wid * 3 * (int64_t)C;
+    float s0 = 0.f;
+    if (DOT) {
+        s0 = ab[0][0];
+        for (int o = lpr; o < 32; o <<= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    }
 #pragma unroll
     for (int j = 0; j < NV; j++) {
         for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
             for (int e = 0; e < VW; e++) {
                 ag[j][e] += __shfl_xor_sync(0xffffffffu, ag[j][e], o);
-                ab[j][e] += __shfl_xor_sync(0xffffffffu, ab[j][e], o);
-                if (DOT) aw[DOT ? j : 0][e] += __shfl_xor_sync(0xffffffffu, aw[DOT ? j : 0][e], o);
+                if (!DOT) ab[DOT ? 0 : j][DOT ? 0 : e] += __shfl_xor_sync(0xffffffffu, ab[DOT ? 0 : j][DOT ? 0 : e], o);
             }
         }
         const int c = (l + lpr * j) * VW;
         if (sub == 0 && c < C) {
+            if (DOT) {   // dy = dl * w: dgamma = w S1, dbeta = w S0, d(dot weight) = gamma S1 + beta S0
+                float w[VW], gm[VW], bt[VW];
+                ldf(dotw + c, w, VW);
+                ldf(gamma + c, gm, VW);
+                ldf(beta + c, bt, VW);
 #pragma unroll
-            for (int e = 0; e < VW; e += 4) {
-                *reinterpret_cast<float4*>(pg + c + e) = make_float4(ag[j][e], ag[j][e + 1], ag[j][e + 2], ag[j][e + 3]);
-                *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(ab[j][e], ab[j][e + 1], ab[j][e + 2], ab[j][e + 3]);
-                if (DOT) *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(aw[DOT ? j : 0][e], aw[DOT ? j : 0][e + 1], aw[DOT ? j : 0][e + 2], aw[DOT ? j : 0][e + 3]);
+                for (int e = 0; e < VW; e += 4) {
+                    *reinterpret_cast<float4*>(pg + c + e) = make_float4(w[e] * ag[j][e], w[e + 1] * ag[j][e + 1], w[e + 2] * ag[j][e + 2], w[e + 3] * ag[j][e + 3]);
+                    *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(w[e] * s0, w[e + 1] * s0, w[e + 2] * s0, w[e + 3] * s0);
+                    *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(fmaf(gm[e], ag[j][e], bt[e] * s0), fmaf(gm[e + 1], ag[j][e + 1], bt[e + 1] * s0),
+                                                                                 fmaf(gm[e + 2], ag[j][e + 2], bt[e + 2] * s0), fmaf(gm[e + 3], ag[j][e + 3], bt[e + 3] * s0));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VW; e += 4) {
+                    *reinterpret_cast<float4*>(pg + c + e) = make_float4(ag[j][e], ag[j][e + 1], ag[j][e + 2], ag[j][e + 3]);
+                    *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(ab[DOT ? 0 : j][DOT ? 0 : e], ab[DOT ? 0 : j][DOT ? 0 : e + 1], ab[DOT ? 0 : j][DOT ? 0 : e + 2], ab[DOT ? 0 : j][DOT ? 0 : e + 3]);
+                }
             }
         }
     }
@@ -298,7 +366,7 @@ static int launch_fwd(const void* X, const float* gamma, const float* beta, void
     MergeGeo mg{0, 0};
     if (out_map == MSU_MAP_WINDOW) wg = make_wingeo(geo);
     if (in_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
-    const int rpb = LN_WARPS * (32 / lpr);
+    const int rpb = LN_WARPS * (32 / lpr) * LN_RG;
     const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
     ln_fwd_kernel<T, NV><<<grid, LN_WARPS * 32, 0, st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd, rows, C, lpr, in_map,
                                                         out_map, wg, mg, dotw);
@@ -363,12 +431,12 @@ extern "C" int msu_ln_fwd(int dtype, const void* X, const float* gamma, const fl
     MSU_REQUIRE(false, "msu_ln_fwd: unsupported dtype %d", dtype);
 }
 
-// number of partial rows P = grid*8 warps: enough warps to cover the SMs, bounded by a 32 MiB workspace
+// number of partial rows P = grid*8 warps: 2 resident blocks per SM, bounded so that the fp32 partial rows stay small
 extern "C" int msu_ln_bwd_partial_rows(int dtype, int64_t rows, int32_t C) {
     const int rpw = 32 / pick_lpr(C, dtype == MSU_F32 ? 4 : 8);
-    int64_t P = imin((rows + rpw - 1) / rpw, (int64_t)num_sms() * 32);
+    int64_t P = imin((rows + rpw - 1) / rpw, (int64_t)num_sms() * 2 * LN_WARPS);
     P = imin(P, (8ll << 20) / (3ll * C));
-    P = imin(P, imax(LN_WARPS, rows / 16));   // keep the fp32 partial rows (3*C floats each) small next to the row data
+    P = imin(P, imax(LN_WARPS, rows / 8));    // keep the fp32 partial rows (3*C floats each) small next to the row data
     const int grid = (int)imax(1, (P + LN_WARPS - 1) / LN_WARPS);
     return grid * LN_WARPS;
 }

@@ -13,19 +13,25 @@ bf = torch.bfloat16
 
 
 def timeit(fn, reps=10):
+    """Device time per call: `reps` calls captured in one CUDA graph (no CPU launch overhead in the number)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
 
-for (B, H, C) in [(16, 128, 96), (16, 64, 192), (16, 32, 384)]:
+for (B, H, C) in [(16, 128, 96), (16, 64, 192), (16, 32, 384), (16, 16, 768)]:
     T = B * H * H
     x = torch.randn(T, C, device=dev).to(bf)
     dy = torch.randn(T, C, device=dev).to(bf)
@@ -48,3 +54,16 @@ for (B, H, C) in [(16, 128, 96), (16, 64, 192), (16, 32, 384)]:
     print(f"colsum         T={T} C={C}: {ms*1e3:7.1f} us  {T*C*2/ms/1e6:7.0f} GB/s")
     ms = timeit(lambda: ops.gather_rows(ops.operand(x, map=ops.MAP_WINDOW, geo=geo), Tw, C, x))
     print(f"gather window  T={T} C={C}: {ms*1e3:7.1f} us  {(T+Tw)*C*2/ms/1e6:7.0f} GB/s")
+
+# head: LayerNorm(96) fused with the 1x1 conv, 16 x 512 x 512 pixels
+T, C = 16 * 512 * 512, 96
+x = torch.randn(T, C, device=dev).to(bf)
+w = torch.ones(C, device=dev)
+b = torch.zeros(C, device=dev)
+ow = torch.randn(C, device=dev)
+y, mean, rstd = ops.ln_fwd(x, w, b, T, C, dotw=ow)
+ms = timeit(lambda: ops.ln_fwd(x, w, b, T, C, dotw=ow), 3)
+print(f"ln_fwd head    T={T} C={C}: {ms*1e3:7.1f} us  {(T*C*2+T*2)/ms/1e6:7.0f} GB/s")
+dl = torch.randn(T, device=dev).to(bf)
+ms = timeit(lambda: ops.ln_bwd(dl, x, w, b, mean, rstd, T, C, dotw=ow), 3)
+print(f"ln_bwd head    T={T} C={C}: {ms*1e3:7.1f} us  {(2*T*C*2+T*2)/ms/1e6:7.0f} GB/s")
