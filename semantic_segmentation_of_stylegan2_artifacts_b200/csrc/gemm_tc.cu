@@ -31,7 +31,8 @@ namespace msu {
 struct TcParams {
     int64_t M;
     int N, K, BN, num_m_tiles, num_n_tiles;
-    int mode;                 // 0 plain, 1 dual, 2 conv3x3
+    int mode;                 // 0 plain, 1 dual, 2 conv3x3 (shifted boxes), 3 conv3x3 halo rows, 4 conv3x3 halo rows x 2 image rows (BK = 32)
+    int nacc;                 // accumulators (128-row segments) per tile: 2 in mode 4
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
     int stages;               // operand pipeline depth
@@ -98,6 +99,26 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// K-major, 64B-swizzled descriptor (rows of 32 bf16 = 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64_g(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+    return d;
+}
+constexpr int TC_HALO32_BYTES = 8704;       // 130 pixels x 64 B (8320) rounded up to the 512 B swizzle period
+
+// first logical row of accumulator `r` of m-tile `mt` (conv modes: tiles are image-row segments)
+__device__ __forceinline__ int64_t tile_row0(const TcParams& p, int mt, int r) {
+    if (p.mode < 2) return (int64_t)mt * TC_BM;
+    const int per_img = p.tiles_x * p.tiles_y;
+    const int cb = mt / per_img, rr = mt % per_img;
+    return ((int64_t)cb * p.H + (rr / p.tiles_x) * p.bmh + r) * p.W + (rr % p.tiles_x) * p.bmw;
+}
+
 // 16 B chunk g of row `row` inside a [32 rows x 64 B] SWIZZLE_64B slab (1 KB aligned): chunk ^= (row / 2) % 4
 __device__ __forceinline__ uint32_t slab_off(int row, int g) { return (uint32_t)(row * 64 + ((g ^ ((row >> 1) & 3)) << 4)); }
 
@@ -157,6 +178,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* a_dst = sA + (size_t)stage * p.a_stage;
                     uint8_t* b_dst = sB + (size_t)stage * p.b_stage;
+                    if (p.mode == 4) {
+                        // two image rows per tile share the three weight tiles of (dy, 32-channel block): halo rows of
+                        // 130 pixels x 32 channels (64B swizzle), K = 9C walked in exact 32-channel steps (no zero padding)
+                        const int dyi = kb / p.cblocks, c0 = (kb % p.cblocks) * 32;
+                        const int bb = p.BN * 64;
+                        mbar_arrive_expect_tx(&full[stage], 2 * 130 * 64 + 3 * bb);
+                        tma_load_4d(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
+                        tma_load_4d(a_dst + TC_HALO32_BYTES, &tmA, &full[stage], c0, cx - 1, cy + dyi, cb);
+                        for (int dx = 0; dx < 3; dx++)
+                            tma_load_2d(b_dst + dx * bb, &tmB, &full[stage], (dyi * 3 + dx) * p.C + c0, nt * p.BN);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (p.mode == 3) {
                         // halo row: 130 pixels x 64 channels once per (dy, channel block); the three dx taps are
                         // row-shifted views of it.  Three weight tiles ride in the same stage.
@@ -205,7 +239,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (kb == 0) TC_TRACE(3);
                     const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage);
                     const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage);
-                    if (p.mode == 3) {
+                    if (p.mode == 4) {
+                        const int bb = p.BN * 64;
+                        for (int r = 0; r < 2; r++) {
+                            for (int dx = 0; dx < 3; dx++) {   // pixel shift = +64 B (swizzle follows the address bits)
+                                const uint64_t adesc = make_desc_kmajor_sw64_g(a_addr + r * TC_HALO32_BYTES + dx * 64);
+                                const uint64_t bdesc = make_desc_kmajor_sw64_g(b_addr + dx * bb);
+                                tc_mma_bf16(d_tmem + r * 128, adesc, bdesc, idesc, (kb | dx) != 0);
+                                tc_mma_bf16(d_tmem + r * 128, adesc + 2, bdesc + 2, idesc, 1);
+                            }
+                        }
+                    } else if (p.mode == 3) {
                         for (int dx = 0; dx < 3; dx++) {
                             // A rows shifted by dx pixels = start address + dx*128 B.  The 128B swizzle is a function of
                             // the shared-memory address bits (measured: base-offset field must stay 0), so a row-shifted
@@ -251,24 +295,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
-            int64_t m0;                                   // first logical row of the tile (rows are consecutive on this path)
-            if (p.mode >= 2) {
-                const int per_img = p.tiles_x * p.tiles_y;
-                const int cb = mt / per_img, rr = mt % per_img;
-                m0 = ((int64_t)cb * p.H + (rr / p.tiles_x) * p.bmh) * p.W + (rr % p.tiles_x) * p.bmw;
-            } else {
-                m0 = (int64_t)mt * TC_BM;
-            }
-            const int row0 = (int)(m0 + quad * 32);       // first row of this warp's slab
-            float rs = 1.0f;
-            if (E.rowscale != nullptr) {
-                const int64_t m_own = m0 + quad * 32 + lane;
-                rs = m_own < p.M ? E.rowscale[m_own / E.rows_per_sample] : 0.0f;
-            }
+            // chunk list of this warp: cc = r * nchunks + c over the tile's accumulators r (consecutive row segments)
+            const int nch_tot = p.nacc * nchunks;
             const int c_first = (sub + it) % NSUB;
-            if (aux_in && c_first < nchunks && lane == 0) {   // operand slab of the first chunk
+            auto row0_of = [&](int cc) { return (int)(tile_row0(p, mt, cc / nchunks) + quad * 32); };
+            if (aux_in && c_first < nch_tot && lane == 0) {   // operand slab of the first chunk
                 mbar_arrive_expect_tx(&abar[aux_buf], 2048);
-                tma_load_2d(slab_aux + aux_buf * 2048, &tmAux, &abar[aux_buf], nt * p.BN + c_first * TC_CW, row0);
+                tma_load_2d(slab_aux + aux_buf * 2048, &tmAux, &abar[aux_buf], nt * p.BN + (c_first % nchunks) * TC_CW, row0_of(c_first));
             }
             if (warp == 2) TC_TRACE(5);
             mbar_wait(&tfull[acc], acc_phase);
@@ -277,17 +310,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
             bool released = false;
             bool first = true;
-            for (int c = c_first; c < nchunks; c += NSUB) {
+            for (int cc = c_first; cc < nch_tot; cc += NSUB) {
+                const int r = cc / nchunks, c = cc - r * nchunks;
                 uint32_t raw[TC_CW];
-                tc_ld32_nowait(t_base + c * TC_CW, raw);
+                tc_ld32_nowait(t_base + r * 128 + c * TC_CW, raw);
                 const int n0 = nt * p.BN + c * TC_CW;
-                if (aux_in && c + NSUB < nchunks && lane == 0) {   // next chunk's operand slab (its buffer was drained a chunk ago)
+                const int row0 = row0_of(cc);
+                float rs = 1.0f;
+                if (E.rowscale != nullptr) {
+                    const int64_t m_own = (int64_t)row0 + lane;
+                    rs = m_own < p.M ? E.rowscale[m_own / E.rows_per_sample] : 0.0f;
+                }
+                if (aux_in && cc + NSUB < nch_tot && lane == 0) {   // next chunk's operand slab (its buffer was drained a chunk ago)
+                    const int cn = cc + NSUB;
                     mbar_arrive_expect_tx(&abar[aux_buf ^ 1], 2048);
-                    tma_load_2d(slab_aux + (aux_buf ^ 1) * 2048, &tmAux, &abar[aux_buf ^ 1], n0 + NSUB * TC_CW, row0);
+                    tma_load_2d(slab_aux + (aux_buf ^ 1) * 2048, &tmAux, &abar[aux_buf ^ 1], nt * p.BN + (cn % nchunks) * TC_CW, row0_of(cn));
                 }
                 tc_ld_wait();
                 if (warp == 2 && first) TC_TRACE(10);
-                if (c + NSUB >= nchunks) {
+                if (cc + NSUB >= nch_tot) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -390,19 +431,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
-            // ---- output row of accumulator lane (quad, lane), computed once per tile by its owner lane
+            bool released = false;
+            bool first = true;
+            for (int racc = 0; racc < p.nacc; racc++) {
+            // ---- output row of accumulator lane (quad, lane), computed once per (tile, accumulator) by its owner lane
             int64_t m_own, ro_own = -1;
             int coff_own = 0;
             float rs_own = 1.0f;
             {
                 const int rl = quad * 32 + lane;
-                if (p.mode >= 2) {
+                if (p.mode == 2) {
                     const int per_img = p.tiles_x * p.tiles_y;
                     const int cb = mt / per_img, rr = mt % per_img;
                     const int y = (rr / p.tiles_x) * p.bmh + rl / p.bmw, x = (rr % p.tiles_x) * p.bmw + rl % p.bmw;
                     m_own = ((int64_t)cb * p.H + y) * p.W + x;
                 } else {
-                    m_own = (int64_t)mt * TC_BM + rl;
+                    m_own = tile_row0(p, mt, racc) + rl;
                 }
                 if (m_own < p.M) {
                     if (E.map == MSU_MAP_WINDOW) {
@@ -435,13 +479,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 coff_r[j] = __shfl_sync(0xffffffffu, coff_own, src);
                 rs_r[j] = __shfl_sync(0xffffffffu, rs_own, src);
             }
-            if (warp == 2) TC_TRACE(5);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            if (warp == 2) TC_TRACE(6);
-            const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-            bool released = false;
-            bool first = true;
+            if (racc == 0) {
+                if (warp == 2) TC_TRACE(5);
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                if (warp == 2) TC_TRACE(6);
+            }
+            const uint32_t t_base = tmem_base + acc * 256 + racc * 128 + ((uint32_t)(quad * 32) << 16);
             for (int c = (sub + it) % NSUB; c < nchunks; c += NSUB) {
                 const int cols = p.BN - c * TC_CW >= TC_CW ? TC_CW : 16;   // BN is a multiple of 16
                 uint32_t raw[TC_CW];
@@ -470,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_ld_wait();
                 if (warp == 2 && first) TC_TRACE(10);
-                if (c + NSUB >= nchunks) {                 // this warp's last read of the accumulator: hand TMEM back
+                if (c + NSUB >= nchunks && racc == p.nacc - 1) {   // this warp's last read of the accumulators: hand TMEM back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -534,7 +578,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (warp == 2 && first) TC_TRACE(9);
                 first = false;
             }
-            if (!released) {                               // no chunk of this tile fell to this warp
+            }   // accumulators of the tile
+            if (!released) {                               // no chunk of the last accumulator fell to this warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -636,6 +681,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
 
     TcParams p{};
     p.M = M; p.N = (int)N; p.K = (int)K;
+    p.nacc = 1;
     static const int env_bn = getenv("MSU_TC_BN") ? atoi(getenv("MSU_TC_BN")) : 0;
     static const int env_stages = getenv("MSU_TC_STAGES") ? atoi(getenv("MSU_TC_STAGES")) : 0;
     static const int env_epi = getenv("MSU_TC_EPI") ? atoi(getenv("MSU_TC_EPI")) : 0;   // 1: force the generic epilogue
@@ -667,7 +713,27 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         p.num_m_tiles = Bn * p.tiles_x * p.tiles_y;
         p.kb1 = 9 * p.cblocks; p.kb2 = 0; p.k_split = 0;
         static const int halo_off = getenv("MSU_CONV_HALO") ? (atoi(getenv("MSU_CONV_HALO")) == 0) : 0;
-        if (!halo_off && bmw == 128) {
+        static const int rows2_off = getenv("MSU_CONV_ROWS2") ? (atoi(getenv("MSU_CONV_ROWS2")) == 0) : 0;
+        p.nacc = 1;
+        if (!halo_off && !rows2_off && bmw == 128 && H % 2 == 0 && C % 32 == 0 && N <= 128) {
+            // two image rows per tile share every weight tile (35 % less operand traffic per pixel), K walked in exact
+            // 32-channel steps (no zero-padded channel block): BK = 32, 64B swizzle
+            p.mode = 4;
+            p.nacc = 2;
+            p.bmh = 2;
+            p.tiles_y = H / 2;
+            p.num_m_tiles = Bn * p.tiles_x * p.tiles_y;
+            p.cblocks = C / 32;
+            p.kb1 = 3 * p.cblocks;
+            cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bn};
+            cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+            cuuint32_t box[4] = {32, 130, 1, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (get_encode()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(A->ptr), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return 1;
+        } else if (!halo_off && bmw == 128) {
             // one 130-pixel halo row per (dy, channel block) instead of nine shifted 128-pixel boxes: 2.9x less A traffic
             p.mode = 3;
             p.kb1 = 3 * p.cblocks;
@@ -690,15 +756,24 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             tmA2 = tmA;
         }
     }
-    if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
+    if (p.mode == 4) {   // weight tiles [BN rows, 32 k] with the 64B swizzle of the halo rows
+        cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint64_t gstr[1] = {(cuuint64_t)B->ld * 2};
+        cuuint32_t box[2] = {32, (cuuint32_t)p.BN};
+        cuuint32_t estr[2] = {1, 1};
+        if (get_encode()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(B->ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    } else if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
 
-    p.a_stage = p.mode == 3 ? 17 * 1024 : TC_A_BYTES;
-    p.b_stage = (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
+    p.a_stage = p.mode == 4 ? 2 * TC_HALO32_BYTES : (p.mode == 3 ? 17 * 1024 : TC_A_BYTES);
+    p.b_stage = p.mode == 4 ? 3 * p.BN * 64 : (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
     const int stage_bytes = p.a_stage + p.b_stage;
     // [operand stages][1 KB: barriers, TMEM slot][epilogue slabs] + 1 KB alignment slack
     auto stages_for = [&](int sb) { int s_ = (227 * 1024 - 2048 - TC_EPI_WARPS * p.epi_bytes) / sb; return s_ > 8 ? 8 : s_; };
     p.stages = stages_for(stage_bytes);
-    if (p.mode != 3 && p.BN > 192 && p.stages < 4 && !env_bn) {
+    if (p.mode < 3 && p.BN > 192 && p.stages < 4 && !env_bn) {
         // operand bytes in flight bound the mainloop: a narrower N tile that buys the 4th stage wins
         const int bn2 = pick_bn(N, 192, epi_tma ? 32 : 16);
         const int sb2 = p.a_stage + bn2 * TC_BK * 2;

@@ -311,3 +311,102 @@ def test_gelu_grad_epilogue(ops):
 
     tc, simt = run_both(ops, go)
     assert relmax(tc, simt) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(900, 96, 384), (4096, 192, 768), (333, 288, 96), (70000, 96, 96)])
+def test_tma_epilogue_residual_rowscale(ops, shape):
+    """(acc + bias) * per-sample scale + residual through the TMA-slab epilogue (fc2 / unmapped proj form)."""
+    M, N, K = shape
+    torch.manual_seed(M + N)
+    a = (torch.randn(M, K) * 0.5).bfloat16().to(DEV)
+    w = (torch.randn(N, K) * 0.1).bfloat16().to(DEV)
+    bias = (torch.randn(N) * 0.1).to(DEV)
+    res = torch.randn(M, N).bfloat16().to(DEV)
+    rps = 128
+    sd = (torch.rand((M + rps - 1) // rps) > 0.3).float().to(DEV) * 1.25
+
+    def go():
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, bias=bias, R=res, rowscale=sd, rps=rps), M, N, K, a.device)
+        return y.float()
+
+    tc, simt = run_both(ops, go)
+    rows = torch.arange(M) // rps
+    ref = (a.double().cpu() @ w.double().cpu().t() + bias.double().cpu()) * sd.double().cpu()[rows][:, None] + res.double().cpu()
+    assert relmax(tc, ref) < 1e-2 and relmax(tc, simt) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(1000, 384, 96), (16384, 1536, 384), (300, 64, 64)])
+def test_tma_epilogue_preact_gelu_and_gelu_grad(ops, shape):
+    """fc1 form (bias + GELU with the pre-activation copy) and the dh form (x GELU'(h) x per-sample scale)."""
+    M, N, K = shape
+    torch.manual_seed(N + K)
+    a = (torch.randn(M, K) * 0.5).bfloat16().to(DEV)
+    w = (torch.randn(N, K) * 0.1).bfloat16().to(DEV)
+    bias = (torch.randn(N) * 0.1).to(DEV)
+    h = torch.randn(M, N).bfloat16().to(DEV)
+    sd = (torch.rand((M + 63) // 64) > 0.3).float().to(DEV) * 1.25
+
+    def fc1():
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        pre = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=bias, act=1), M, N, K, a.device)
+        return torch.stack([y.float(), pre.float()])
+
+    tc, simt = run_both(ops, fc1)
+    ref_pre = a.double().cpu() @ w.double().cpu().t() + bias.double().cpu()
+    assert relmax(tc[1], ref_pre) < 1e-2 and relmax(tc[0], torch.nn.functional.gelu(ref_pre)) < 1e-2
+    assert relmax(tc, simt) < 8e-3
+    # the activation is evaluated on the stored (bf16) pre-activation: GELU(pre) reproduces y to bf16 rounding
+    assert relmax(tc[0], torch.nn.functional.gelu(tc[1].double())) < 5e-3
+
+    def dh():
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, H=h, ldh=N, rowscale=sd, rps=64), M, N, K, a.device)
+        return y.float()
+
+    tc, simt = run_both(ops, dh)
+    hd = h.double().cpu()
+    gp = 0.5 * (1 + torch.erf(hd / 2 ** 0.5)) + hd * torch.exp(-0.5 * hd * hd) / (2 * torch.pi) ** 0.5
+    ref = (a.double().cpu() @ w.double().cpu().t()) * gp * sd.double().cpu()[torch.arange(M) // 64][:, None]
+    assert relmax(tc, ref) < 1e-2 and relmax(tc, simt) < 8e-3
+
+
+@pytest.mark.parametrize("geom", [(2, 128, 96), (1, 256, 96), (1, 128, 128)])
+def test_conv3x3_two_row_tiles_fused_epilogues(ops, geom):
+    """Whole-row conv tiles (two image rows per tile, two accumulators): bias + GELU + pre-activation copy through
+    the TMA-slab epilogue, and x GELU'(h) with the inverse depth-to-space output map through the generic epilogue
+    (the head's conv1 forward / conv1 dgrad forms, network/model_parts.py:468-471)."""
+    B, S, E = geom
+    torch.manual_seed(S * E)
+    x = torch.randn(B, S, S, E).bfloat16().to(DEV)
+    wt = torch.randn(E, E, 3, 3) * 0.05
+    bias = (torch.randn(E) * 0.1).to(DEV)
+    wr = ops.prep_weight(2, wt.to(DEV), E, E, (E, 9 * E), torch.bfloat16)
+    Mp = B * S * S
+
+    def fwd():
+        y = torch.empty(Mp, E, dtype=torch.bfloat16, device=DEV)
+        pre = torch.empty(Mp, E, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(x.view(Mp, E), ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(wr),
+                 ops.epilogue(y, Cpre=pre, bias=bias, act=1), Mp, E, 9 * E, x.device)
+        return torch.stack([y.float(), pre.float()])
+
+    tc, simt = run_both(ops, fwd)
+    ref = torch.nn.functional.conv2d(x.float().cpu().permute(0, 3, 1, 2).double(), wt.bfloat16().double(),
+                                     bias.double().cpu(), padding=1).permute(0, 2, 3, 1).reshape(Mp, E)
+    assert relmax(tc[1], ref) < 1e-2 and relmax(tc[0], torch.nn.functional.gelu(ref)) < 1e-2
+    assert relmax(tc, simt) < 8e-3
+
+    r = S // 4
+    T = B * r * r
+    h0 = torch.randn(Mp, E).bfloat16().to(DEV)
+
+    def dgrad():
+        out = torch.zeros(T, 16 * E, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(ops.operand(x.view(Mp, E), ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(wr),
+                 ops.epilogue(out, ldc=16 * E, H=h0, ldh=E, map=ops.MAP_UNSHUFFLE, geo=[r, r, 4, E]), Mp, E, 9 * E, x.device)
+        return out.float()
+
+    tc, simt = run_both(ops, dgrad)
+    assert relmax(tc, simt) < 8e-3
