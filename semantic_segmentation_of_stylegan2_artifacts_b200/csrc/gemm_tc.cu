@@ -68,25 +68,26 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 // GELU(x) = x * Phi(x) for the bf16 epilogues.  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as
-// sigmoid(2 x (c0 + c1 x^2 + c2 x^4)) with minimax-fitted c (|Phi error| <= 5.1e-5, |GELU error| <= 6.5e-5 absolute,
-// 60x below the bf16 rounding of an O(1) output; tails keep their relative accuracy because 1 / (1 + 2^v) is
-// exact in the limit).  9 issue slots per element (2 MUFU) instead of erff's ~45: the store warps of the
-// short-K GEMMs are ALU-bound.  The fp32 parity mode keeps erff (common.cuh).
+// 0.5 + 0.5 tanh(x (c0 + c1 x^2 + c2 x^4)) with minimax-fitted c (|Phi error| <= 5.1e-5 before the MUFU.TANH error of
+// 2^-11 relative, i.e. <= 3e-4 absolute on Phi: below the bf16 rounding of an O(1) output).  8 issue slots per element
+// with ONE transcendental: ncu showed the XU pipe (MUFU + F2F conversions, 16 lanes/clk/SM) as the top pipe of the
+// short-K GEMMs at 3 XU ops per element (ex2, rcp, F2F.BF16), so the epilogues use tanh and never F2F.
+// The fp32 parity mode keeps erff (common.cuh).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
+__device__ __forceinline__ float tanh_approx(float x) {
     float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float phi_cdf_fast(float x, float& x2c) {
     x2c = fminf(x * x, 50.0f);                     // beyond |x| = 7.07 Phi is 0 / 1 to fp32 precision
-    float p = fmaf(1.070594816e-03f, x2c, -1.070108842e-01f);
-    p = fmaf(p, x2c, -2.301264832e+00f);           // -2 log2(e) (c0 + c1 x^2 + c2 x^4)
-    return rcp_approx(1.0f + ex2_approx(x * p));
+    float p = fmaf(-3.710398891e-04f, x2c, 3.708714633e-02f);
+    p = fmaf(p, x2c, 7.975576149e-01f);
+    return fmaf(0.5f, tanh_approx(x * p), 0.5f);
 }
 __device__ __forceinline__ float gelu_fast(float x) {
     float x2c;
@@ -98,6 +99,9 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     const float e = ex2_approx(x2c * -0.72134752044448170368f);   // exp(-x^2 / 2)
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// the two bf16 halves of a packed word as fp32 (ALU shifts / masks; no XU conversion)
+__device__ __forceinline__ float bf16lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // K-major, 64B-swizzled descriptor (rows of 32 bf16 = 64 B, 8-row groups 512 B apart)
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw64_g(uint32_t saddr) {
@@ -350,14 +354,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) tma_store_wait_read0();
                 __syncwarp();
                 if (E.Cpre != nullptr) {
-#pragma unroll
-                    for (int g = 0; g < 4; g++)
-                        *reinterpret_cast<uint4*>(slab_aux + slab_off(lane, g)) =
-                            make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
                     // the activation sees the bf16-rounded pre-activation, exactly like a separate GELU pass over Cpre
+                    // (rounded by the pack itself and unpacked with shifts: F2F.BF16 would run on the XU pipe)
 #pragma unroll
-                    for (int i = 0; i < TC_CW; i++) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+                    for (int g = 0; g < 4; g++) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            pk[i] = pack_bf16x2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
+                            v[g * 8 + 2 * i] = bf16lo_f(pk[i]);
+                            v[g * 8 + 2 * i + 1] = bf16hi_f(pk[i]);
+                        }
+                        *reinterpret_cast<uint4*>(slab_aux + slab_off(lane, g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
                 }
                 if (E.act == 1) {
 #pragma unroll

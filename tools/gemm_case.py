@@ -60,7 +60,30 @@ def conv(B, S, E):
                              B * S * S, E, 9 * E, dev), 2 * B * S * S * E * 9 * E, 2 * B * S * S * E * 2)
 
 
+def head_expand(Bn, r, E):
+    M, N = Bn * r * r, 16 * E
+    a = torch.randn(M, E, device=dev).to(bf)
+    w = (torch.randn(N, E, device=dev) * 0.1).to(bf)
+    y = torch.empty(16 * M, E, dtype=bf, device=dev)
+    pre = torch.empty(16 * M, E, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, ldc=E, Cpre=pre, act=1, map=ops.MAP_SHUFFLE, geo=[r, r, 4, E]),
+                             M, N, E, dev), 2 * M * N * E, (M * E + 2 * M * N) * 2)
+
+
+def proj_win(Bn, H, C):
+    geo = [H, H, 7 * ((H + 6) // 7), 7 * ((H + 6) // 7), 3, 3]
+    Tw, T = Bn * geo[2] * geo[3], Bn * H * H
+    a = torch.randn(Tw, C, device=dev).to(bf)
+    w = (torch.randn(C, C, device=dev) * 0.1).to(bf)
+    b = torch.randn(C, device=dev)
+    r = torch.randn(T, C, device=dev).to(bf)
+    y = torch.empty(T, C, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, bias=b, R=r, map=ops.MAP_WINDOW, geo=geo), Tw, C, C, dev),
+            2 * Tw * C * C, (Tw * C + 2 * T * C) * 2)
+
+
 cases = {
+    "head_expand": lambda: head_expand(16, 128, 96), "projwin_s0": lambda: proj_win(16, 128, 96),
     "fc1_s0": lambda: fc1(262144, 384, 96), "fc2_s0": lambda: resid(262144, 96, 384),
     "dh_s0": lambda: dgelu(262144, 384, 96), "qkv_s0": lambda: plain(283024, 288, 96),
     "fc1_s1": lambda: fc1(65536, 768, 192), "fc2_s1": lambda: resid(65536, 192, 768),
