@@ -72,6 +72,10 @@ typedef struct {
     int32_t geo[6];
     int32_t out_f32;        /* 1: C is fp32 regardless of dtype (weight gradients)                        */
     int32_t accumulate;     /* 1: C += result (shared weights / gradient accumulation)                    */
+    float* colsum;          /* weight-gradient GEMMs (A, B orient 1) only, or NULL: also writes            \
+                               colsum[m] = sum_k A(m,k), the bias gradient of the same layer (autograd's   \
+                               grad_output.sum(0)); fused into the tensor-core kernel as one extra N=16     \
+                               MMA against a tile of ones where the tiling allows, else a column-sum pass */
 } MsuEpilogue;
 
 /* C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ), fp32 accumulation.

@@ -33,7 +33,7 @@ int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, in
 int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
             float* splitk_ws, int64_t splitk_ws_elems, cudaStream_t st);
 int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
-             float* ws, int64_t ws_elems, cudaStream_t st);
+             float* ws, int64_t ws_elems, cudaStream_t st, int* fused_colsum);
 
 }  // namespace msu
 
@@ -46,14 +46,27 @@ extern "C" int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilo
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     g_last_backend = 0;
+    const bool wgrad = (A->orient == 1 && B->orient == 1);
+    MSU_REQUIRE(E->colsum == nullptr || (wgrad && E->out_f32), "msu_gemm: colsum is defined for weight-gradient GEMMs (orient 1 operands, fp32 output) only");
+    int rc = 1, fused = 0;
     if (backend == 0) {
-        const int rc = (A->orient == 1 && B->orient == 1)
-                           ? wgrad_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st)
-                           : gemm_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
-        if (rc == 0) { g_last_backend = 1; return 0; }
-        if (rc != 1) return rc;
+        rc = wgrad ? wgrad_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st, &fused)
+                   : gemm_tc(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+        if (rc == 0) g_last_backend = 1;
+        else if (rc != 1) return rc;
     }
-    return gemm_simt(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+    if (rc == 1) {
+        rc = gemm_simt(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
+        if (rc != 0) return rc;
+    }
+    if (E->colsum != nullptr && !fused) {
+        // bias gradient not fused by the kernel above: column sums of A read as [K rows (tokens), M columns]
+        // (stream ordered after the split-K reduce, so the workspace can be shared)
+        MsuOperand X = *A;
+        X.orient = 0;
+        return msu_colsum(&X, K, M, E->colsum, 0, splitk_ws, splitk_ws_elems, stream);
+    }
+    return 0;
 }
 
 extern "C" int msu_version(void) { return 100; }

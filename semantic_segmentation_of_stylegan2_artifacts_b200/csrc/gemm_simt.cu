@@ -144,17 +144,27 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(MsuOperand A, MsuOperand 
     }
 }
 
-__global__ void splitk_reduce_kernel(MsuEpilogue E, int64_t M, int64_t N, int splits, const float* ws) {
+__global__ void splitk_reduce_kernel(MsuEpilogue E, int64_t M, int64_t N, int splits, const float* ws, const float* bws, int brows) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * N) return;
+    if (idx >= M * N) {
+        // bias-gradient partials [split][M] of the fused column sums (fixed order: deterministic)
+        const int64_t m = idx - M * N;
+        if (bws != nullptr && m < M) {
+            float b = 0.f;
+            for (int z = 0; z < brows; z++) b += bws[(int64_t)z * M + m];
+            E.colsum[m] = b;
+        }
+        return;
+    }
     float s = 0.f;
     for (int z = 0; z < splits; z++) s += ws[(int64_t)z * M * N + idx];  // fixed order: deterministic
     epilogue_store(E, idx / N, (int)(idx % N), s);
 }
 
-void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st) {
-    const int64_t tot = M * N;
-    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, M, N, splits, ws);
+void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st,
+                          const float* bws, int brows) {
+    const int64_t tot = M * N + (bws != nullptr ? M : 0);
+    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, M, N, splits, ws, bws, brows);
     count_launch();
 }
 
@@ -175,7 +185,7 @@ int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, in
     count_launch();
     if (splits > 1) {
         const int64_t tot = M * N;
-        splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*E, M, N, splits, splitk_ws);
+        splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*E, M, N, splits, splitk_ws, nullptr, 0);
         count_launch();
     }
     return check_launch("gemm_simt");

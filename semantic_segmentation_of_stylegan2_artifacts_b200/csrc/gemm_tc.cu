@@ -863,6 +863,7 @@ struct WgParams {
     int64_t tok_per_split;
     int stages, qboxes;
     float* ws;
+    float* bws;         // bias-gradient partials [split][Pn] (column sums of the M-side operand), or nullptr
 };
 
 constexpr int WG_BK = 64;            // tokens per stage
@@ -896,9 +897,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     const int KB = (int)((t1 - t0 + WG_BK - 1) / WG_BK);
     const int p0 = sup * p.MT * 128;   // first M-side channel of this CTA
     const int q0 = qt * p.BN;
+    // bias gradient = column sums of the call's A operand (the M side, or the N side when swapped): the four epilogue
+    // warps, idle during the main loop, add the operand tiles up from shared memory as the stages land (an extra
+    // MMA against a tile of ones cost +20 % kernel time: MN-major MMAs are shared-memory-read bound).  Only the CTAs of the
+    // first tile along the other axis do it (sharing the stages among all tiles measured slower: every CTA then pays
+    // the later slot release).
+    const bool do_bias = (p.bws != nullptr) && (p.swap ? sup == 0 : qt == 0);
+    constexpr int nq = 1, myq = 0;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // a stage is free when its MMAs have retired (+ when the four column-sum warps have read it)
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -952,6 +961,52 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
         // (coalesced 128 B rows, out-of-range rows / columns clipped by the tensor map)
         const int quad = warp & 3;
         uint8_t* slab = sSlab + (size_t)(warp - 2) * 2 * 4096;
+        if (do_bias) {
+            // warp w adds tokens [16 w, 16 w + 16) of every stage; lane = channel pair of a 64-channel box (one 128 B row
+            // of the swizzled tile per load instruction: conflict free).  Fixed order => deterministic.
+            const int ew = warp - 2;
+            const int nbx = p.swap ? p.qboxes : p.MT * 2;          // <= 8 boxes of [64 tokens x 64 channels]
+            float2 acc[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) acc[b] = make_float2(0.f, 0.f);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&full[stage], phase);
+                const uint8_t* src = p.swap ? sB + (size_t)stage * B_BYTES : sA + (size_t)stage * A_BYTES;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    if (b < nbx && kb % nq == myq) {
+#pragma unroll
+                        for (int tt = 0; tt < 16; tt++) {
+                            const int t = ew * 16 + tt;
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(src + b * WG_BOX_BYTES + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4);
+                            acc[b].x += bf16lo_f(u);
+                            acc[b].y += bf16hi_f(u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            // combine the four token quarters through the (still unused) output slabs, then one partial row per split
+            float2* comb = reinterpret_cast<float2*>(sSlab);       // [4 warps][8 boxes][32 pairs]
+#pragma unroll
+            for (int b = 0; b < 8; b++) comb[(ew * 8 + b) * 32 + lane] = acc[b];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int org = p.swap ? q0 : p0;
+            const int ext = p.swap ? (p.Qn < q0 + p.BN ? p.Qn : q0 + p.BN) : p.Pn;   // channels this CTA owns
+            const int ldb = p.swap ? p.Qn : p.Pn;
+            for (int idx = ew * 32 + lane; idx < nbx * 32; idx += 128) {
+                const int b = idx >> 5, l = idx & 31;
+                float2 t = comb[(0 * 8 + b) * 32 + l];
+                for (int w = 1; w < 4; w++) { const float2 u = comb[(w * 8 + b) * 32 + l]; t.x += u.x; t.y += u.y; }
+                const int c = org + b * 64 + l * 2;
+                if (c < ext) p.bws[((int64_t)split * nq + myq) * ldb + c] = t.x;
+                if (c + 1 < ext) p.bws[((int64_t)split * nq + myq) * ldb + c + 1] = t.y;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");         // the slabs are reused by the stores below
+        }
         mbar_wait(tfull, 0);
         tc_fence_after();
         int nb = 0;
@@ -1003,7 +1058,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     }
 }
 
-void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st);
+void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st,
+                          const float* bws = nullptr, int brows = 0);
 
 // ================================================================================================
 // 3x3 conv weight gradient on tcgen05:  dW[co, (tap, ci)] = sum_pix dZ[pix, co] * X[pix + off(tap), ci]
@@ -1018,6 +1074,7 @@ struct WcParams {
     int stages;
     int halo;                 // 1: one (WB+2)-pixel halo slab per dy, the three dx taps are row-shifted views of it
     float* ws;
+    float* bws;               // bias-gradient partials [split][E] (column sums of dZ), or nullptr
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -1038,7 +1095,10 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    float2* sComb = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [4 warps][2 boxes][32 pairs]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // conv bias gradient = column sums of dZ: added up from the dZ tiles by the epilogue warps while the MMAs run
+    const bool do_bias = (p.bws != nullptr) && (grp == p.n_groups - 1);   // the last tap group has the fewest taps
     const int64_t s0 = (int64_t)split * p.slabs_per_split;
     int64_t s1 = s0 + p.slabs_per_split;
     if (s1 > p.slabs) s1 = p.slabs;
@@ -1046,7 +1106,7 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int slabs_per_row = p.W / p.WB;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1109,6 +1169,40 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         }
     } else {
         const int quad = warp & 3;
+        if (do_bias) {
+            const int ew = warp - 2, tpw = p.WB / 4;               // tokens of a slab per warp
+            float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&full[stage], phase);
+                const uint8_t* src = sA + (size_t)stage * A_BYTES;
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    if (b < p.boxes) {
+                        for (int tt = 0; tt < tpw; tt++) {
+                            const int t = ew * tpw + tt;
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(src + b * BOX + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4);
+                            acc[b].x += bf16lo_f(u);
+                            acc[b].y += bf16hi_f(u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            sComb[(ew * 2 + 0) * 32 + lane] = acc[0];
+            sComb[(ew * 2 + 1) * 32 + lane] = acc[1];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int idx = ew * 32 + lane; idx < p.boxes * 32; idx += 128) {
+                const int b = idx >> 5, l = idx & 31;
+                float2 t = sComb[(0 * 2 + b) * 32 + l];
+                for (int w = 1; w < 4; w++) { const float2 u = sComb[(w * 2 + b) * 32 + l]; t.x += u.x; t.y += u.y; }
+                const int c = b * 64 + l * 2;
+                if (c < p.E) p.bws[(int64_t)split * p.E + c] = t.x;
+                if (c + 1 < p.E) p.bws[(int64_t)split * p.E + c + 1] = t.y;
+            }
+        }
         mbar_wait(tfull, 0);
         tc_fence_after();
         const int J = 9 * p.E;
@@ -1138,7 +1232,7 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 
 // A = dZ (orient 1, plain [pix, E]); B = X (orient 1, MAP_CONV3 over NHWC [Bn,H,W,E]); out fp32 [E, 9E]
 static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
-                         float* ws, int64_t ws_elems, cudaStream_t st) {
+                         float* ws, int64_t ws_elems, cudaStream_t st, int* fused_colsum) {
     const int H = B->geo[0], W = B->geo[1], Ec = B->geo[2];
     if (I != Ec || J != 9 * (int64_t)Ec || Ec > 128 || Ec % 8 != 0 || A->ld != Ec || B->ld != Ec) return 1;
     if (T % ((int64_t)H * W) != 0) return 1;
@@ -1148,6 +1242,7 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     if (p.WB == 0) return 1;
     p.BN = (Ec + 15) / 16 * 16;
     p.boxes = (Ec + 63) / 64;
+    const bool want_bias = E->colsum != nullptr && Ec <= 128;
     p.G = TC_TMEM_COLS / p.BN;
     if (p.G > 9) p.G = 9;
     const int BOX = p.WB * 128;
@@ -1168,11 +1263,12 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     p.slabs = (int64_t)p.Bn * H * (W / p.WB);
     int splits = (2 * num_sms() + p.n_groups - 1) / p.n_groups;
     if (splits > p.slabs) splits = (int)p.slabs;
-    while (splits > 1 && (int64_t)splits * I * J > ws_elems) splits--;
-    if ((int64_t)splits * I * J > ws_elems) return 1;
+    while (splits > 1 && (int64_t)splits * I * (J + 1) > ws_elems) splits--;
+    if ((int64_t)splits * I * (J + 1) > ws_elems) return 1;
     p.slabs_per_split = (p.slabs + splits - 1) / splits;
     splits = (int)((p.slabs + p.slabs_per_split - 1) / p.slabs_per_split);
     p.splits = splits;
+    p.bws = want_bias ? ws + (int64_t)splits * I * J : nullptr;
     CUtensorMap tmZ, tmX;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)Ec, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Bn};
@@ -1187,7 +1283,7 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
                 return 1;
         }
     }
-    const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+    const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 48 + 4 * 2 * 32 * 8 + 1024;   // + column-sum combine buffer
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1196,7 +1292,8 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     }
     wgrad_conv_tc_kernel<<<p.n_groups * splits, WG_THREADS, smem, st>>>(tmZ, tmX, p);
     count_launch();
-    launch_splitk_reduce(*E, I, J, splits, ws, st);
+    launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits);
+    if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;
     return check_launch("wgrad_conv_tc");
 }
 
@@ -1206,13 +1303,14 @@ static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, in
 
 // returns 0 = launched, 1 = unsupported (SIMT fallback), other = error.  A(i, t) and B(j, t) both orient=1.
 int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
-             float* ws, int64_t ws_elems, cudaStream_t st) {
+             float* ws, int64_t ws_elems, cudaStream_t st, int* fused_colsum) {
+    if (fused_colsum) *fused_colsum = 0;
     if (A->dtype != MSU_BF16 || B->dtype != MSU_BF16 || !E->out_f32) return 1;
     if (A->orient == 1 && B->orient == 1 && A->map == MSU_MAP_NONE && B->map == MSU_MAP_CONV3) {
         if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale || !aligned16(A->ptr) || !aligned16(B->ptr)) return 1;
         if (E->map != MSU_MAP_NONE || E->bias || E->R || E->H || E->Cpre || E->act || E->rowscale) return 1;
         if (ws == nullptr || get_encode() == nullptr) return 1;
-        return wgrad_conv_tc(A, B, E, I, J, T, ws, ws_elems, st);
+        return wgrad_conv_tc(A, B, E, I, J, T, ws, ws_elems, st, fused_colsum);
     }
     if (A->orient != 1 || B->orient != 1 || A->map != MSU_MAP_NONE || B->map != MSU_MAP_NONE) return 1;
     if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale) return 1;
@@ -1240,6 +1338,7 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     }
     p.n_q_tiles = (p.Qn + p.BN - 1) / p.BN;
     p.qboxes = (p.BN + 63) / 64;
+    const bool want_bias = (E->colsum != nullptr);   // column sums of the call's A operand ride along (either side)
     while (p.MT > 1 && p.MT * p.BN > TC_TMEM_COLS) p.MT--;
     // keep at least 2 pipeline stages in 200 KB
     while (p.MT > 1 && 2 * (p.MT * 2 + p.qboxes) * WG_BOX_BYTES > 200 * 1024) p.MT--;
@@ -1252,12 +1351,14 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     int splits = (num_sms() + base_ctas - 1) / base_ctas;
     const int64_t max_splits_t = (T + 511) / 512;
     if (splits > max_splits_t) splits = (int)max_splits_t;
-    while (splits > 1 && (int64_t)splits * I * J > ws_elems) splits--;
-    if ((int64_t)splits * I * J > ws_elems) return 1;
+    const int nq = 1;   // bias partial rows per split
+    while (splits > 1 && (int64_t)splits * I * (J + nq) > ws_elems) splits--;
+    if ((int64_t)splits * I * (J + nq) > ws_elems) return 1;
     int64_t tps = (T + splits - 1) / splits;
     tps = (tps + WG_BK - 1) / WG_BK * WG_BK;
     splits = (int)((T + tps - 1) / tps);
     p.splits = splits; p.tok_per_split = tps;
+    p.bws = want_bias ? ws + (int64_t)splits * I * J : nullptr;
     CUtensorMap tmP, tmQ;
     if (!make_map_2d_box64(&tmP, P->ptr, T, p.Pn, P->ld)) return 1;
     if (!make_map_2d_box64(&tmQ, Q->ptr, T, p.Qn, Q->ld)) return 1;
@@ -1281,7 +1382,8 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     }
     wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, tmW, p);
     count_launch();
-    launch_splitk_reduce(*E, I, J, splits, ws, st);
+    launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq);
+    if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;
     return check_launch("wgrad_tc");
 }
 

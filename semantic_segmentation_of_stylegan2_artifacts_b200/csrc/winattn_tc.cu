@@ -11,6 +11,9 @@
 // (rows 49..63 of a box belong to the next window: finite values that meet exact zeros in P).
 // The Q/K boxes alias the two diagonal blocks of the P tile, so a CTA needs 40 KB of shared memory and
 // 128 TMEM columns: four CTAs per SM overlap each other's TMA / MMA / softmax phases.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace msu {
@@ -271,7 +274,8 @@ constexpr int AB_SMEM = 4 * AB_TILE + 3 * AB_X + AT_BIAS_BYTES + 64 + 1024;
 __global__ void __launch_bounds__(128, 2)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_partial,
-                      int64_t n_windows, int nH, WinGeo g) {
+                      int64_t n_windows, int nH, WinGeo g, long long* trace) {
+#define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
@@ -313,8 +317,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
     for (int j = 0; j < WT; j++) acc[j] = 0.f;
 
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    int it = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, it++) {
         const int64_t win = pair * 2 + half;
+        AT_TRACE(0);
         if (tid == 0) {
             mbar_arrive_expect_tx(bar_load, 8 * 4096);
             const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
@@ -328,6 +334,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tma_load_2d(sD + 4096, &tmDO, bar_load, h * HD, r1);
             mbar_wait(bar_load, ph_load);
             tc_fence_after();
+            AT_TRACE(1);
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
             const uint64_t vd = make_desc_kmajor_sw64(smem_u32(sV)), dd = make_desc_kmajor_sw64(smem_u32(sD));
             tc_mma_bf16(tmem, qd, kd, id_s, 0);
@@ -344,6 +351,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        AT_TRACE(2);
         uint32_t pk[32], dk_[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) { pk[j] = 0u; dk_[j] = 0u; }
@@ -379,6 +387,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 }
             }
         }
+        AT_TRACE(3);
         {   // row tid of both compact tiles (zeros for padding rows: they are contracted over in dV / dK)
             uint8_t* prow = sXP + tid * 128;
             uint8_t* srow = sXS + tid * 128;
@@ -392,6 +401,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();
+        AT_TRACE(4);
         if (tid == 0) {
             tc_fence_after();
             const uint32_t xp = smem_u32(sXP), xs = smem_u32(sXS);
@@ -415,6 +425,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        AT_TRACE(5);
         {
             float o[32];
             const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
@@ -455,8 +466,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 }
             }
         }
+        AT_TRACE(6);
         tc_fence_before();
         __syncthreads();
+        AT_TRACE(7);
     }
     // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i
     if (i < WT) {
@@ -500,8 +513,32 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         attr = true;
     }
     dim3 grid(winattn_bwd_tc_grid(n_windows, nH), nH);
+    static const int trace_on = getenv("MSU_ATT_TRACE") ? atoi(getenv("MSU_ATT_TRACE")) : 0;
+    static long long* trace_buf = nullptr;
+    const size_t trace_n = (size_t)grid.x * 8 * 8;
+    if (trace_on) {
+        if (trace_buf != nullptr) cudaFree(trace_buf);
+        cudaMalloc(&trace_buf, trace_n * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
+    }
     winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, bias, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_partial,
-                                                    n_windows, nH, g);
+                                                    n_windows, nH, g, trace_on ? trace_buf : nullptr);
+    if (trace_on) {   // debug only: synchronous dump of the per-unit phase timeline of two CTAs
+        long long* host = (long long*)malloc(trace_n * sizeof(long long));
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, trace_buf, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+        static const char* names[8] = {"start", "loaded", "S_dP_ready", "softmax_done", "tiles_synced", "mma2_done", "stored", "end"};
+        for (int cta : {0, (int)grid.x / 2}) {
+            const long long t0 = host[(size_t)cta * 64];
+            fprintf(stderr, "[att trace] nwin=%lld nH=%d grid=%d cta %d\n", (long long)n_windows, nH, (int)grid.x, cta);
+            for (int it = 0; it < 8; it++) {
+                fprintf(stderr, "  unit %d:", it);
+                for (int ev = 0; ev < 8; ev++) fprintf(stderr, " %s=%lld", names[ev], host[((size_t)cta * 8 + it) * 8 + ev] ? host[((size_t)cta * 8 + it) * 8 + ev] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+        }
+        free(host);
+    }
     count_launch();
     return check_launch("winattn_bwd_tc");
 }

@@ -140,28 +140,29 @@ class SwinBlockFn(Function):
         f32 = dict(dtype=torch.float32, device=dev)
         # ---- MLP half
         dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
-        db2 = ops.colsum(dy2, T, Cd, dev)
+        # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum: one extra N=16 MMA against ones)
+        db2 = torch.empty(Cd, **f32)
         dW2 = torch.empty(Cd, hid, **f32)
-        gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True), Cd, hid, T, dev)
+        gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev)
         dh = torch.empty(T, hid, dtype=dt, device=dev)
         gemm(dy2, w_dgrad(f2w, dt), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
-        db1 = ops.colsum(operand(dh), T, hid, dev)
+        db1 = torch.empty(hid, **f32)
         dW1 = torch.empty(hid, Cd, **f32)
-        gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True), hid, Cd, T, dev)
+        gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev)
         dxn = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
         dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
         # ---- attention half: gradient rows gathered into window order (zero rows for the padding tokens)
         dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
-        dbp = ops.colsum(dy1, Tw, Cd, dev)
+        dbp = torch.empty(Cd, **f32)
         dWp = torch.empty(Cd, Cd, **f32)
-        gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True), Cd, Cd, Tw, dev)
+        gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev)
         do = torch.empty(Tw, Cd, dtype=dt, device=dev)
         gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
         dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo)
-        dbqkv = ops.colsum(operand(dqkv), Tw, 3 * Cd, dev)
+        dbqkv = torch.empty(3 * Cd, **f32)
         dWqkv = torch.empty(3 * Cd, Cd, **f32)
-        gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True), 3 * Cd, Cd, Tw, dev)
+        gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv), 3 * Cd, Cd, Tw, dev)
         dxw = torch.empty(Tw, Cd, dtype=dt, device=dev)
         gemm(operand(dqkv), w_dgrad(qkvw, dt), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
         dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
@@ -199,9 +200,9 @@ class PatchEmbedFn(Function):
         T = y.shape[0]
         dout = _c(dout).view(T, E)
         dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, T, E)
-        dpb = ops.colsum(operand(dy), T, E, dev)
+        dpb = torch.empty(E, dtype=torch.float32, device=dev)
         dW64 = torch.empty(E, 64, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True), E, 64, T, dev)
+        gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True, colsum=dpb), E, 64, T, dev)
         dpw = ops.prep_weight(6, dW64, E, 48, (E, 3, 4, 4), torch.float32)
         return None, dpw, dpb, dnw, dnb, None
 
@@ -302,9 +303,9 @@ class ConcatLinearFn(Function):
         Cd = x.shape[-1]
         T = x.numel() // Cd
         dy = _c(dy).view(T, Cd)
-        db = ops.colsum(operand(dy), T, Cd, dev)
+        db = torch.empty(Cd, dtype=torch.float32, device=dev)
         dw = torch.empty(Cd, 2 * Cd, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True),
+        gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True, colsum=db),
              Cd, Cd, T, dev)
         gemm(operand(dy, orient=1), operand(skip.view(T, Cd), orient=1),
              epilogue(dw, ldc=2 * Cd, out_f32=True, offset=Cd), Cd, Cd, T, dev)
@@ -387,19 +388,19 @@ class HeadFn(Function):
         dl = _c(dlogits).view(Mp)
         dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
         # conv2
-        dc2b = ops.colsum(operand(dz2), Mp, E, dev)
+        dc2b = torch.empty(E, **f32)
         dw2r = torch.empty(E, 9 * E, **f32)
-        gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw2r, out_f32=True),
-             E, 9 * E, Mp, dev)
+        gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+             epilogue(dw2r, out_f32=True, colsum=dc2b), E, 9 * E, Mp, dev)
         dc2w = ops.prep_weight(4, dw2r, E, E, (E, E, 3, 3), torch.float32)
         w2f = shadow(c2w, 3, E, E, (E, 9 * E), wd)
         dz1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
         # conv1
-        dc1b = ops.colsum(operand(dz1), Mp, E, dev)
+        dc1b = torch.empty(E, **f32)
         dw1r = torch.empty(E, 9 * E, **f32)
-        gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo), epilogue(dw1r, out_f32=True),
-             E, 9 * E, Mp, dev)
+        gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+             epilogue(dw1r, out_f32=True, colsum=dc1b), E, 9 * E, Mp, dev)
         dc1w = ops.prep_weight(4, dw1r, E, E, (E, E, 3, 3), torch.float32)
         w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
         # conv1 dgrad (x gelu'(h0)) written by the GEMM epilogue in the inverse depth-to-space layout [T, 16E]

@@ -54,7 +54,7 @@ def operand(t: torch.Tensor, ld: Optional[int] = None, *, t2: Optional[torch.Ten
 
 def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=None, R=None, ldr: Optional[int] = None,
              H=None, ldh: int = 0, rowscale=None, rps: int = 0, act: int = 0, map: int = MAP_NONE, geo=None,
-             out_f32: bool = False, accumulate: bool = False, offset: int = 0) -> MsuEpilogue:
+             out_f32: bool = False, accumulate: bool = False, offset: int = 0, colsum=None) -> MsuEpilogue:
     e = MsuEpilogue()
     e.C = Cm.data_ptr() + offset * Cm.element_size()
     e.Cpre = L.ptr(Cpre)
@@ -72,12 +72,15 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     e.geo = L.geo6(geo)
     e.out_f32 = 1 if out_f32 else 0
     e.accumulate = 1 if accumulate else 0
+    e.colsum = L.ptr(colsum)
+    if colsum is not None and (colsum.dtype != torch.float32 or not out_f32):
+        raise TypeError("colsum (bias gradient) needs an fp32 vector and an fp32 weight-gradient output")
     if out_f32 and Cm.dtype != torch.float32:
         raise TypeError("out_f32 needs an fp32 output tensor")
     for t in (Cpre, R, H):
         if t is not None and t.dtype != Cm.dtype:
             raise TypeError("epilogue tensors must share the output dtype")
-    e._keep = (Cm, Cpre, bias, R, H, rowscale)
+    e._keep = (Cm, Cpre, bias, R, H, rowscale, colsum)
     return e
 
 

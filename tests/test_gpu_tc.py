@@ -158,12 +158,23 @@ def test_wgrad_mn_major(ops, shape):
         ops.gemm(ops.operand(dy, orient=1), ops.operand(x, orient=1), ops.epilogue(dw, out_f32=True), I, J, T, dy.device)
         return dw
 
+    def go_bias():   # bias gradient (column sums of dY) riding along: MsuEpilogue.colsum
+        dw = torch.empty(I, J, dtype=torch.float32, device=DEV)
+        db = torch.full((I,), float("nan"), dtype=torch.float32, device=DEV)
+        ops.gemm(ops.operand(dy, orient=1), ops.operand(x, orient=1), ops.epilogue(dw, out_f32=True, colsum=db), I, J, T, dy.device)
+        return torch.cat([dw.flatten(), db])
+
     tc, simt = run_both(ops, go)
     ref = dy.double().cpu().t() @ x.double().cpu()
     assert relmax(tc, ref) < 2e-5
     assert relmax(tc, simt) < 2e-5
     tc2, _ = run_both(ops, go)
     assert torch.equal(tc, tc2)  # fixed reduction order
+    tcb, simtb = run_both(ops, go_bias)
+    assert torch.equal(tcb[:I * J].view(I, J), tc)
+    refb = dy.double().cpu().sum(0)
+    assert relmax(tcb[I * J:], refb) < 2e-5 and relmax(simtb[I * J:], refb) < 2e-5
+    assert torch.equal(tcb, run_both(ops, go_bias)[0])
 
 
 @pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128), (3, 48, 64)])
@@ -177,11 +188,15 @@ def test_conv3x3_wgrad(ops, geom):
 
     def go():
         dw = torch.empty(E, 9 * E, dtype=torch.float32, device=DEV)
+        db = torch.full((E,), float("nan"), dtype=torch.float32, device=DEV)
         ops.gemm(ops.operand(dz.view(Mp, E), orient=1), ops.operand(x.view(Mp, E), ld=E, orient=1, map=ops.MAP_CONV3, geo=[S, S, E]),
-                 ops.epilogue(dw, out_f32=True), E, 9 * E, Mp, x.device)
-        return dw
+                 ops.epilogue(dw, out_f32=True, colsum=db), E, 9 * E, Mp, x.device)
+        return torch.cat([dw.flatten(), db])
 
     tc, simt = run_both(ops, go)
+    refb = dz.double().cpu().view(Mp, E).sum(0)                       # conv bias gradient from the same kernel
+    assert relmax(tc[E * 9 * E:], refb) < 2e-5 and relmax(simt[E * 9 * E:], refb) < 2e-5
+    tc, simt = tc[:E * 9 * E].view(E, 9 * E), simt[:E * 9 * E].view(E, 9 * E)
     xr = x.float().cpu().permute(0, 3, 1, 2).double().requires_grad_(False)
     w = torch.zeros(E, E, 3, 3, dtype=torch.float64, requires_grad=True)
     y = torch.nn.functional.conv2d(xr, w, padding=1)
