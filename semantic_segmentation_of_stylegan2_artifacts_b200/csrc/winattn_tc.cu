@@ -2,15 +2,10 @@
 // TMEM accumulators; the softmax (scale, relative-position bias, -100 shift mask, fp32 statistics) runs on
 // the TMEM lanes: one thread owns one query row.  TV:models/swin_transformer.py:181-214.
 //
-// Tiny-tile strategy (49 tokens x head-dim 32): two windows are packed into one M=128 MMA.
-//   MMA 1:  S[128 x 128] = [Q_a; Q_b] [K_a; K_b]^T      (K = 32; the two off-diagonal 64x64 blocks are unused)
-//   softmax per row on its own 64-column block -> P (bf16) written block-diagonally into a 128B-swizzled
-//           K-major tile [128 rows x 128 keys] (off-diagonal blocks stay zero)
-//   MMA 2:  O[128 x 32] = P V, V read MN-major straight from its TMA tile (no transpose)
-// Q/K/V tiles are [64 rows x 32] bf16 TMA boxes (64B swizzle) taken directly from the window-ordered qkv rows
-// (rows 49..63 of a box belong to the next window: finite values that meet exact zeros in P).
-// The Q/K boxes alias the two diagonal blocks of the P tile, so a CTA needs 40 KB of shared memory and
-// 128 TMEM columns: four CTAs per SM overlap each other's TMA / MMA / softmax phases.
+// Tiny-tile strategy (49 tokens x head-dim 32): two windows are packed into one M=128 MMA; Q/K/V(/dO) tiles are
+// [64 rows x 32] bf16 TMA boxes (64B swizzle) taken directly from the window-ordered qkv rows (rows 49..63 of a box
+// belong to the next window: finite values that meet exact zeros in P), double buffered so that the loads of the
+// next unit are in flight while the current one is computed.  Kernel-specific notes precede each kernel.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -66,23 +61,28 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-constexpr int AT_P_BYTES = 32 * 1024;   // P tile: two [128 x 128 B] swizzle atoms
-constexpr int AT_V_BYTES = 8 * 1024;
+constexpr int AT_P_BYTES = 16 * 1024;   // compact P tile: row = query (128), 64 own-window keys (128 B rows, 128B swizzle)
+constexpr int AT_OPS_BYTES = 24 * 1024;  // one stage of Q, K, V tiles (8 KB each: two [64 rows x 32] boxes)
 constexpr int AT_BIAS_BYTES = 2404 * 4;  // this head's [49,49] bias, pre-multiplied by log2(e)
-constexpr int AT_SMEM = AT_P_BYTES + AT_V_BYTES + AT_BIAS_BYTES + 64 + 1024;
+constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 1024;
 
-__global__ void __launch_bounds__(128, 4)
+// Forward.  Unit = two windows x one head.  The operand tiles are double buffered: the TMA loads of unit n+1 are issued
+// before unit n is touched, so a CTA never waits for HBM; 75 KB of shared memory and 128 TMEM columns per CTA let three
+// CTAs per SM overlap each other's MMA / softmax / store phases.
+//   MMA 1:  S[128 x 128] = [Q_a; Q_b] [K_a; K_b]^T      (K = 32; the two off-diagonal 64x64 blocks are unused)
+//   softmax per row on its own 64-column block -> P row (bf16, keys >= 49 zero) in the compact K-major tile
+//   MMA 2:  O_w[128 x 32] = P[:, own keys] V_w for w = a, b into TMEM columns [32 w, 32 w + 32): rows of the other
+//           window hold unused values; V is read MN-major straight from its TMA tile (no transpose)
+__global__ void __launch_bounds__(128, 3)
 winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ bias, __nv_bfloat16* __restrict__ O,
                       int64_t n_windows, int nH, WinGeo g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sP = smem;                       // atom 0 = keys 0..63, atom 1 = keys 64..127
-    uint8_t* sQ = smem;                       // aliases P atom 0 rows 0..63   (data block of window a)
-    uint8_t* sK = smem + 24 * 1024;           // aliases P atom 1 rows 64..127 (data block of window b)
-    uint8_t* sV = smem + AT_P_BYTES;
-    float* sBias = reinterpret_cast<float*>(sV + AT_V_BYTES);
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sV + AT_V_BYTES + AT_BIAS_BYTES);
-    uint64_t* bar_mma = bar_load + 1;
+    uint8_t* sP = smem;
+    uint8_t* sOps = smem + AT_P_BYTES;        // [2][Q 8K | K 8K | V 8K]
+    float* sBias = reinterpret_cast<float*>(sOps + 2 * AT_OPS_BYTES);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);   // [2]
+    uint64_t* bar_mma = bar_load + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int C = nH * HD;
@@ -90,7 +90,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
     for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
 
     if (tid == 0) {
-        mbar_init(bar_load, 1);
+        mbar_init(&bar_load[0], 1);
+        mbar_init(&bar_load[1], 1);
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -98,12 +99,6 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // the two off-diagonal blocks of P are zero for the whole kernel: [8K, 24K)
-    {
-        uint4* z = reinterpret_cast<uint4*>(smem + 8 * 1024);
-        for (int i = tid; i < 16 * 1024 / 16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -115,27 +110,38 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
     const int i = tid & 63;                // token index inside the window (valid if < 49)
     const uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc2 = make_idesc_bf16(128, 32, 0, 1);
-    uint32_t ph_load = 0, ph_mma = 0;
+    uint32_t ph_mma = 0;
 
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    auto issue_loads = [&](int64_t pair, int buf) {
+        uint8_t* q = sOps + buf * AT_OPS_BYTES;
+        mbar_arrive_expect_tx(&bar_load[buf], 6 * 4096);
+        const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
+        tma_load_2d(q, &tm, &bar_load[buf], h * HD, r0);
+        tma_load_2d(q + 4096, &tm, &bar_load[buf], h * HD, r1);
+        tma_load_2d(q + 8192, &tm, &bar_load[buf], C + h * HD, r0);
+        tma_load_2d(q + 12288, &tm, &bar_load[buf], C + h * HD, r1);
+        tma_load_2d(q + 16384, &tm, &bar_load[buf], 2 * C + h * HD, r0);
+        tma_load_2d(q + 20480, &tm, &bar_load[buf], 2 * C + h * HD, r1);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < n_pairs) issue_loads(blockIdx.x, 0);
+
+    int it = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, it++) {
+        const int buf = it & 1;
         const int64_t win = pair * 2 + half;
+        uint8_t* sQ = sOps + buf * AT_OPS_BYTES;
+        uint8_t* sK = sQ + 8192;
+        uint8_t* sV = sQ + 16384;
         if (tid == 0) {
-            mbar_arrive_expect_tx(bar_load, 6 * 4096);
-            const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
-            tma_load_2d(sQ, &tm, bar_load, h * HD, r0);
-            tma_load_2d(sQ + 4096, &tm, bar_load, h * HD, r1);
-            tma_load_2d(sK, &tm, bar_load, C + h * HD, r0);
-            tma_load_2d(sK + 4096, &tm, bar_load, C + h * HD, r1);
-            tma_load_2d(sV, &tm, bar_load, 2 * C + h * HD, r0);
-            tma_load_2d(sV + 4096, &tm, bar_load, 2 * C + h * HD, r1);
-            mbar_wait(bar_load, ph_load);
+            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
+            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
+            mbar_wait(&bar_load[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
             tc_mma_bf16(tmem, qd, kd, idesc1, 0);
             tc_mma_bf16(tmem, qd + 2, kd + 2, idesc1, 1);   // +32 B: second K=16 slice of the 64 B rows
             tc_commit(bar_mma);
         }
-        ph_load ^= 1;
         // ---- softmax on this thread's row
         const bool row_ok = (i < WT) && (win < n_windows);
         const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
@@ -145,11 +151,13 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
         ph_mma ^= 1;
         tc_fence_after();
         float s[64];
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
-        tc_ld16(trow, s);
-        tc_ld16(trow + 16, s + 16);
-        tc_ld16(trow + 32, s + 32);
-        tc_ld16(trow + 48, s + 48);
+        {
+            uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
+            tc_ld32_nowait(trow, sr);
+            tc_ld32_nowait(trow + 32, sr + 32);
+            tc_ld_wait();
+        }
         float inv = 0.f;
         uint32_t pk[32];
 #pragma unroll
@@ -174,25 +182,27 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
             }
             inv = 1.0f / sum;
         }
-        // all TMEM reads of S are done before MMA 2 overwrites columns 0..31; all Q/K smem reads (MMA 1) completed
-        // P row -> its diagonal block: atom `half`, row tid, 8 x 16 B chunks, 128B swizzle (chunk ^ (row & 7))
+        // P row -> compact tile: row tid, 8 x 16 B chunks, 128B swizzle (chunk ^ (row & 7)); padding rows are zero
         {
-            uint8_t* prow = sP + half * 16 * 1024 + tid * 128;
+            uint8_t* prow = sP + tid * 128;
 #pragma unroll
             for (int c = 0; c < 8; c++)
                 *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();   // all S rows are read (MMA 2 overwrites columns 0..63) and all P rows are written
         if (tid == 0) {
             tc_fence_after();
             const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {   // 128 keys = 8 K-steps: 4 per swizzle atom (+32 B each), V advances 16 rows = 1 KB
-                const uint64_t ad = make_desc_kmajor_sw128(pa + (k >> 2) * 16 * 1024 + (k & 3) * 32);
-                const uint64_t bd = make_desc_mnmajor_sw64(va + k * 1024);
-                tc_mma_bf16(tmem, ad, bd, idesc2, k != 0);
+            for (int w = 0; w < 2; w++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {   // 64 own keys = 4 K-steps (+32 B inside the 128 B rows), V_w advances 16 rows = 1 KB
+                    const uint64_t ad = make_desc_kmajor_sw128(pa + k * 32);
+                    const uint64_t bd = make_desc_mnmajor_sw64(va + w * 4096 + k * 1024);
+                    tc_mma_bf16(tmem + w * 32, ad, bd, idesc2, k != 0);
+                }
             }
             tc_commit(bar_mma);
         }
@@ -200,9 +210,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
         ph_mma ^= 1;
         tc_fence_after();
         float o[32];
-        const uint32_t orow = tmem + ((uint32_t)(warp * 32) << 16);
-        tc_ld16(orow, o);
-        tc_ld16(orow + 16, o + 16);
+        {
+            uint32_t* orr = reinterpret_cast<uint32_t*>(o);
+            tc_ld32_nowait(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, orr);
+            tc_ld_wait();
+        }
         if (row_ok) {
             __nv_bfloat16* dst = O + (win * WT + i) * (int64_t)C + h * HD;
 #pragma unroll
@@ -216,7 +228,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
             }
         }
         tc_fence_before();
-        __syncthreads();   // TMEM columns and the Q/K/V/P tiles are free for the next unit
+        __syncthreads();   // TMEM columns and the P tile are free for the next unit
     }
     if (warp == 0) {
         tc_fence_after();
@@ -246,7 +258,7 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
         attr = true;
     }
     const int64_t pairs = (n_windows + 1) / 2;
-    const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 4 + nH - 1) / nH));
+    const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3 + nH - 1) / nH));
     dim3 grid(gx, nH);
     winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, bias, reinterpret_cast<__nv_bfloat16*>(O), n_windows, nH, g);
     count_launch();
@@ -267,10 +279,13 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
 // ================================================================================================
 constexpr int AB_TILE = 8 * 1024;          // one [128 x 32] bf16 operand tile (two 64-row boxes)
 constexpr int AB_X = 16 * 1024;            // one [128 x 64] bf16 P / dS tile
-// + one spare tile: the M=128 MN-major A descriptors of dV / dK read a second 64-key chunk `AB_X` bytes after the
-// real one (its products land in TMEM lanes 64..127, which nobody reads) and must stay inside the allocation.
-constexpr int AB_SMEM = 4 * AB_TILE + 3 * AB_X + AT_BIAS_BYTES + 64 + 1024;
+constexpr int AB_OPS = 4 * AB_TILE;        // one stage of Q, K, V, dO
+constexpr int AB_SMEM = 2 * AB_X + 2 * AB_OPS + AT_BIAS_BYTES + 64 + 1024;
 
+// Operand tiles are double buffered (the loads of unit n+1 are issued before unit n is touched).  dV / dK of window w
+// use ONE MN-major A descriptor over the compact tile with the two 64-key chunks 8 KB apart (= the two windows' row
+// blocks): the products of window w's rows land in TMEM lanes 64 w .. 64 w + 63 (the other half holds unused values),
+// so every thread drains its own key row of dV, dK and its query row of dQ — a balanced epilogue.
 __global__ void __launch_bounds__(128, 2)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_partial,
@@ -278,22 +293,20 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + AB_TILE;
-    uint8_t* sV = sK + AB_TILE;
-    uint8_t* sD = sV + AB_TILE;                 // dO
-    uint8_t* sXP = sD + AB_TILE;                // P rows
+    uint8_t* sXP = smem;                        // P rows
     uint8_t* sXS = sXP + AB_X;                  // dS rows
-    float* sBias = reinterpret_cast<float*>(sXS + 2 * AB_X);
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);
-    uint64_t* bar_mma = bar_load + 1;
+    uint8_t* sOps = sXS + AB_X;                 // [2][Q | K | V | dO]
+    float* sBias = reinterpret_cast<float*>(sOps + 2 * AB_OPS);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);   // [2]
+    uint64_t* bar_mma = bar_load + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int C = nH * HD;
     const int h = blockIdx.y;
     for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
     if (tid == 0) {
-        mbar_init(bar_load, 1);
+        mbar_init(&bar_load[0], 1);
+        mbar_init(&bar_load[1], 1);
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -312,27 +325,39 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
     const uint32_t id_kv = make_idesc_bf16(128, 32, 1, 1);     // dV, dK: A MN-major, B MN-major
     const uint32_t id_q = make_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
-    uint32_t ph_load = 0, ph_mma = 0;
+    uint32_t ph_mma = 0;
     float acc[WT];
 #pragma unroll
     for (int j = 0; j < WT; j++) acc[j] = 0.f;
 
+    auto issue_loads = [&](int64_t pair, int buf) {
+        uint8_t* q = sOps + buf * AB_OPS;
+        mbar_arrive_expect_tx(&bar_load[buf], 8 * 4096);
+        const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
+        tma_load_2d(q, &tmQKV, &bar_load[buf], h * HD, r0);
+        tma_load_2d(q + 4096, &tmQKV, &bar_load[buf], h * HD, r1);
+        tma_load_2d(q + AB_TILE, &tmQKV, &bar_load[buf], C + h * HD, r0);
+        tma_load_2d(q + AB_TILE + 4096, &tmQKV, &bar_load[buf], C + h * HD, r1);
+        tma_load_2d(q + 2 * AB_TILE, &tmQKV, &bar_load[buf], 2 * C + h * HD, r0);
+        tma_load_2d(q + 2 * AB_TILE + 4096, &tmQKV, &bar_load[buf], 2 * C + h * HD, r1);
+        tma_load_2d(q + 3 * AB_TILE, &tmDO, &bar_load[buf], h * HD, r0);
+        tma_load_2d(q + 3 * AB_TILE + 4096, &tmDO, &bar_load[buf], h * HD, r1);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < n_pairs) issue_loads(blockIdx.x, 0);
+
     int it = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, it++) {
+        const int buf = it & 1;
         const int64_t win = pair * 2 + half;
+        uint8_t* sQ = sOps + buf * AB_OPS;
+        uint8_t* sK = sQ + AB_TILE;
+        uint8_t* sV = sK + AB_TILE;
+        uint8_t* sD = sV + AB_TILE;                 // dO
         AT_TRACE(0);
         if (tid == 0) {
-            mbar_arrive_expect_tx(bar_load, 8 * 4096);
-            const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
-            tma_load_2d(sQ, &tmQKV, bar_load, h * HD, r0);
-            tma_load_2d(sQ + 4096, &tmQKV, bar_load, h * HD, r1);
-            tma_load_2d(sK, &tmQKV, bar_load, C + h * HD, r0);
-            tma_load_2d(sK + 4096, &tmQKV, bar_load, C + h * HD, r1);
-            tma_load_2d(sV, &tmQKV, bar_load, 2 * C + h * HD, r0);
-            tma_load_2d(sV + 4096, &tmQKV, bar_load, 2 * C + h * HD, r1);
-            tma_load_2d(sD, &tmDO, bar_load, h * HD, r0);
-            tma_load_2d(sD + 4096, &tmDO, bar_load, h * HD, r1);
-            mbar_wait(bar_load, ph_load);
+            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
+            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
+            mbar_wait(&bar_load[buf], (it >> 1) & 1);
             tc_fence_after();
             AT_TRACE(1);
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
@@ -343,7 +368,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tc_mma_bf16(tmem + 128, dd + 2, vd + 2, id_s, 1);
             tc_commit(bar_mma);
         }
-        ph_load ^= 1;
         const bool row_ok = (i < WT) && (win < n_windows);
         const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
         const int ri = region_tc(mi, i);
@@ -357,9 +381,16 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         for (int j = 0; j < 32; j++) { pk[j] = 0u; dk_[j] = 0u; }
         {
             float s[64], dp[64];
-            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
-            tc_ld16(trow, s); tc_ld16(trow + 16, s + 16); tc_ld16(trow + 32, s + 32); tc_ld16(trow + 48, s + 48);
-            tc_ld16(trow + 128, dp); tc_ld16(trow + 144, dp + 16); tc_ld16(trow + 160, dp + 32); tc_ld16(trow + 176, dp + 48);
+            {
+                uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+                uint32_t* dr = reinterpret_cast<uint32_t*>(dp);
+                const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
+                tc_ld32_nowait(trow, sr);
+                tc_ld32_nowait(trow + 32, sr + 32);
+                tc_ld32_nowait(trow + 128, dr);
+                tc_ld32_nowait(trow + 160, dr + 32);
+                tc_ld_wait();
+            }
             if (row_ok) {
                 float mx = -INFINITY;
 #pragma unroll
@@ -406,11 +437,14 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tc_fence_after();
             const uint32_t xp = smem_u32(sXP), xs = smem_u32(sXS);
             const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sD);
+#pragma unroll
             for (int w = 0; w < 2; w++) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {   // contraction over the 64 rows of window w, 16 rows (2 KB of X, 1 KB of B) per step
-                    const uint64_t ap = make_desc_mnmajor_sw128(xp + w * 8192 + k * 2048, AB_X);
-                    const uint64_t as = make_desc_mnmajor_sw128(xs + w * 8192 + k * 2048, AB_X);
+                    // M chunk 0 = keys of window a (rows [16k, 16k+16) of block a), chunk 1 = 8 KB further = block b:
+                    // with window w's B rows only lanes [64 w, 64 w + 64) are meaningful
+                    const uint64_t ap = make_desc_mnmajor_sw128(xp + k * 2048, 8192);
+                    const uint64_t as = make_desc_mnmajor_sw128(xs + k * 2048, 8192);
                     tc_mma_bf16(tmem + w * 32, ap, make_desc_mnmajor_sw64(da + w * 4096 + k * 1024), id_kv, k != 0);       // dV_w
                     tc_mma_bf16(tmem + 64 + w * 32, as, make_desc_mnmajor_sw64(qa + w * 4096 + k * 1024), id_kv, k != 0);  // dK_w
                 }
@@ -427,42 +461,25 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tc_fence_after();
         AT_TRACE(5);
         {
-            float o[32];
+            // own query row of dQ and own key row of dK, dV (lanes 64..127 hold window b): three 64 B stores per thread
+            float dq[32], dkk[32], dvv[32];
             const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-            // dQ: own row
-            tc_ld16(lane_base + 128 + half * 32, o);
-            tc_ld16(lane_base + 128 + half * 32 + 16, o + 16);
+            tc_ld32_nowait(lane_base + 128 + half * 32, reinterpret_cast<uint32_t*>(dq));
+            tc_ld32_nowait(lane_base + 64 + half * 32, reinterpret_cast<uint32_t*>(dkk));
+            tc_ld32_nowait(lane_base + half * 32, reinterpret_cast<uint32_t*>(dvv));
+            tc_ld_wait();
             if (row_ok) {
                 __nv_bfloat16* dst = dqkv + (win * WT + i) * (int64_t)(3 * C) + h * HD;
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pk2(o[8 * c] * ATT_SCALE, o[8 * c + 1] * ATT_SCALE),
-                        pk2(o[8 * c + 2] * ATT_SCALE, o[8 * c + 3] * ATT_SCALE), pk2(o[8 * c + 4] * ATT_SCALE, o[8 * c + 5] * ATT_SCALE),
-                        pk2(o[8 * c + 6] * ATT_SCALE, o[8 * c + 7] * ATT_SCALE));
-            }
-            // dK / dV: key-indexed results of BOTH windows live in lanes 0..63 -> warps 0,1 store them
-            if (warp < 2) {
-                for (int w = 0; w < 2; w++) {
-                    const int64_t wn = pair * 2 + w;
-                    const bool ok = (i < WT) && (wn < n_windows);
-                    __nv_bfloat16* dst = dqkv + (wn * WT + i) * (int64_t)(3 * C) + h * HD;
-                    tc_ld16(lane_base + 64 + w * 32, o);
-                    tc_ld16(lane_base + 64 + w * 32 + 16, o + 16);
-                    if (ok) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            *reinterpret_cast<uint4*>(dst + C + 8 * c) = make_uint4(pk2(o[8 * c] * ATT_SCALE, o[8 * c + 1] * ATT_SCALE),
-                                pk2(o[8 * c + 2] * ATT_SCALE, o[8 * c + 3] * ATT_SCALE), pk2(o[8 * c + 4] * ATT_SCALE, o[8 * c + 5] * ATT_SCALE),
-                                pk2(o[8 * c + 6] * ATT_SCALE, o[8 * c + 7] * ATT_SCALE));
-                    }
-                    tc_ld16(lane_base + w * 32, o);
-                    tc_ld16(lane_base + w * 32 + 16, o + 16);
-                    if (ok) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            *reinterpret_cast<uint4*>(dst + 2 * C + 8 * c) = make_uint4(pk2(o[8 * c], o[8 * c + 1]), pk2(o[8 * c + 2], o[8 * c + 3]),
-                                pk2(o[8 * c + 4], o[8 * c + 5]), pk2(o[8 * c + 6], o[8 * c + 7]));
-                    }
+                for (int c = 0; c < 4; c++) {
+                    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
+                        pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
+                        pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
+                    *reinterpret_cast<uint4*>(dst + C + 8 * c) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
+                        pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
+                        pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
+                    *reinterpret_cast<uint4*>(dst + 2 * C + 8 * c) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
+                        pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
                 }
             }
         }
