@@ -74,7 +74,7 @@ constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 102
 //   MMA 2:  O_w[128 x 32] = P[:, own keys] V_w for w = a, b into TMEM columns [32 w, 32 w + 32): rows of the other
 //           window hold unused values; V is read MN-major straight from its TMA tile (no transpose)
 __global__ void __launch_bounds__(128, 3)
-winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ bias, __nv_bfloat16* __restrict__ O,
+winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
                       int64_t n_windows, int nH, WinGeo g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -136,6 +136,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
             // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
             if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
+            tma_store_wait_read0();      // the previous unit's output boxes (staged in the P tile) have left shared memory
             tc_fence_after();
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
             tc_mma_bf16(tmem, qd, kd, idesc1, 0);
@@ -215,8 +216,10 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
             tc_ld32_nowait(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, orr);
             tc_ld_wait();
         }
-        if (row_ok) {
-            __nv_bfloat16* dst = O + (win * WT + i) * (int64_t)C + h * HD;
+        // O row -> staging box of its window ([49 x 32] bf16, 64B swizzle) in the P tile (MMA 2 has consumed it); the
+        // two boxes leave as TMA stores: per-thread 64 B row stores were 32 separate lines per instruction
+        {
+            uint8_t* orow = sP + half * 4096 + i * 64;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 uint4 v;
@@ -224,12 +227,19 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const float* __res
                 v.y = pk2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
                 v.z = pk2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
                 v.w = pk2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-                *reinterpret_cast<uint4*>(dst + 8 * c) = v;
+                *reinterpret_cast<uint4*>(orow + ((c ^ ((i >> 1) & 3)) << 4)) = v;
             }
         }
+        fence_proxy_async_smem();
         tc_fence_before();
-        __syncthreads();   // TMEM columns and the P tile are free for the next unit
+        __syncthreads();   // TMEM columns are free for the next unit; the staged rows are complete
+        if (tid == 0) {
+            for (int w = 0; w < 2; w++)
+                if (pair * 2 + w < n_windows) tma_store_2d(sP + w * 4096, &tmO, h * HD, (int)((pair * 2 + w) * WT));
+            tma_store_commit();
+        }
     }
+    if (tid == 0) tma_store_wait_all();
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
@@ -242,7 +252,16 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15)) return 1;
     const int64_t rows = n_windows * WT;
-    CUtensorMap tm;
+    CUtensorMap tm, tmO;
+    {   // output [rows, C], box = one window's [49 x 32] head slice
+        cuuint64_t od[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+        cuuint64_t os[1] = {(cuuint64_t)C * 2};
+        cuuint32_t ob[2] = {32, (cuuint32_t)WT};
+        cuuint32_t oe[2] = {1, 1};
+        if (tc_get_encode()(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, O, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    }
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
     cuuint32_t box[2] = {32, 64};
@@ -260,7 +279,7 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     const int64_t pairs = (n_windows + 1) / 2;
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3 + nH - 1) / nH));
     dim3 grid(gx, nH);
-    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, bias, reinterpret_cast<__nv_bfloat16*>(O), n_windows, nH, g);
+    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tmO, bias, n_windows, nH, g);
     count_launch();
     return check_launch("winattn_fwd_tc");
 }
@@ -288,7 +307,7 @@ constexpr int AB_SMEM = 2 * AB_X + 2 * AB_OPS + AT_BIAS_BYTES + 64 + 1024;
 // so every thread drains its own key row of dV, dK and its query row of dQ — a balanced epilogue.
 __global__ void __launch_bounds__(128, 2)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_partial,
+                      const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
                       int64_t n_windows, int nH, WinGeo g, long long* trace) {
 #define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -358,6 +377,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
             if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
+            tma_store_wait_read0();      // the previous unit's output boxes (staged in the P / dS tiles) have left shared memory
             tc_fence_after();
             AT_TRACE(1);
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
@@ -468,26 +488,36 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tc_ld32_nowait(lane_base + 64 + half * 32, reinterpret_cast<uint32_t*>(dkk));
             tc_ld32_nowait(lane_base + half * 32, reinterpret_cast<uint32_t*>(dvv));
             tc_ld_wait();
-            if (row_ok) {
-                __nv_bfloat16* dst = dqkv + (win * WT + i) * (int64_t)(3 * C) + h * HD;
+            // rows -> staging boxes [window][dq | dk | dv][49 x 32] (64B swizzle) in the P / dS tiles (consumed by the
+            // MMAs above); they leave as six TMA stores instead of 32-line scattered stores per instruction
+            uint8_t* row = sXP + half * 3 * 4096 + i * 64;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
-                        pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
-                        pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
-                    *reinterpret_cast<uint4*>(dst + C + 8 * c) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
-                        pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
-                        pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
-                    *reinterpret_cast<uint4*>(dst + 2 * C + 8 * c) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
-                        pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
-                }
+            for (int c = 0; c < 4; c++) {
+                const int sw = (c ^ ((i >> 1) & 3)) << 4;
+                *reinterpret_cast<uint4*>(row + sw) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
+                    pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
+                    pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
+                *reinterpret_cast<uint4*>(row + 4096 + sw) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
+                    pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
+                    pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
+                *reinterpret_cast<uint4*>(row + 8192 + sw) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
+                    pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
             }
         }
         AT_TRACE(6);
+        fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (tid == 0) {
+            for (int w = 0; w < 2; w++)
+                if (pair * 2 + w < n_windows)
+                    for (int part = 0; part < 3; part++)
+                        tma_store_2d(sXP + (w * 3 + part) * 4096, &tmOut, part * C + h * HD, (int)((pair * 2 + w) * WT));
+            tma_store_commit();
+        }
         AT_TRACE(7);
     }
+    if (tid == 0) tma_store_wait_all();
     // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i
     if (i < WT) {
         float* out = dbias_partial + (((int64_t)blockIdx.x * 2 + half) * nH + h) * (WT * WT) + i * WT;
@@ -500,10 +530,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
 }
 
-static bool make_attn_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols) {
+static bool make_attn_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int box_rows = 64) {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {32, 64};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return tc_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -521,8 +551,10 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15)) return 1;
-    CUtensorMap tmQKV, tmDO;
-    if (!make_attn_map(&tmQKV, qkv, n_windows * WT, 3 * C) || !make_attn_map(&tmDO, dO, n_windows * WT, C)) return 1;
+    CUtensorMap tmQKV, tmDO, tmOut;
+    if (!make_attn_map(&tmQKV, qkv, n_windows * WT, 3 * C) || !make_attn_map(&tmDO, dO, n_windows * WT, C) ||
+        !make_attn_map(&tmOut, dqkv, n_windows * WT, 3 * C, WT))
+        return 1;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(winattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
@@ -538,8 +570,8 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         cudaMalloc(&trace_buf, trace_n * sizeof(long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
     }
-    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, bias, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_partial,
-                                                    n_windows, nH, g, trace_on ? trace_buf : nullptr);
+    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmOut, bias, dbias_partial, n_windows, nH, g,
+                                                    trace_on ? trace_buf : nullptr);
     if (trace_on) {   // debug only: synchronous dump of the per-unit phase timeline of two CTAs
         long long* host = (long long*)malloc(trace_n * sizeof(long long));
         cudaStreamSynchronize(st);
