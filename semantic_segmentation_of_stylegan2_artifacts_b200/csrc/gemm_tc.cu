@@ -36,7 +36,8 @@ struct TcParams {
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
     int stages;               // operand pipeline depth
-    int epi_tma;              // 1: unmapped output -> per-warp swizzled slabs + TMA stores (Cpre out / R or H in through TMA too)
+    int epi_tma;              // 1: per-warp swizzled slabs + TMA stores (Cpre out / R or H in through TMA too); depth-to-space maps
+                              //    ride on a 5-D tensor map of the output (the TMA unit does the scatter)
     int epi_bytes;            // shared memory per epilogue warp
     int a_stage, b_stage;     // bytes per pipeline stage of the A / B operand rings
     long long* trace;         // debug (MSU_TC_TRACE=1): clock64 stamps [cta][tile < 8][16 events]
@@ -406,8 +407,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (warp == 2 && first) TC_TRACE(8);
                 if (lane == 0) {
-                    tma_store_2d(slab_out, &tmC, n0, row0);
-                    if (E.Cpre != nullptr) tma_store_2d(slab_aux, &tmAux, n0, row0);
+                    if (E.map == MSU_MAP_NONE) {
+                        tma_store_2d(slab_out, &tmC, n0, row0);
+                        if (E.Cpre != nullptr) tma_store_2d(slab_aux, &tmAux, n0, row0);
+                    } else if (E.map == MSU_MAP_SHUFFLE) {
+                        // rows = 32 tokens (b, h, w0..w0+31), columns = 32 channels of one (p1, p2): box [32 c, 1, 32 w, 1, 1]
+                        const int Wt = E.geo[1], pp = E.geo[2], cc = E.geo[3];
+                        const int q = n0 / cc, c0 = n0 - q * cc, p1 = q / pp, p2 = q - p1 * pp;
+                        const int bh = row0 / Wt, w0 = row0 - bh * Wt;
+                        tma_store_5d(slab_out, &tmC, c0, p2, w0, p1, bh);
+                        if (E.Cpre != nullptr) tma_store_5d(slab_aux, &tmAux, c0, p2, w0, p1, bh);
+                    } else {
+                        // UNSHUFFLE: rows = 32 pixels (b, y, x0..x0+31) of the shuffled map, box [32 c, p (p2), 32/p (w), 1, 1]
+                        const int Wt = E.geo[1], pp = E.geo[2];
+                        const int Wp = Wt * pp;
+                        const int by = row0 / Wp, x0 = row0 - by * Wp;          // by = b * (H p) + y
+                        const int Hp = E.geo[0] * pp;
+                        const int b = by / Hp, y = by - b * Hp;
+                        tma_store_5d(slab_out, &tmC, n0, 0, x0 / pp, y % pp, b * E.geo[0] + y / pp);
+                    }
                     tma_store_commit();
                 }
                 if (warp == 2 && first) TC_TRACE(9);
@@ -697,6 +715,13 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     // unmapped outputs whose tile rows are consecutive leave through TMA stores (conv tiles: whole-row tiles only)
     bool epi_tma = env_epi != 1 && E->map == MSU_MAP_NONE && !(E->R && E->H) && !(E->Cpre && (E->R || E->H)) &&
                    E->ldr == E->ldc;
+    // depth-to-space output maps: every 32-row x 32-column slab is one box of a 5-D view of the output
+    if (env_epi != 1 && E->map == MSU_MAP_SHUFFLE && !E->R && !E->H && E->geo[1] % 32 == 0 && E->geo[3] % 32 == 0 &&
+        E->ldc == E->geo[3] && N == (int64_t)E->geo[2] * E->geo[2] * E->geo[3] && A->map == MSU_MAP_NONE)
+        epi_tma = true;
+    if (env_epi != 1 && E->map == MSU_MAP_UNSHUFFLE && !E->R && !E->Cpre && 32 % E->geo[2] == 0 &&
+        (E->geo[1] * E->geo[2]) % 32 == 0 && N == E->geo[3] && E->ldc == (int64_t)E->geo[2] * E->geo[2] * E->geo[3])
+        epi_tma = true;
     if (A->map == MSU_MAP_CONV3 && A->geo[1] % 128 != 0) epi_tma = false;
     const int naux = E->Cpre ? 1 : ((E->R || E->H) ? 2 : 0);
     p.epi_tma = epi_tma ? 1 : 0;
@@ -801,10 +826,38 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     const int smem = p.stages * stage_bytes_final + fixed_bytes;
     CUtensorMap tmC = tmB, tmAux = tmB;
     if (epi_tma) {
-        if (!make_map_slab(&tmC, E->C, M, N, E->ldc)) return 1;
         const void* aux = E->Cpre ? E->Cpre : (E->R ? E->R : E->H);
         const int64_t ldaux = E->Cpre ? E->ldc : (E->R ? E->ldr : E->ldh);
-        if (aux != nullptr && !make_map_slab(&tmAux, aux, M, N, ldaux)) return 1;
+        if (E->map == MSU_MAP_NONE) {
+            if (!make_map_slab(&tmC, E->C, M, N, E->ldc)) return 1;
+            if (aux != nullptr && !make_map_slab(&tmAux, aux, M, N, ldaux)) return 1;
+        } else {
+            // 5-D view (c, p2, w, p1, b*H + h) of the depth-to-space tensor: SHUFFLE memory is [(b, h p + p1, w p + p2), c],
+            // UNSHUFFLE memory is [(b, h, w), (p1 p2 c)]
+            const int Ht = E->geo[0], Wt = E->geo[1], pp = E->geo[2], cc = E->geo[3];
+            const int64_t BH = (E->map == MSU_MAP_SHUFFLE ? M : M / ((int64_t)pp * pp)) / Wt;
+            cuuint64_t gdim[5] = {(cuuint64_t)cc, (cuuint64_t)pp, (cuuint64_t)Wt, (cuuint64_t)pp, (cuuint64_t)BH};
+            cuuint64_t gstr[4];
+            cuuint32_t box[5] = {32, 1, 32, 1, 1};
+            if (E->map == MSU_MAP_SHUFFLE) {
+                gstr[0] = (cuuint64_t)cc * 2; gstr[1] = (cuuint64_t)pp * cc * 2; gstr[2] = (cuuint64_t)Wt * pp * cc * 2;
+                gstr[3] = (cuuint64_t)pp * Wt * pp * cc * 2;
+            } else {
+                gstr[0] = (cuuint64_t)cc * 2; gstr[1] = (cuuint64_t)pp * pp * cc * 2; gstr[2] = (cuuint64_t)pp * cc * 2;
+                gstr[3] = (cuuint64_t)Wt * pp * pp * cc * 2;
+                box[1] = (cuuint32_t)pp; box[2] = (cuuint32_t)(32 / pp);
+            }
+            (void)Ht;
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            auto enc5 = [&](CUtensorMap* tm, const void* ptr) {
+                return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            if (!enc5(&tmC, E->C)) return 1;
+            if (E->Cpre != nullptr && !enc5(&tmAux, E->Cpre)) return 1;
+            if (E->H != nullptr && !make_map_slab(&tmAux, E->H, M, N, E->ldh)) return 1;   // gelu' operand: unmapped [M, N]
+        }
     }
     static int smem_set = 0;
     if (smem > smem_set) {

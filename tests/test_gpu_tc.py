@@ -124,8 +124,9 @@ def test_output_maps_window_and_shuffle(ops):
     tc, simt = run_both(ops, go)
     assert relmax(tc, simt) < 8e-3
     # depth-to-space x2 and x4 (PatchExpand / head expand) with GELU and pre-activation copy
-    for (p, Cin, cc) in [(2, 192, 96), (4, 96, 96), (2, 96, 48)]:
-        Hh = 8
+    # (Hh = 32 / 64 with 32-aligned channel groups take the TMA-store epilogue over a 5-D view of the output)
+    for (p, Cin, cc, Hh) in [(2, 192, 96, 8), (4, 96, 96, 8), (2, 96, 48, 8), (2, 192, 96, 32), (4, 96, 96, 32), (2, 128, 64, 64),
+                             (4, 96, 96, 24)]:
         T = 2 * Hh * Hh
         x = torch.randn(T, Cin).bfloat16().to(DEV)
         N = p * p * cc
