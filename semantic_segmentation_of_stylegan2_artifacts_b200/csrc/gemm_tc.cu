@@ -1312,9 +1312,17 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     }
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 6) p.stages = 6;
+    static const int env_wstages = getenv("MSU_WGRAD_STAGES") ? atoi(getenv("MSU_WGRAD_STAGES")) : 0;
+    if (env_wstages && p.stages > env_wstages) p.stages = env_wstages;
     if (p.stages < 2) return 1;
     p.slabs = (int64_t)p.Bn * H * (W / p.WB);
-    int splits = (2 * num_sms() + p.n_groups - 1) / p.n_groups;
+    // whole waves: resident CTAs per SM follow from the shared memory of a CTA (TMEM: G * BN columns each)
+    const int smem_cta = p.stages * stage_bytes + 4096;
+    int cps = smem_cta <= 113 * 1024 ? 2 : 1;
+    if (cps * p.G * p.BN > TC_TMEM_COLS) cps = 1;
+    int splits = (cps == 1 ? 2 : 1) * cps * num_sms() / p.n_groups;   // two waves of single CTAs, or one wave of pairs
+    if (p.halo) splits = cps * num_sms() / p.n_groups;
+    if (splits < 1) splits = 1;
     if (splits > p.slabs) splits = (int)p.slabs;
     while (splits > 1 && (int64_t)splits * I * (J + 1) > ws_elems) splits--;
     if ((int64_t)splits * I * (J + 1) > ws_elems) return 1;
@@ -1389,6 +1397,11 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
         p.BN = p.Qn <= 256 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 256, 32);
         p.MT = m_tiles < 4 ? m_tiles : 4;
     }
+    static const int env_mt = getenv("MSU_WG_MT") ? atoi(getenv("MSU_WG_MT")) : 0;       // tuning overrides (tools/wgrad_case.py)
+    static const int env_wbn = getenv("MSU_WG_BN") ? atoi(getenv("MSU_WG_BN")) : 0;
+    static const int env_splits = getenv("MSU_WG_SPLITS") ? atoi(getenv("MSU_WG_SPLITS")) : 0;
+    if (env_wbn) p.BN = p.Qn <= env_wbn ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, env_wbn, 32);
+    if (env_mt) p.MT = m_tiles < env_mt ? m_tiles : env_mt;
     p.n_q_tiles = (p.Qn + p.BN - 1) / p.BN;
     p.qboxes = (p.BN + 63) / 64;
     const bool want_bias = (E->colsum != nullptr);   // column sums of the call's A operand ride along (either side)
@@ -1402,6 +1415,7 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     if (p.stages < 2) return 1;
     const int base_ctas = p.n_super * p.n_q_tiles;
     int splits = (num_sms() + base_ctas - 1) / base_ctas;
+    if (env_splits) splits = env_splits;
     const int64_t max_splits_t = (T + 511) / 512;
     if (splits > max_splits_t) splits = (int)max_splits_t;
     const int nq = 1;   // bias partial rows per split

@@ -1,0 +1,70 @@
+// Micro-benchmark: tcgen05.mma issue rate (clocks per MMA) for K-major vs MN-major shared-memory operands, M=128,
+// N in {32, 96, 128, 256}, K=16, bf16.  One CTA per SM, one issuing thread, operands are fixed (uninitialised) tiles.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I semantic_segmentation_of_stylegan2_artifacts_b200/csrc \
+//        -o tools/build/mma_rate_bench tools/mma_rate_bench.cu      (analysis aid, not part of the library)
+#include <stdio.h>
+
+#include "tc_common.cuh"
+using namespace msu;
+
+__global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int iters, int kstep_bytes_a, int kstep_bytes_b, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+        long long t0 = clock64();
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const uint64_t ad = a_mn ? make_desc_mnmajor_sw128(a0 + ks * kstep_bytes_a, 8192) : make_desc_kmajor_sw128(a0 + ks * 32);
+                const uint64_t bd = b_mn ? make_desc_mnmajor_sw128(b0 + ks * kstep_bytes_b, 8192) : make_desc_kmajor_sw128(b0 + ks * 32);
+                tc_mma_bf16(tmem, ad, bd, idesc, 1);
+            }
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 8);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const int iters = 2000;
+    for (int N : {32, 64, 96, 128, 192, 256}) {
+        for (int mode = 0; mode < 4; mode++) {
+            const int a_mn = mode & 1, b_mn = mode >> 1;
+            k<<<148, 128, 100 * 1024>>>(N, a_mn, b_mn, iters, 2048, 2048, d);
+            long long h = 0;
+            cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaGetLastError();
+            const double clk = (double)h / (iters * 4);
+            printf("N=%3d A %s B %s : %7.1f clk/MMA  (ideal %5.1f)  %s\n", N, a_mn ? "MN-major" : "K-major ", b_mn ? "MN-major" : "K-major ", clk,
+                   128.0 * N * 16 * 2 / 8192, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+    }
+    return 0;
+}

@@ -10,7 +10,8 @@ from semantic_segmentation_of_stylegan2_artifacts_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 bf = torch.bfloat16
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-for (T, I, J) in [(262144, 384, 96), (283024, 288, 96), (262144, 96, 384), (65536, 768, 192), (78400, 576, 192),
+only = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]]
+for (T, I, J) in only or [(262144, 384, 96), (283024, 288, 96), (262144, 96, 384), (65536, 768, 192), (78400, 576, 192),
                   (16384, 1536, 384), (19600, 1152, 384), (16384, 384, 1536), (4096, 3072, 768), (7056, 2304, 768)]:
     dy = torch.randn(T, I, device=dev).to(bf)
     x = torch.randn(T, J, device=dev).to(bf)
