@@ -77,14 +77,29 @@ __device__ __forceinline__ int64_t merge_off(const MergeGeo& mg, int64_t lr, int
     return (b * (int64_t)(mg.H * mg.W) + y * mg.W + x) * Cin + ci;
 }
 
+// Both kernels are templated on the row map so that each instantiation is straight-line code (ncu showed the generic
+// version issue-bound at ~23 instructions per element: runtime map branches, gamma / beta reloaded per row, IEEE
+// divisions); gamma / beta / the dot weight live in registers for narrow rows, statistics use rsqrtf and a host-side 1/C.
+constexpr int LNM_PLAIN = 0, LNM_WINDOW = 1, LNM_MERGE = 2, LNM_DOT = 3, LNM_UNSHUFFLE = 4;
+
+__device__ __forceinline__ float group_sum_u(float v, int lpr) {   // branch-free: always five shuffles, selects for lpr < 32
+    float t;
+    t = __shfl_xor_sync(0xffffffffu, v, 16); v += lpr > 16 ? t : 0.f;
+    t = __shfl_xor_sync(0xffffffffu, v, 8);  v += lpr > 8 ? t : 0.f;
+    t = __shfl_xor_sync(0xffffffffu, v, 4);  v += lpr > 4 ? t : 0.f;
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 // Forward: every warp owns LN_RG row groups (rpw rows each) whose 16 B loads are all issued before the first
 // reduction, so ~2x the bytes are in flight per warp (the one-group version topped out at 3.4 TB/s).
 constexpr int LN_RG = 2;
-template <typename T, int NV>
+template <typename T, int NV, int MODE>
 __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ Y,
                                                               float* __restrict__ mean, float* __restrict__ rstd,
-                                                              int64_t rows, int C, int lpr, int in_map, int out_map,
+                                                              int64_t rows, int C, float invC, int lpr,
                                                               WinGeo wg, MergeGeo mg, const float* __restrict__ dotw) {
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
@@ -92,85 +107,85 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(
     const int Cin = C / 4;
     const int64_t wbase = ((int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_RG;
     int64_t r[LN_RG], lr[LN_RG];
-    bool in_range[LN_RG], pad[LN_RG];
+    bool live[LN_RG];
     uint4 xr[LN_RG][NV];
+    bool vld[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) vld[j] = (l + lpr * j) * VW < C;
 #pragma unroll
     for (int g = 0; g < LN_RG; g++) {
         r[g] = (wbase + g) * rpw + sub;
-        in_range[g] = r[g] < rows;
         lr[g] = r[g];       // LayerNorm row (statistics index)
-        pad[g] = false;
-        if (in_range[g] && out_map == MSU_MAP_WINDOW) {
+        live[g] = r[g] < rows;
+        if (MODE == LNM_WINDOW && live[g]) {
             lr[g] = win_to_pix(wg, r[g]);
-            pad[g] = lr[g] < 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
+            live[g] = lr[g] >= 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
         }
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
             xr[g][j] = make_uint4(0, 0, 0, 0);
-            if (in_range[g] && !pad[g] && c < C) {
-                const T* p = (in_map == MSU_MAP_MERGE) ? X + merge_off(mg, lr[g], c, Cin) : X + lr[g] * C + c;
+            if (live[g] && vld[j]) {
+                const T* p = (MODE == LNM_MERGE) ? X + merge_off(mg, lr[g], c, Cin) : X + lr[g] * C + c;
                 xr[g][j] = *reinterpret_cast<const uint4*>(p);
             }
         }
     }
 #pragma unroll
     for (int g = 0; g < LN_RG; g++) {
-        const bool live = in_range[g] && !pad[g];
+        float x[NV][VW];
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            float x[VW];
-            cvt_raw<T>(xr[g][j], x);
+            cvt_raw<T>(xr[g][j], x[j]);
 #pragma unroll
-            for (int e = 0; e < VW; e++) s += x[e];
+            for (int e = 0; e < VW; e++) s += x[j][e];
         }
-        const float mu = group_sum(s, lpr) / C;
+        const float mu = group_sum_u(s, lpr) * invC;
         float v = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            const int c = (l + lpr * j) * VW;
-            if (c < C) {
-                float x[VW];
-                cvt_raw<T>(xr[g][j], x);
+            if (vld[j]) {
 #pragma unroll
-                for (int e = 0; e < VW; e++) { const float a = x[e] - mu; v = fmaf(a, a, v); }
+                for (int e = 0; e < VW; e++) { const float a = x[j][e] - mu; v = fmaf(a, a, v); }
             }
         }
-        const float rs = 1.0f / sqrtf(group_sum(v, lpr) / C + LN_EPS);
-        if (live && l == 0) {
+        const float rs = rsqrtf(group_sum_u(v, lpr) * invC + LN_EPS);
+        const float nmr = -mu * rs;
+        if (live[g] && l == 0) {
             mean[lr[g]] = mu;
             rstd[lr[g]] = rs;
         }
+        const bool in_range = r[g] < rows;
         float dot = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
-            if (in_range[g] && c < C) {
+            if (in_range && vld[j]) {
                 float y[VW];
+                if (live[g]) {
+                    float gl[VW], bl[VW];
+                    ldf(gamma + c, gl, VW);
+                    ldf(beta + c, bl, VW);
 #pragma unroll
-                for (int e = 0; e < VW; e++) y[e] = 0.f;
-                if (!pad[g]) {
-                    float x[VW], gm[VW], b[VW];
-                    cvt_raw<T>(xr[g][j], x);
-                    ldf(gamma + c, gm, VW);
-                    ldf(beta + c, b, VW);
+                    for (int e = 0; e < VW; e++) y[e] = fmaf(fmaf(x[j][e], rs, nmr), gl[e], bl[e]);
+                } else {
 #pragma unroll
-                    for (int e = 0; e < VW; e++) y[e] = (x[e] - mu) * rs * gm[e] + b[e];
+                    for (int e = 0; e < VW; e++) y[e] = 0.f;
                 }
-                if (dotw != nullptr) {
-                    float w[VW];
-                    ldf(dotw + c, w, VW);
+                if (MODE == LNM_DOT) {
+                    float wl[VW];
+                    ldf(dotw + c, wl, VW);
 #pragma unroll
-                    for (int e = 0; e < VW; e++) dot = fmaf(y[e], w[e], dot);
+                    for (int e = 0; e < VW; e++) dot = fmaf(y[e], wl[e], dot);
                 } else {
                     VecW<T>::st(Y + r[g] * C + c, y);
                 }
             }
         }
-        if (dotw != nullptr) {
-            dot = group_sum(dot, lpr);
-            if (in_range[g] && l == 0) Y[r[g]] = from_f<T>(dot);
+        if (MODE == LNM_DOT) {
+            dot = group_sum_u(dot, lpr);
+            if (in_range && l == 0) Y[r[g]] = from_f<T>(dot);
         }
     }
 }
@@ -180,20 +195,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(
 // Operands stay packed (16 B) in registers between the two passes over a row and the residual gradient is requested
 // together with x and dy, so a row group costs ONE memory round trip and the kernel fits 2 blocks (16 warps) per SM:
 // ~75 KB of loads in flight per SM instead of 24 KB (the first version ran at 8 warps/SM and ~1.4 TB/s).
-template <typename T, int NV, bool DOT>
+template <typename T, int NV, int MODE, bool RES>
 __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ X,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const T* __restrict__ dRes, T* __restrict__ dX, int64_t rows,
-                                                              int C, int lpr, int dy_map, int dx_map, WinGeo wg, MergeGeo mg,
+                                                              int C, float invC, int lpr, WinGeo wg, MergeGeo mg,
                                                               const float* __restrict__ dotw, float* __restrict__ partial,
                                                               MsuOperand ug) {
+    constexpr bool DOT = MODE == LNM_DOT;
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
     const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int64_t P = (int64_t)gridDim.x * LN_WARPS;
     constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
+    bool vld[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) vld[j] = (l + lpr * j) * VW < C;
     // ag = sum dy * x-hat (DOT: sum dl * x-hat), ab = sum dy (DOT: the scalar sum dl lives in ab[0][0])
     float ag[NV][VW], ab[DOT ? 1 : NV][DOT ? 1 : VW];
 #pragma unroll
@@ -211,28 +230,29 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
         const bool live = lr < rows;
         const float mu = live ? mean[lr] : 0.f, rs = live ? rstd[lr] : 0.f;
         const float nmr = -mu * rs;
-        const int64_t dyr = (live && dy_map == MSU_MAP_WINDOW) ? pix_to_win(wg, lr) : lr;
+        const int64_t dyr = (MODE == LNM_WINDOW && live) ? pix_to_win(wg, lr) : lr;
         const float dl = (DOT && live) ? to_f<T>(dY[lr]) : 0.f;
         const int64_t rowoff = lr * C;
-        uint4 xr[NV], yr[DOT ? 1 : NV], rr[NV];
+        uint4 xr[NV], yr[DOT ? 1 : NV], rr[RES ? NV : 1];
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
-            if (live && c < C) {
-                const int64_t xo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
+            if (live && vld[j]) {
+                const int64_t xo = (MODE == LNM_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
                 xr[j] = *reinterpret_cast<const uint4*>(X + xo);
                 if (!DOT) yr[DOT ? 0 : j] = *reinterpret_cast<const uint4*>(dY + dyr * C + c);
-                if (dRes != nullptr) rr[j] = *reinterpret_cast<const uint4*>(dRes + xo);
+                if (RES) rr[RES ? j : 0] = *reinterpret_cast<const uint4*>(dRes + xo);
             }
         }
+        // pass 1: row sums of g = dy * gamma and g * x-hat
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            const int c = (l + lpr * j) * VW;
-            if (live && c < C) {
-                float x[VW], dy[VW], gm[VW];
+            if (live && vld[j]) {
+                const int c = (l + lpr * j) * VW;
+                float x[VW], dy[VW], gl[VW];
                 cvt_raw<T>(xr[j], x);
-                ldf(gamma + c, gm, VW);
+                ldf(gamma + c, gl, VW);
                 if (DOT) {
                     ldf(dotw + c, dy, VW);
 #pragma unroll
@@ -242,23 +262,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                 }
 #pragma unroll
                 for (int e = 0; e < VW; e++) {
-                    const float g = dy[e] * gm[e];
+                    const float g = dy[e] * gl[e];
                     s1 += g;
                     s2 = fmaf(g, fmaf(x[e], rs, nmr), s2);
                 }
             }
         }
-        s1 = group_sum(s1, lpr) / C;
-        s2 = group_sum(s2, lpr) / C;
-        const float k1 = -s1 * rs;
+        s1 = group_sum_u(s1, lpr) * invC;
+        s2 = group_sum_u(s2, lpr) * invC;
+        const float k1 = -s1 * rs, k2 = -s2 * rs;
         if (DOT) ab[0][0] += dl;
+        // pass 2: dx = rs * (g - s1 - xh * s2) + dres, parameter gradients d gamma += dy * x-hat, d beta += dy
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
-            if (live && c < C) {
-                float x[VW], dy[VW], gm[VW], dx[VW];
+            if (live && vld[j]) {
+                float x[VW], dy[VW], gl[VW], dx[VW];
                 cvt_raw<T>(xr[j], x);
-                ldf(gamma + c, gm, VW);
+                ldf(gamma + c, gl, VW);
                 if (DOT) {
                     ldf(dotw + c, dy, VW);
 #pragma unroll
@@ -266,21 +287,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                 } else {
                     cvt_raw<T>(yr[DOT ? 0 : j], dy);
                 }
-                if (dRes != nullptr) cvt_raw<T>(rr[j], dx);
+                if (RES) cvt_raw<T>(rr[RES ? j : 0], dx);
                 else {
 #pragma unroll
                     for (int e = 0; e < VW; e++) dx[e] = 0.f;
                 }
 #pragma unroll
                 for (int e = 0; e < VW; e++) {
-                    const float xh = fmaf(x[e], rs, nmr);                 // x-hat
-                    // dx = rs * (dy*gamma - s1 - xh*s2) + dres
-                    dx[e] += fmaf(dy[e] * gm[e], rs, fmaf(-xh * s2, rs, k1));
+                    const float xh = fmaf(x[e], rs, nmr);
+                    dx[e] += fmaf(dy[e] * gl[e], rs, fmaf(xh, k2, k1));
                     ag[j][e] = fmaf(DOT ? dl : dy[e], xh, ag[j][e]);
                     if (!DOT) ab[DOT ? 0 : j][DOT ? 0 : e] += dy[e];
                 }
-                int64_t wo = (dx_map == MSU_MAP_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
-                if (dx_map == MSU_MAP_UNSHUFFLE) {   // gradient written straight in the inverse depth-to-space layout
+                int64_t wo = (MODE == LNM_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
+                if (MODE == LNM_UNSHUFFLE) {   // gradient written straight in the inverse depth-to-space layout
                     const RowCol rc = map_rc(MSU_MAP_UNSHUFFLE, ug.geo, lr, c);
                     wo = rc.row * (int64_t)(ug.geo[2] * ug.geo[2] * ug.geo[3]) + rc.col;
                 }
@@ -307,16 +327,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
         const int c = (l + lpr * j) * VW;
         if (sub == 0 && c < C) {
             if (DOT) {   // dy = dl * w: dgamma = w S1, dbeta = w S0, d(dot weight) = gamma S1 + beta S0
-                float w[VW], gm[VW], bt[VW];
+                float w[VW], gl[VW], bt[VW];
                 ldf(dotw + c, w, VW);
-                ldf(gamma + c, gm, VW);
+                ldf(gamma + c, gl, VW);
                 ldf(beta + c, bt, VW);
 #pragma unroll
                 for (int e = 0; e < VW; e += 4) {
                     *reinterpret_cast<float4*>(pg + c + e) = make_float4(w[e] * ag[j][e], w[e + 1] * ag[j][e + 1], w[e + 2] * ag[j][e + 2], w[e + 3] * ag[j][e + 3]);
                     *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(w[e] * s0, w[e + 1] * s0, w[e + 2] * s0, w[e + 3] * s0);
-                    *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(fmaf(gm[e], ag[j][e], bt[e] * s0), fmaf(gm[e + 1], ag[j][e + 1], bt[e + 1] * s0),
-                                                                                 fmaf(gm[e + 2], ag[j][e + 2], bt[e + 2] * s0), fmaf(gm[e + 3], ag[j][e + 3], bt[e + 3] * s0));
+                    *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(fmaf(gl[e], ag[j][e], bt[e] * s0), fmaf(gl[e + 1], ag[j][e + 1], bt[e + 1] * s0),
+                                                                                 fmaf(gl[e + 2], ag[j][e + 2], bt[e + 2] * s0), fmaf(gl[e + 3], ag[j][e + 3], bt[e + 3] * s0));
                 }
             } else {
 #pragma unroll
@@ -368,8 +388,22 @@ static int launch_fwd(const void* X, const float* gamma, const float* beta, void
     if (in_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
     const int rpb = LN_WARPS * (32 / lpr) * LN_RG;
     const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
-    ln_fwd_kernel<T, NV><<<grid, LN_WARPS * 32, 0, st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd, rows, C, lpr, in_map,
-                                                        out_map, wg, mg, dotw);
+    const float invC = 1.0f / (float)C;
+#define LN_FWD_LAUNCH(MODE)                                                                                               \
+    ln_fwd_kernel<T, NV, MODE><<<grid, LN_WARPS * 32, 0, st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd, rows, C, invC, lpr, \
+                                                              wg, mg, dotw)
+    if (dotw != nullptr) {
+        if (in_map != MSU_MAP_NONE || out_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: dotw with a row map is not supported"); return -1; }
+        LN_FWD_LAUNCH(LNM_DOT);
+    } else if (out_map == MSU_MAP_WINDOW) {
+        if (in_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: in_map and out_map together are not supported"); return -1; }
+        LN_FWD_LAUNCH(LNM_WINDOW);
+    } else if (in_map == MSU_MAP_MERGE) {
+        LN_FWD_LAUNCH(LNM_MERGE);
+    } else {
+        LN_FWD_LAUNCH(LNM_PLAIN);
+    }
+#undef LN_FWD_LAUNCH
     count_launch();
     return check_launch("msu_ln_fwd");
 }
@@ -384,14 +418,24 @@ static int launch_bwd(const void* dY, const void* X, const float* gamma, const f
     if (dx_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
     MsuOperand ug{};
     if (dx_map == MSU_MAP_UNSHUFFLE) for (int k = 0; k < 4; k++) ug.geo[k] = geo[k];
-    if (dotw != nullptr)
-        ln_bwd_kernel<T, NV, true><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,
-                                                                  (const T*)dRes, (T*)dX, rows, C, lpr, dy_map, dx_map, wg, mg,
-                                                                  dotw, partial, ug);
-    else
-        ln_bwd_kernel<T, NV, false><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,
-                                                                   (const T*)dRes, (T*)dX, rows, C, lpr, dy_map, dx_map, wg, mg,
-                                                                   dotw, partial, ug);
+    const float invC = 1.0f / (float)C;
+#define LN_BWD_LAUNCH(MODE, RES)                                                                                           \
+    ln_bwd_kernel<T, NV, MODE, RES><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,     \
+                                                                   (const T*)dRes, (T*)dX, rows, C, invC, lpr, wg, mg, dotw, partial, ug)
+    const int nmaps = (dy_map != MSU_MAP_NONE) + (dx_map != MSU_MAP_NONE) + (dotw != nullptr);
+    if (nmaps > 1) { set_error("msu_ln_bwd: at most one of dy_map / dx_map / dotw"); return -1; }
+    if (dotw != nullptr) {
+        if (dRes) LN_BWD_LAUNCH(LNM_DOT, true); else LN_BWD_LAUNCH(LNM_DOT, false);
+    } else if (dy_map == MSU_MAP_WINDOW) {
+        if (dRes) LN_BWD_LAUNCH(LNM_WINDOW, true); else LN_BWD_LAUNCH(LNM_WINDOW, false);
+    } else if (dx_map == MSU_MAP_MERGE) {
+        if (dRes) LN_BWD_LAUNCH(LNM_MERGE, true); else LN_BWD_LAUNCH(LNM_MERGE, false);
+    } else if (dx_map == MSU_MAP_UNSHUFFLE) {
+        if (dRes) LN_BWD_LAUNCH(LNM_UNSHUFFLE, true); else LN_BWD_LAUNCH(LNM_UNSHUFFLE, false);
+    } else {
+        if (dRes) LN_BWD_LAUNCH(LNM_PLAIN, true); else LN_BWD_LAUNCH(LNM_PLAIN, false);
+    }
+#undef LN_BWD_LAUNCH
     count_launch();
     return check_launch("msu_ln_bwd");
 }
