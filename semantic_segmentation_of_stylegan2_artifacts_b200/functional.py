@@ -40,6 +40,54 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# Weight-gradient side stream: dW / db GEMMs (and their split-K reduces) are off the critical path of a block's
+# backward, so they are enqueued on a second stream and overlap the dgrad chain (small reduce kernels fill the SMs a
+# persistent GEMM leaves idle).  Every Function joins the side stream before it returns, so tensor lifetimes stay
+# those of the main stream (the caching allocator never sees a cross-stream use after free) and CUDA-graph capture
+# records a plain fork / join.  MSUNET_B200_WGRAD_STREAM=0 keeps everything on one stream.
+# ----------------------------------------------------------------------------------------------
+import os as _os
+
+_WG_ON = _os.environ.get("MSUNET_B200_WGRAD_STREAM", "1") != "0"
+_wg_streams: dict = {}
+
+
+class _WgradFork:
+    def __init__(self, dev):
+        self.on = _WG_ON and ops.PROF is None      # per-op profiling keeps one stream (events bracket each launch)
+        self.keep = []                             # temporaries read on the side stream: released after the join
+        if self.on:
+            st = _wg_streams.get(dev.index)
+            if st is None:
+                st = _wg_streams[dev.index] = torch.cuda.Stream(device=dev)
+            self.side = st
+            self.main = torch.cuda.current_stream(dev)
+
+    def run(self, fn):
+        """fn() enqueues GEMMs whose inputs are complete on the main stream at this point."""
+        if not self.on:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            fn()
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+    def __enter__(self):
+        self._prev = ops.SIDE
+        ops.SIDE = self if self.on else None
+        return self
+
+    def __exit__(self, *exc):
+        ops.SIDE = self._prev
+        self.join()
+        return False
+
+
+# ----------------------------------------------------------------------------------------------
 # bf16 weight shadows (caller-owned tensors, refreshed when the fp32 master changes)
 # ----------------------------------------------------------------------------------------------
 _shadows: dict = {}
@@ -138,17 +186,19 @@ class SwinBlockFn(Function):
         T, HW, Tw, hid = B * H * W, H * W, B * nW * 49, f1w.shape[0]
         dx2 = _c(dx2).view(T, Cd)
         f32 = dict(dtype=torch.float32, device=dev)
+        wg = _WgradFork(dev)
+        wg.__enter__()
         # ---- MLP half
         dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
-        # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum: one extra N=16 MMA against ones)
+        # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum)
         db2 = torch.empty(Cd, **f32)
         dW2 = torch.empty(Cd, hid, **f32)
-        gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev)
+        wg.run(lambda: gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev))
         dh = torch.empty(T, hid, dtype=dt, device=dev)
         gemm(dy2, w_dgrad(f2w, dt), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
         db1 = torch.empty(hid, **f32)
         dW1 = torch.empty(hid, Cd, **f32)
-        gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev)
+        wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))
         dxn = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
         dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
@@ -156,16 +206,18 @@ class SwinBlockFn(Function):
         dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
         dbp = torch.empty(Cd, **f32)
         dWp = torch.empty(Cd, Cd, **f32)
-        gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev)
+        wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))
         do = torch.empty(Tw, Cd, dtype=dt, device=dev)
         gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
         dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo)
         dbqkv = torch.empty(3 * Cd, **f32)
         dWqkv = torch.empty(3 * Cd, Cd, **f32)
-        gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv), 3 * Cd, Cd, Tw, dev)
+        wg.run(lambda: gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv),
+                            3 * Cd, Cd, Tw, dev))
         dxw = torch.empty(Tw, Cd, dtype=dt, device=dev)
         gemm(operand(dqkv), w_dgrad(qkvw, dt), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
         dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
+        wg.__exit__()
         return (dx.view(B, H, W, Cd), dn1w, dn1b, dWqkv, dbqkv, dWp, dbp, dtable, dn2w, dn2b, dW1, db1, dW2, db2,
                 None, None, None, None, None, None, None)
 
@@ -199,10 +251,11 @@ class PatchEmbedFn(Function):
         dev = y.device
         T = y.shape[0]
         dout = _c(dout).view(T, E)
-        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, T, E)
-        dpb = torch.empty(E, dtype=torch.float32, device=dev)
-        dW64 = torch.empty(E, 64, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True, colsum=dpb), E, 64, T, dev)
+        with _WgradFork(dev):
+            dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, T, E)
+            dpb = torch.empty(E, dtype=torch.float32, device=dev)
+            dW64 = torch.empty(E, 64, dtype=torch.float32, device=dev)
+            gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True, colsum=dpb), E, 64, T, dev)
         dpw = ops.prep_weight(6, dW64, E, 48, (E, 3, 4, 4), torch.float32)
         return None, dpw, dpb, dnw, dnb, None
 
@@ -234,10 +287,11 @@ class PatchMergeFn(Function):
         Tm = B * (H // 2) * (W // 2)
         dy = _c(dy).view(Tm, 2 * Cd)
         drw = torch.empty(2 * Cd, 4 * Cd, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(xm, orient=1), epilogue(drw, out_f32=True), 2 * Cd, 4 * Cd, Tm, dev)
-        dxm = torch.empty(Tm, 4 * Cd, dtype=dt, device=dev)
-        gemm(operand(dy), w_dgrad(rw, dt), epilogue(dxm), Tm, 4 * Cd, 2 * Cd, dev)
-        dx, dnw, dnb, _ = ops.ln_bwd(dxm, x, nw, nb, mean, rstd, Tm, 4 * Cd, dx_map=MAP_MERGE, geo=[H, W, Cd])
+        with _WgradFork(dev) as wg:
+            wg.run(lambda: gemm(operand(dy, orient=1), operand(xm, orient=1), epilogue(drw, out_f32=True), 2 * Cd, 4 * Cd, Tm, dev))
+            dxm = torch.empty(Tm, 4 * Cd, dtype=dt, device=dev)
+            gemm(operand(dy), w_dgrad(rw, dt), epilogue(dxm), Tm, 4 * Cd, 2 * Cd, dev)
+            dx, dnw, dnb, _ = ops.ln_bwd(dxm, x, nw, nb, mean, rstd, Tm, 4 * Cd, dx_map=MAP_MERGE, geo=[H, W, Cd])
         return dx, dnw, dnb, drw, None, None, None
 
 
@@ -270,12 +324,13 @@ class PatchExpandFn(Function):
         c2 = Cd // 2
         dout = _c(dout).view(4 * T, c2)
         # LayerNorm backward writes its result straight in the inverse depth-to-space layout [T, 2C]
-        dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2, dx_map=MAP_UNSHUFFLE, geo=geo,
-                                     dx_shape=(T, 2 * Cd))
-        dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev)
-        dx = torch.empty(T, Cd, dtype=dt, device=dev)
-        gemm(operand(dy), w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
+        with _WgradFork(dev) as wg:
+            dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2, dx_map=MAP_UNSHUFFLE, geo=geo,
+                                         dx_shape=(T, 2 * Cd))
+            dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
+            wg.run(lambda: gemm(operand(dy, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev))
+            dx = torch.empty(T, Cd, dtype=dt, device=dev)
+            gemm(operand(dy), w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
         return dx.view(xshape), dew, dnw, dnb, None, None, None
 
 
@@ -305,14 +360,19 @@ class ConcatLinearFn(Function):
         dy = _c(dy).view(T, Cd)
         db = torch.empty(Cd, dtype=torch.float32, device=dev)
         dw = torch.empty(Cd, 2 * Cd, dtype=torch.float32, device=dev)
-        gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True, colsum=db),
-             Cd, Cd, T, dev)
-        gemm(operand(dy, orient=1), operand(skip.view(T, Cd), orient=1),
-             epilogue(dw, ldc=2 * Cd, out_f32=True, offset=Cd), Cd, Cd, T, dev)
-        dx = torch.empty(T, Cd, dtype=dt, device=dev)
-        dskip = torch.empty(T, Cd, dtype=dt, device=dev)
-        gemm(operand(dy), w_dgrad(w, dt, 0, Cd), epilogue(dx), T, Cd, Cd, dev)
-        gemm(operand(dy), w_dgrad(w, dt, Cd, Cd), epilogue(dskip), T, Cd, Cd, dev)
+
+        def wgrads():
+            gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True, colsum=db),
+                 Cd, Cd, T, dev)
+            gemm(operand(dy, orient=1), operand(skip.view(T, Cd), orient=1),
+                 epilogue(dw, ldc=2 * Cd, out_f32=True, offset=Cd), Cd, Cd, T, dev)
+
+        with _WgradFork(dev) as wg:
+            wg.run(wgrads)
+            dx = torch.empty(T, Cd, dtype=dt, device=dev)
+            dskip = torch.empty(T, Cd, dtype=dt, device=dev)
+            gemm(operand(dy), w_dgrad(w, dt, 0, Cd), epilogue(dx), T, Cd, Cd, dev)
+            gemm(operand(dy), w_dgrad(w, dt, Cd, Cd), epilogue(dskip), T, Cd, Cd, dev)
         return dx.view(x.shape), dskip.view(skip.shape), dw, db
 
 

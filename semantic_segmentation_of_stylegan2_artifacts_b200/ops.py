@@ -84,6 +84,20 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     return e
 
 
+SIDE = None  # functional.py: the active weight-gradient fork (parameter-gradient reduces ride on its side stream)
+
+
+def _off_path(fn, *keep):
+    """Run a launch whose result is only needed after the backward joins (parameter-gradient reductions).
+    `keep`: temporaries read by that launch; they must outlive the join (the caching allocator would otherwise hand
+    their memory to a later main-stream allocation while the side stream still reads it)."""
+    if SIDE is not None:
+        SIDE.keep.extend(keep)
+        SIDE.run(fn)
+    else:
+        fn()
+
+
 PROF = None  # bench.py / tools set this to a list to collect (tag, start_event, end_event, bytes, flops) per launch
 
 
@@ -171,8 +185,8 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     dg = torch.empty(Cdim, dtype=torch.float32, device=dev)
     db = torch.empty(Cdim, dtype=torch.float32, device=dev)
     dw = torch.empty(Cdim, dtype=torch.float32, device=dev) if dotw is not None else None
-    L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), L.ptr(dw), 0,
-                                        L.stream_ptr()), "msu_ln_param_reduce")
+    _off_path(lambda: L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), L.ptr(dw), 0,
+                                                          L.stream_ptr()), "msu_ln_param_reduce"), part)
     _p1(e0, (rows, Cdim, 0, "ln_bwd" + ("_dot" if dotw is not None else "") + ("_res" if dres is not None else "")),
         (dy.numel() + (2 + (dres is not None)) * rows * Cdim) * x.element_size())
     return dx, dg, db, dw
@@ -207,8 +221,8 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
                                     dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p),
                                     L.stream_ptr()), "msu_winattn_bwd")
     dtable = torch.empty(169, nH, dtype=torch.float32, device=dev)
-    L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
-            "msu_relbias_reduce")
+    _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
+                              "msu_relbias_reduce"), part)
     _p1(e0, (n_windows, nH, 0, "winattn_bwd"), (2 * qkv.numel() + 2 * o.numel()) * qkv.element_size(),
         5 * 2 * n_windows * nH * 49 * 49 * 32)
     return dqkv, dtable
