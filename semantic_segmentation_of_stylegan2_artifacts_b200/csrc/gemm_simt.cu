@@ -144,27 +144,37 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(MsuOperand A, MsuOperand 
     }
 }
 
-__global__ void splitk_reduce_kernel(MsuEpilogue E, int64_t M, int64_t N, int splits, const float* ws, const float* bws, int brows) {
+// `sscale` (optional): per-sample scale of the contraction rows (stochastic depth on the gradient rows); every split
+// lies inside one sample (splits_per_sample of them each), so the scale is applied to whole partials.
+__global__ void splitk_reduce_kernel(MsuEpilogue E, int64_t M, int64_t N, int splits, const float* ws, const float* bws, int brows,
+                                     const float* sscale, int splits_per_sample) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * N) {
         // bias-gradient partials [split][M] of the fused column sums (fixed order: deterministic)
         const int64_t m = idx - M * N;
         if (bws != nullptr && m < M) {
             float b = 0.f;
-            for (int z = 0; z < brows; z++) b += bws[(int64_t)z * M + m];
+            for (int z = 0; z < brows; z++) {
+                const float v = bws[(int64_t)z * M + m];
+                b += sscale != nullptr ? v * sscale[z / splits_per_sample] : v;
+            }
             E.colsum[m] = b;
         }
         return;
     }
     float s = 0.f;
-    for (int z = 0; z < splits; z++) s += ws[(int64_t)z * M * N + idx];  // fixed order: deterministic
+    if (sscale != nullptr) {
+        for (int z = 0; z < splits; z++) s = fmaf(ws[(int64_t)z * M * N + idx], sscale[z / splits_per_sample], s);
+    } else {
+        for (int z = 0; z < splits; z++) s += ws[(int64_t)z * M * N + idx];  // fixed order: deterministic
+    }
     epilogue_store(E, idx / N, (int)(idx % N), s);
 }
 
 void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st,
-                          const float* bws, int brows) {
+                          const float* bws, int brows, const float* sscale, int splits_per_sample) {
     const int64_t tot = M * N + (bws != nullptr ? M : 0);
-    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, M, N, splits, ws, bws, brows);
+    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, M, N, splits, ws, bws, brows, sscale, splits_per_sample);
     count_launch();
 }
 
@@ -185,7 +195,7 @@ int gemm_simt(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, in
     count_launch();
     if (splits > 1) {
         const int64_t tot = M * N;
-        splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*E, M, N, splits, splitk_ws, nullptr, 0);
+        splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*E, M, N, splits, splitk_ws, nullptr, 0, nullptr, 1);
         count_launch();
     }
     return check_launch("gemm_simt");

@@ -1112,7 +1112,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
 }
 
 void launch_splitk_reduce(const MsuEpilogue& E, int64_t M, int64_t N, int splits, const float* ws, cudaStream_t st,
-                          const float* bws = nullptr, int brows = 0);
+                          const float* bws = nullptr, int brows = 0, const float* sscale = nullptr, int splits_per_sample = 1);
 
 // ================================================================================================
 // 3x3 conv weight gradient on tcgen05:  dW[co, (tap, ci)] = sum_pix dZ[pix, co] * X[pix + off(tap), ci]
@@ -1374,7 +1374,11 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
         return wgrad_conv_tc(A, B, E, I, J, T, ws, ws_elems, st, fused_colsum);
     }
     if (A->orient != 1 || B->orient != 1 || A->map != MSU_MAP_NONE || B->map != MSU_MAP_NONE) return 1;
-    if (A->ptr2 || B->ptr2 || A->rowscale || B->rowscale) return 1;
+    if (A->ptr2 || B->ptr2 || B->rowscale) return 1;
+    // per-sample scale of A's token rows (stochastic depth on gradient rows): every split is kept inside one sample and
+    // the reduce scales whole partials, so the scaled rows are never materialised
+    const int64_t rps = A->rowscale ? A->rows_per_sample : 0;
+    if (A->rowscale && (rps < WG_BK || rps % WG_BK != 0 || T % rps != 0)) return 1;
     if (E->map != MSU_MAP_NONE || E->bias || E->R || E->H || E->Cpre || E->act || E->rowscale) return 1;
     if ((A->ld % 8) || (B->ld % 8) || !aligned16(A->ptr) || !aligned16(B->ptr) || (I % 8) || (J % 8)) return 1;
     if (T < 512 || ws == nullptr || get_encode() == nullptr) return 1;
@@ -1423,6 +1427,14 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     if ((int64_t)splits * I * (J + nq) > ws_elems) return 1;
     int64_t tps = (T + splits - 1) / splits;
     tps = (tps + WG_BK - 1) / WG_BK * WG_BK;
+    int sps = 1;                                  // splits per sample
+    if (rps) {
+        // tokens per split = rps / sps with sps a power of two (rps = H*W is one), as close to the balanced choice as possible
+        while (sps * 2 <= rps / WG_BK && rps / (sps * 2) >= tps && (rps / (sps * 2)) % WG_BK == 0) sps *= 2;
+        if (rps % sps != 0 || (rps / sps) % WG_BK != 0) return 1;
+        tps = rps / sps;
+        if ((T / tps) * I * (J + nq) > ws_elems) return 1;
+    }
     splits = (int)((T + tps - 1) / tps);
     p.splits = splits; p.tok_per_split = tps;
     p.bws = want_bias ? ws + (int64_t)splits * I * J : nullptr;
@@ -1449,7 +1461,7 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     }
     wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, tmW, p);
     count_launch();
-    launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq);
+    launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq, A->rowscale, sps);
     if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;
     return check_launch("wgrad_tc");
 }

@@ -189,13 +189,21 @@ class SwinBlockFn(Function):
         wg = _WgradFork(dev)
         wg.__enter__()
         # ---- MLP half
-        dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
+        # stochastic-depth scale of the incoming gradient rows: large maps never materialise sd2 * dx2 — the dgrad GEMM scales its
+        # output rows in the epilogue and the weight-gradient GEMM keeps every split-K slab inside one sample and scales whole
+        # partials in its reduce (MsuOperand.rowscale); small maps (few tokens per sample) gather the scaled rows once
+        fused_sd = dt == BF16 and sd2 is not None and HW >= 4096 and HW % 64 == 0
+        if fused_sd:
+            dy2, dy2t = operand(dx2), operand(dx2, orient=1, rowscale=sd2, rps=HW)
+        else:
+            dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
         # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum)
         db2 = torch.empty(Cd, **f32)
         dW2 = torch.empty(Cd, hid, **f32)
         wg.run(lambda: gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev))
         dh = torch.empty(T, hid, dtype=dt, device=dev)
-        gemm(dy2, w_dgrad(f2w, dt), epilogue(dh, H=h, ldh=hid), T, hid, Cd, dev)
+        gemm(dy2, w_dgrad(f2w, dt),
+             epilogue(dh, H=h, ldh=hid, rowscale=sd2 if fused_sd else None, rps=HW if fused_sd else 0), T, hid, Cd, dev)
         db1 = torch.empty(hid, **f32)
         dW1 = torch.empty(hid, Cd, **f32)
         wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))

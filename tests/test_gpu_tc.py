@@ -178,6 +178,31 @@ def test_wgrad_mn_major(ops, shape):
     assert torch.equal(tcb, run_both(ops, go_bias)[0])
 
 
+@pytest.mark.parametrize("shape", [(4, 4096, 96, 384), (3, 1024, 384, 96), (16, 256, 192, 192), (2, 16384, 96, 96)])
+def test_wgrad_per_sample_rowscale(ops, shape):
+    """dW = sum_t s[sample(t)] dY[t]^T X[t] (stochastic depth on gradient rows): split-K slabs stay inside a sample and the
+    reduce scales whole partials; the fused bias gradient is scaled the same way."""
+    Bn, HW, I, J = shape
+    T = Bn * HW
+    torch.manual_seed(HW + I)
+    dy = torch.randn(T, I).bfloat16().to(DEV)
+    x = torch.randn(T, J).bfloat16().to(DEV)
+    sd = (torch.rand(Bn) > 0.3).float().div(0.7).to(DEV)
+
+    def go():
+        dw = torch.empty(I, J, dtype=torch.float32, device=DEV)
+        db = torch.full((I,), float("nan"), dtype=torch.float32, device=DEV)
+        ops.gemm(ops.operand(dy, orient=1, rowscale=sd, rps=HW), ops.operand(x, orient=1), ops.epilogue(dw, out_f32=True, colsum=db),
+                 I, J, T, dy.device)
+        return torch.cat([dw.flatten(), db])
+
+    tc, simt = run_both(ops, go)
+    dys = dy.double().cpu() * sd.double().cpu().repeat_interleave(HW)[:, None]
+    ref = torch.cat([(dys.t() @ x.double().cpu()).flatten(), dys.sum(0)])
+    assert relmax(tc, ref) < 2e-5 and relmax(simt, ref) < 2e-5
+    assert torch.equal(tc, run_both(ops, go)[0])
+
+
 @pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128), (3, 48, 64)])
 def test_conv3x3_wgrad(ops, geom):
     """dW[co,(tap ci)] = sum_pix dZ[pix,co] X[pix+off(tap),ci] with shifted NHWC slabs straight from TMA."""
