@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--drop-path", type=float, default=0.1)
+    ap.add_argument("--attn-drop", type=float, default=0.0, help="attention dropout (config.yaml of the reference: 0.05)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -162,7 +163,7 @@ def main():
     B, S = args.batch, args.img
 
     torch.manual_seed(1234)
-    model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, **T96).set_precision(args.precision).to(dev).train()
+    model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, attn_drop_rate=args.attn_drop, **T96).set_precision(args.precision).to(dev).train()
     if world > 1:
         from semantic_segmentation_of_stylegan2_artifacts_b200.dp import DataParallelB200
         model = DataParallelB200(model)
@@ -321,7 +322,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"MS-UNet T96 (embed 96, depths 2-2-6-2, window 7) training step fwd+DynamicLoss+bwd, "
-                                   f"{S}x{S}, batch {B}/GPU (global {B * world}), drop_path {args.drop_path}",
+                                   f"{S}x{S}, batch {B}/GPU (global {B * world}), drop_path {args.drop_path}, attn_drop {args.attn_drop}",
                        "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                        "l2": "working set >> L2: ~10 GB of activations are written and re-read every step",
                        "optimizer": "excluded (metric is fwd+bwd)"},

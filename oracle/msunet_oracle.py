@@ -258,6 +258,33 @@ def window_attention(x: torch.Tensor, sd, p: str, nH: int, shift: int) -> torch.
     return out[:, : H * W].reshape(B, H, W, C)
 
 
+def _lowbias32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64)
+    m = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def attn_drop_keep(n_windows: int, nH: int, p: float, seed0: int, seed1: int) -> torch.Tensor:
+    """Keep mask [n_windows, nH, 49, 49] (bool) of this repo's attention dropout — a restatement of the counter hash in
+    csrc/common.cuh (attn_drop_hash / attn_drop_keep): one 32-bit hash per (window, head, query row, key pair), its two
+    16-bit halves decide the two keys, keep iff half >= round(p * 65536).  The reference draws its mask from torch's Philox
+    stream (TV:models/swin_transformer.py:205), which no other implementation can reproduce bit for bit; parity tests apply
+    THIS mask to the PyTorch restatement of the attention so that forward and backward are compared element for element."""
+    m = np.uint64(0xFFFFFFFF)
+    thr = int(p * 65536.0 + 0.5)
+    rowkey = np.arange(n_windows * nH * 49, dtype=np.uint64).reshape(n_windows, nH, 49, 1)
+    jp = np.arange(25, dtype=np.uint64).reshape(1, 1, 1, 25)
+    key = ((rowkey << np.uint64(5)) & m) + jp
+    x = (((key + np.uint64(seed0 & 0xFFFFFFFF)) & m) * np.uint64(0x9E3779B1)) & m
+    h = _lowbias32(x ^ np.uint64(seed1 & 0xFFFFFFFF))
+    lo, hi = h & np.uint64(0xFFFF), h >> np.uint64(16)
+    keep = np.stack([lo >= thr, hi >= thr], -1).reshape(n_windows, nH, 49, 50)[..., :49]
+    return torch.from_numpy(np.ascontiguousarray(keep))
+
+
 def _ln(x, sd, p):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], LN_EPS)
 

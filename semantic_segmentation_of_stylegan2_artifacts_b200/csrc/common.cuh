@@ -177,6 +177,36 @@ __device__ __forceinline__ RowCol map_rc(int map, const int32_t* geo, int64_t r,
     }
 }
 
+// ---- attention dropout (TV:models/swin_transformer.py:205 F.dropout on the softmax output) -----------------
+// Counter-based mask shared by forward and backward: one lowbias32 hash per (window, head, query row, key pair),
+// its two 16-bit halves decide the two keys; keep iff half >= thr, thr = round(p * 65536).  oracle/msunet_oracle.py
+// restates it (attn_drop_keep) so the parity tests apply the identical mask to the PyTorch reference.
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t attn_drop_hash(uint32_t rowkey, int jpair, uint32_t s0, uint32_t s1) {
+    return lowbias32((((rowkey << 5) + (uint32_t)jpair) + s0) * 0x9E3779B1u ^ s1);
+}
+__host__ __device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int j, uint32_t s0, uint32_t s1, uint32_t thr) {
+    const uint32_t h = attn_drop_hash(rowkey, j >> 1, s0, s1);
+    return ((j & 1) ? (h >> 16) : (h & 0xffffu)) >= thr;
+}
+struct AttnDrop {           // thr == 0: no dropout
+    uint32_t thr;
+    float inv_keep;
+    const uint32_t* seed;   // device pointer to two 32-bit words (written by the caller's RNG, CUDA-graph friendly)
+};
+inline AttnDrop make_attn_drop(float p, const uint32_t* seed) {
+    AttnDrop d{0u, 1.0f, nullptr};
+    if (p > 0.f && seed != nullptr) {
+        d.thr = (uint32_t)(p * 65536.0f + 0.5f);
+        d.inv_keep = 1.0f / (1.0f - p);
+        d.seed = seed;
+    }
+    return d;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (!n) {

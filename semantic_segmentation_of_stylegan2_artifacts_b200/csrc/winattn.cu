@@ -79,7 +79,7 @@ __device__ __forceinline__ void store_row(T* dst, const float* reg, float scale)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(AW * 32) winattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ bias,
-                                                             T* __restrict__ O, int64_t n_windows, int nH, WinGeo g) {
+                                                             T* __restrict__ O, int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
     extern __shared__ __align__(16) float smem[];
     float* sbias = smem;                                   // [49*49]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(AW * 32) winattn_fwd_kernel(const T* __restric
     for (int i = threadIdx.x; i < WT * WT; i += blockDim.x) sbias[i] = bias[h * WT * WT + i];
     __syncthreads();
     const int nwin_img = g.nwin();
+    const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
     for (int64_t win = (int64_t)blockIdx.x * AW + warp; win < n_windows; win += (int64_t)gridDim.x * AW) {
         const T* base = qkv + win * WT * 3 * (int64_t)C + h * HD;
         load_tile<T>(sK, base + C, 3 * C, lane, 1.f);
@@ -115,12 +116,13 @@ __global__ void __launch_bounds__(AW * 32) winattn_fwd_kernel(const T* __restric
 #pragma unroll
             for (int d = 0; d < HD; d++) o[d] = 0.f;
             float sum = 0.f;
+            const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + ic);
             for (int j = 0; j < WT; j++) {
                 const float p = expf(sc[j * 32 + lane] - mx);
                 sum += p;
-                axpy_row(o, p, sV + j * HD);
+                if (ad.thr == 0 || attn_drop_keep(rowkey, j, ds0, ds1, ad.thr)) axpy_row(o, p, sV + j * HD);
             }
-            if (act) store_row<T>(O + (win * WT + i) * (int64_t)C + h * HD, o, 1.0f / sum);
+            if (act) store_row<T>(O + (win * WT + i) * (int64_t)C + h * HD, o, ad.inv_keep / sum);
         }
         __syncwarp();
     }
@@ -131,9 +133,10 @@ template <typename T>
 __global__ void __launch_bounds__(AW * 32, 1) winattn_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ bias,
                                                                 const T* __restrict__ O, const T* __restrict__ dO,
                                                                 T* __restrict__ dqkv, float* __restrict__ dbias_partial,
-                                                                int64_t n_windows, int nH, WinGeo g) {
+                                                                int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
     extern __shared__ __align__(16) float smem[];
     float* sbias = smem;  // [2401] (+3 pad)
+    const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int PER_WARP = 4 * WT * HD + WT * 32 + 3 * 64 + 2404;
     float* sQ = smem + 2404 + warp * PER_WARP;  // scaled q
@@ -197,9 +200,12 @@ __global__ void __launch_bounds__(AW * 32, 1) winattn_bwd_kernel(const T* __rest
             // dO_i in registers (reuse q[] for it after S is done)
 #pragma unroll
             for (int d = 0; d < HD; d++) q[d] = sD[ic * HD + d];
+            const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + ic);
             for (int j = 0; j < WT; j++) {
                 const float p = sc[j * 32 + lane] * inv;
-                const float dp = dot_row(q, sV + j * HD);
+                // dP = m * dP~ with the forward's dropout mask m in {0, 1/keep}; delta_i = dO_i . O_i still equals sum_j P dP
+                const float m = (ad.thr == 0 || attn_drop_keep(rowkey, j, ds0, ds1, ad.thr)) ? ad.inv_keep : 0.f;
+                const float dp = dot_row(q, sV + j * HD) * m;
                 axpy_row(dq, p * (dp - dot_o), sK + j * HD);
             }
             if (act) {
@@ -221,9 +227,10 @@ __global__ void __launch_bounds__(AW * 32, 1) winattn_bwd_kernel(const T* __rest
                 float s = dot_row(k, sQ + i * HD) + sbias[i * WT + jc];
                 if (mi.any && region_of(mi, i) != rj) s += -100.0f;
                 const float p = expf(s - sM[i]) * sL[i];
-                const float dp = dot_row(v, sD + i * HD);
+                const float m = (ad.thr == 0 || attn_drop_keep((uint32_t)((win * nH + h) * WT + i), jc, ds0, ds1, ad.thr)) ? ad.inv_keep : 0.f;
+                const float dp = dot_row(v, sD + i * HD) * m;
                 const float ds = p * (dp - sDl[i]);
-                axpy_row(dv, p, sD + i * HD);
+                axpy_row(dv, p * m, sD + i * HD);
                 axpy_row(dk, ds, sQ + i * HD);
                 if (act) sdb[i * WT + j] += ds;
             }
@@ -296,10 +303,10 @@ static int attn_grid(int64_t n_windows, int nH) {
 }  // namespace msu
 
 namespace msu {
-int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, cudaStream_t st);
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st);
 int winattn_bwd_tc_grid(int64_t n_windows, int nH);
 int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
-                   int nH, const WinGeo& g, cudaStream_t st);
+                   int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st);
 static int g_attn_backend = 0;  // 0 auto (tcgen05 for bf16), 1 force the SIMT kernels
 }
 
@@ -308,25 +315,27 @@ using namespace msu;
 extern "C" int msu_set_attn_backend(int backend) { g_attn_backend = backend; return 0; }
 
 extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
-                               const int32_t* geo, void* stream) {
+                               const int32_t* geo, float p_drop, const uint32_t* seed, void* stream) {
     MSU_REQUIRE(qkv && bias && O && geo, "msu_winattn_fwd: null pointer");
     MSU_REQUIRE(nH > 0 && nH <= 65535, "msu_winattn_fwd: bad head count %d", nH);
+    MSU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "msu_winattn_fwd: bad dropout probability %f", (double)p_drop);
     if (n_windows == 0) return 0;
     WinGeo g = make_wingeo(geo);
+    const AttnDrop ad = make_attn_drop(p_drop, seed);
     dim3 grid(attn_grid(n_windows, nH), nH);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MSU_BF16 && g_attn_backend == 0) {
-        const int rc = winattn_fwd_tc(qkv, bias, O, n_windows, nH, g, st);
+        const int rc = winattn_fwd_tc(qkv, bias, O, n_windows, nH, g, ad, st);
         if (rc != 1) return rc;
     }
     if (dtype == MSU_F32) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr = true; }
-        winattn_fwd_kernel<float><<<grid, AW * 32, FWD_SMEM, st>>>((const float*)qkv, bias, (float*)O, n_windows, nH, g);
+        winattn_fwd_kernel<float><<<grid, AW * 32, FWD_SMEM, st>>>((const float*)qkv, bias, (float*)O, n_windows, nH, g, ad);
     } else if (dtype == MSU_BF16) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr = true; }
-        winattn_fwd_kernel<__nv_bfloat16><<<grid, AW * 32, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)O, n_windows, nH, g);
+        winattn_fwd_kernel<__nv_bfloat16><<<grid, AW * 32, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)O, n_windows, nH, g, ad);
     } else {
         MSU_REQUIRE(false, "msu_winattn_fwd: unsupported dtype %d", dtype);
     }
@@ -341,14 +350,17 @@ extern "C" int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH) {
 
 // O (the forward output) supplies delta_i = dO_i . O_i without a second P.V product.
 extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
-                               float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, void* stream) {
+                               float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
+                               const uint32_t* seed, void* stream) {
     MSU_REQUIRE(qkv && bias && O && dO && dqkv && dbias_partial && geo, "msu_winattn_bwd: null pointer");
+    MSU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "msu_winattn_bwd: bad dropout probability %f", (double)p_drop);
     WinGeo g = make_wingeo(geo);
+    const AttnDrop ad = make_attn_drop(p_drop, seed);
     const int gx = attn_grid(n_windows, nH);
     dim3 grid(gx, nH);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MSU_BF16 && g_attn_backend == 0) {
-        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, st);
+        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, ad, st);
         if (rc != 1) return rc;
         MSU_REQUIRE(false, "msu_winattn_bwd: tcgen05 path unavailable for these pointers (workspace was sized for it)");
     }
@@ -356,13 +368,13 @@ extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, co
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr = true; }
         winattn_bwd_kernel<float><<<grid, AW * 32, BWD_SMEM, st>>>((const float*)qkv, bias, (const float*)O, (const float*)dO,
-                                                                  (float*)dqkv, dbias_partial, n_windows, nH, g);
+                                                                  (float*)dqkv, dbias_partial, n_windows, nH, g, ad);
     } else if (dtype == MSU_BF16) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(winattn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr = true; }
         winattn_bwd_kernel<__nv_bfloat16><<<grid, AW * 32, BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (const __nv_bfloat16*)O,
                                                                           (const __nv_bfloat16*)dO, (__nv_bfloat16*)dqkv,
-                                                                          dbias_partial, n_windows, nH, g);
+                                                                          dbias_partial, n_windows, nH, g, ad);
     } else {
         MSU_REQUIRE(false, "msu_winattn_bwd: unsupported dtype %d", dtype);
     }

@@ -75,7 +75,7 @@ constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 102
 //           window hold unused values; V is read MN-major straight from its TMA tile (no transpose)
 __global__ void __launch_bounds__(128, 3)
 winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
-                      int64_t n_windows, int nH, WinGeo g) {
+                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sP = smem;
@@ -111,6 +111,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     const uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc2 = make_idesc_bf16(128, 32, 0, 1);
     uint32_t ph_mma = 0;
+    const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
 
     auto issue_loads = [&](int64_t pair, int buf) {
         uint8_t* q = sOps + buf * AT_OPS_BYTES;
@@ -181,7 +182,16 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
                 const float2 back = __bfloat1622float2(b2);      // normalise by what the tensor core will actually sum
                 sum += back.x + back.y;
             }
-            inv = 1.0f / sum;
+            inv = ad.inv_keep / sum;
+            if (ad.thr) {   // attention dropout: dropped probabilities leave the P tile (the row sum above is the undropped one)
+                const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
+#pragma unroll
+                for (int jp = 0; jp < 25; jp++) {
+                    const uint32_t hs = attn_drop_hash(rowkey, jp, ds0, ds1);
+                    if ((hs & 0xffffu) < ad.thr) pk[jp] &= 0xffff0000u;
+                    if ((hs >> 16) < ad.thr) pk[jp] &= 0x0000ffffu;
+                }
+            }
         }
         // P row -> compact tile: row tid, 8 x 16 B chunks, 128B swizzle (chunk ^ (row & 7)); padding rows are zero
         {
@@ -247,7 +257,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
 }
 
 // returns 0 launched, 1 unsupported
-int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, cudaStream_t st) {
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15)) return 1;
@@ -279,7 +289,7 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     const int64_t pairs = (n_windows + 1) / 2;
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3 + nH - 1) / nH));
     dim3 grid(gx, nH);
-    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tmO, bias, n_windows, nH, g);
+    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tmO, bias, n_windows, nH, g, ad);
     count_launch();
     return check_launch("winattn_fwd_tc");
 }
@@ -308,7 +318,7 @@ constexpr int AB_SMEM = 2 * AB_X + 2 * AB_OPS + AT_BIAS_BYTES + 64 + 1024;
 __global__ void __launch_bounds__(128, 2)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
-                      int64_t n_windows, int nH, WinGeo g, long long* trace) {
+                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad, long long* trace) {
 #define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -345,6 +355,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const uint32_t id_kv = make_idesc_bf16(128, 32, 1, 1);     // dV, dK: A MN-major, B MN-major
     const uint32_t id_q = make_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
     uint32_t ph_mma = 0;
+    const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
     float acc[WT];
 #pragma unroll
     for (int j = 0; j < WT; j++) acc[j] = 0.f;
@@ -423,19 +434,39 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
                 for (int j = 0; j < WT; j++) { s[j] = ex2_fast(s[j] - mx); sum += s[j]; }
                 const float inv = 1.0f / sum;
+                if (ad.thr) {   // attention dropout: dP = m * dP~ with the forward's mask m in {0, 1/keep}
+                    const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
+#pragma unroll
+                    for (int jp = 0; jp < 25; jp++) {
+                        const uint32_t hs = attn_drop_hash(rowkey, jp, ds0, ds1);
+                        dp[2 * jp] *= ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
+                        if (2 * jp + 1 < WT) dp[2 * jp + 1] *= ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
+                    }
+                }
                 float delta = 0.f;
 #pragma unroll
                 for (int j = 0; j < WT; j++) { s[j] *= inv; delta = fmaf(s[j], dp[j], delta); }
+#pragma unroll
+                for (int j = 0; j < WT; j += 2)   // P tile for dV: without dropout the probabilities themselves
+                    pk[j >> 1] = pk2(s[j], (j + 1 < WT) ? s[j + 1] : 0.f);
+                if (ad.thr) {   // with dropout: P~ = m * P (the kept entries scaled by 1/keep)
+                    const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
+#pragma unroll
+                    for (int jp = 0; jp < 25; jp++) {
+                        const uint32_t hs = attn_drop_hash(rowkey, jp, ds0, ds1);
+                        const float m0 = ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
+                        const float m1 = ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
+                        pk[jp] = pk2(s[2 * jp] * m0, (2 * jp + 1 < WT) ? s[2 * jp + 1] * m1 : 0.f);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < WT; j++) {
                     dp[j] = s[j] * (dp[j] - delta);   // dS
                     acc[j] += dp[j];
                 }
 #pragma unroll
-                for (int j = 0; j < WT; j += 2) {
-                    pk[j >> 1] = pk2(s[j], (j + 1 < WT) ? s[j + 1] : 0.f);
+                for (int j = 0; j < WT; j += 2)
                     dk_[j >> 1] = pk2(dp[j], (j + 1 < WT) ? dp[j + 1] : 0.f);
-                }
             }
         }
         AT_TRACE(3);
@@ -547,7 +578,7 @@ int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
 
 // returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
 int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
-                   int nH, const WinGeo& g, cudaStream_t st) {
+                   int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15)) return 1;
@@ -570,7 +601,7 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         cudaMalloc(&trace_buf, trace_n * sizeof(long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
     }
-    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmOut, bias, dbias_partial, n_windows, nH, g,
+    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
                                                     trace_on ? trace_buf : nullptr);
     if (trace_on) {   // debug only: synchronous dump of the per-unit phase timeline of two CTAs
         long long* host = (long long*)malloc(trace_n * sizeof(long long));

@@ -143,7 +143,7 @@ class SwinBlockFn(Function):
 
     @staticmethod
     def forward(ctx, x, n1w, n1b, qkvw, qkvb, projw, projb, table, n2w, n2b, f1w, f1b, f2w, f2b, sd1, sd2,
-                B, H, W, nH, shift):
+                B, H, W, nH, shift, attn_p=0.0, drop_seed=None):
         ops._need_cuda(x, "x")
         x = _c(x)
         dev, dt = x.device, x.dtype
@@ -159,7 +159,7 @@ class SwinBlockFn(Function):
         qkv = torch.empty(Tw, 3 * Cd, dtype=dt, device=dev)
         gemm(operand(xw), w_fwd(qkvw, dt), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
         bias = ops.relbias_expand(table, nH)
-        o = ops.winattn_fwd(qkv, bias, B * nW, nH, geo)
+        o = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed)
         # proj + window reverse + un-roll + crop + stochastic depth + residual in the GEMM epilogue
         x1 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(o), w_fwd(projw, dt),
@@ -173,6 +173,7 @@ class SwinBlockFn(Function):
         ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
                               xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a)
         ctx.cfg = (B, H, W, nH, geo, nW)
+        ctx.drop = (attn_p, drop_seed)
         return x2.view(B, H, W, Cd)
 
     @staticmethod
@@ -217,7 +218,7 @@ class SwinBlockFn(Function):
         wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))
         do = torch.empty(Tw, Cd, dtype=dt, device=dev)
         gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
-        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo)
+        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo, *ctx.drop)
         dbqkv = torch.empty(3 * Cd, **f32)
         dWqkv = torch.empty(3 * Cd, Cd, **f32)
         wg.run(lambda: gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv),
@@ -227,7 +228,7 @@ class SwinBlockFn(Function):
         dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
         wg.__exit__()
         return (dx.view(B, H, W, Cd), dn1w, dn1b, dWqkv, dbqkv, dWp, dbp, dtable, dn2w, dn2b, dW1, db1, dW2, db2,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -64,19 +64,24 @@ class SwinTransformerBlock(nn.Module):
         hidden = int(dim * mlp_ratio)
         self.mlp = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(dropout), nn.Linear(hidden, dim),
                                  nn.Dropout(dropout))
-        if (dropout > 0 or attention_dropout > 0):
-            warnings.warn("dropout / attention dropout are not fused yet and run with p=0 "
-                          "(stochastic depth is supported); see DESIGN.md", stacklevel=3)
+        self.attn_p = float(attention_dropout)
+        if dropout > 0:
+            warnings.warn("MLP / projection dropout (DROP_RATE, 0.0 in config.yaml) is not fused yet and runs with p=0 "
+                          "(attention dropout and stochastic depth are supported); see DESIGN.md", stacklevel=3)
 
     def forward(self, x):  # x [B, H, W, C]
         B, H, W, _ = x.shape
         sd1 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
         sd2 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
         a, m = self.attn, self.mlp
+        # attention dropout (TV:models/swin_transformer.py:205): two fresh 32-bit words per call from PyTorch's generator
+        # (a device tensor, so CUDA-graph replays draw new masks); the kernels hash (seed, window, head, query, key)
+        drop_seed = (torch.randint(-2 ** 31, 2 ** 31 - 1, (2,), dtype=torch.int32, device=x.device)
+                     if (self.training and self.attn_p > 0.0) else None)
         return Fn.SwinBlockFn.apply(x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight,
                                     a.proj.bias, a.relative_position_bias_table, self.norm2.weight, self.norm2.bias,
                                     m[0].weight, m[0].bias, m[3].weight, m[3].bias, sd1, sd2, B, H, W,
-                                    self.num_heads, self.shift)
+                                    self.num_heads, self.shift, self.attn_p if drop_seed is not None else 0.0, drop_seed)
 
 
 class PatchMerging(nn.Module):

@@ -198,18 +198,20 @@ def relbias_expand(table: torch.Tensor, nH: int) -> torch.Tensor:
     return bias
 
 
-def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, geo) -> torch.Tensor:
+def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, geo, p_drop: float = 0.0,
+                seed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`seed`: int32[2] device tensor (two 32-bit words of the dropout counter hash); the backward needs the same."""
     o = torch.empty(n_windows * 49, nH * 32, dtype=qkv.dtype, device=qkv.device)
     g = L.geo6(geo)
     e0 = _p0()
     L.check(L.lib().msu_winattn_fwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), n_windows, nH,
-                                    C.cast(g, C.c_void_p), L.stream_ptr()), "msu_winattn_fwd")
+                                    C.cast(g, C.c_void_p), float(p_drop), L.ptr(seed), L.stream_ptr()), "msu_winattn_fwd")
     _p1(e0, (n_windows, nH, 0, "winattn_fwd"), (qkv.numel() + o.numel()) * qkv.element_size(),
         2 * 2 * n_windows * nH * 49 * 49 * 32)
     return o
 
 
-def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
+def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 0.0, seed=None):
     """Returns (dqkv, dtable[169, nH])."""
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
@@ -218,8 +220,8 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo):
     g = L.geo6(geo)
     e0 = _p0()
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
-                                    dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p),
-                                    L.stream_ptr()), "msu_winattn_bwd")
+                                    dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p), float(p_drop),
+                                    L.ptr(seed), L.stream_ptr()), "msu_winattn_bwd")
     dtable = torch.empty(169, nH, dtype=torch.float32, device=dev)
     _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
                               "msu_relbias_reduce"), part)

@@ -281,3 +281,30 @@ def test_drop_path_and_dead_branches_and_eval(pkg):
     assert relmax(c, ref) > 1e-3                                   # train: rows are dropped / rescaled
     c.float().sum().backward()
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+@pytest.mark.gpu
+def test_model_attention_dropout_train_vs_eval():
+    """attn_drop_rate > 0 (config.yaml: 0.05): training draws a fresh mask per call (outputs differ, gradients finite),
+    eval is deterministic and equals the dropout-free model."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    kw = dict(img_size=96, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], drop_path_rate=0.0)
+    m = MSUNetSys(attn_drop_rate=0.3, **kw).to(dev)
+    m0 = MSUNetSys(attn_drop_rate=0.0, **kw).to(dev)
+    m0.load_state_dict(m.state_dict())
+    x = torch.rand(2, 3, 96, 96, device=dev)
+    y = (torch.rand(2, 96, 96, device=dev) > 0.8).float()
+    m.train()
+    a = m(x).float()
+    b = m(x).float()
+    assert torch.isfinite(a).all() and (a - b).abs().max() > 1e-3
+    loss = DynamicLoss()(m(x), y)
+    loss.backward()
+    g = m.layers[1].blocks[0].attn.qkv.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    m.eval(); m0.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x)) and torch.equal(m(x), m0(x))

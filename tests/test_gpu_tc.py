@@ -288,6 +288,59 @@ def test_window_attention_fwd_tcgen05(ops, geom):
     assert float((o_tc.double() - ref).norm() / ref.norm()) < 6e-3
 
 
+@pytest.mark.parametrize("geom", [(2, 14, 14, 3, 1, 0.05), (3, 16, 16, 3, 2, 0.2), (2, 35, 35, 3, 12, 0.05), (1, 10, 12, 0, 6, 0.5)])
+def test_window_attention_dropout(ops, geom):
+    """Attention dropout (TV:models/swin_transformer.py:205) fused into both attention backends: forward and backward vs an
+    fp64 autograd reference that applies the identical counter-hash mask (oracle.attn_drop_keep), plus the drop rate."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    from semantic_segmentation_of_stylegan2_artifacts_b200.functional import window_geo
+    from oracle import msunet_oracle as O
+    B, H, W, shift, nH, p = geom
+    C = nH * 32
+    geo = window_geo(H, W, shift)
+    nW = (geo[2] // 7) * (geo[3] // 7)
+    nwin = B * nW
+    torch.manual_seed(H * 19 + nH)
+    qkv = (torch.randn(nwin * 49, 3 * C) * 1.2).bfloat16().to(DEV)
+    do = torch.randn(nwin * 49, C).bfloat16().to(DEV)
+    table = (torch.randn(169, nH) * 0.5).to(DEV)
+    bias = ops.relbias_expand(table, nH)
+    seed = torch.tensor([123456789, -987654321], dtype=torch.int32, device=DEV)
+    keep = O.attn_drop_keep(nwin, nH, p, 123456789, -987654321)
+    assert abs(1.0 - keep.double().mean().item() - p) < 0.02
+    lib = _lib.lib()
+    res = {}
+    for name, be in (("tc", 0), ("simt", 1)):
+        lib.msu_set_attn_backend(be)
+        o = ops.winattn_fwd(qkv, bias, nwin, nH, geo, p, seed)
+        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, nwin, nH, geo, p, seed)
+        res[name] = (o.float().cpu(), dqkv.float().cpu(), dtable.cpu())
+    lib.msu_set_attn_backend(0)
+    o_nodrop = ops.winattn_fwd(qkv, bias, nwin, nH, geo).float().cpu()
+    _, _, sh, sw, _, region = O.window_geometry(H, W, shift)
+    x = qkv.double().cpu().requires_grad_(True)
+    tb = table.double().cpu().requires_grad_(True)
+    xx = x.view(B, nW, 49, 3, nH, 32).permute(3, 0, 1, 4, 2, 5)
+    q, k, v = xx[0] * 32 ** -0.5, xx[1], xx[2]
+    bexp = tb[O.relative_position_index()].view(49, 49, nH).permute(2, 0, 1)
+    att = q @ k.transpose(-1, -2) + bexp[None, None]
+    if sh + sw > 0:
+        reg = region.view(nW, 49)
+        att = att + torch.where(reg[:, :, None] != reg[:, None, :], -100.0, 0.0).double()[None, :, None]
+    pm = att.softmax(-1) * keep.view(B, nW, nH, 49, 49).double() / (1.0 - p)
+    out = (pm @ v).permute(0, 1, 3, 2, 4).reshape(nwin * 49, C)
+    out.backward(do.double().cpu())
+
+    def rl2(a, b):
+        return float((a.double() - b).norm() / b.norm())
+
+    ref = out.detach()
+    assert rl2(o_nodrop, ref) > 0.05                                  # the mask really changes the output
+    assert rl2(res["simt"][0], ref) < 6e-3 and rl2(res["tc"][0], ref) < 8e-3
+    assert rl2(res["simt"][1], x.grad) < 6e-3 and rl2(res["simt"][2], tb.grad) < 2e-3
+    assert rl2(res["tc"][1], x.grad) < 1.2e-2 and rl2(res["tc"][2], tb.grad) < 1.2e-2
+
+
 @pytest.mark.parametrize("geom", [(2, 14, 14, 3, 1), (3, 16, 16, 3, 2), (1, 16, 16, 0, 3), (5, 7, 7, 3, 1), (2, 35, 35, 3, 12),
                                   (1, 10, 12, 3, 6), (16, 21, 21, 3, 24)])
 def test_window_attention_bwd_tcgen05(ops, geom):
