@@ -63,6 +63,127 @@ __global__ void __launch_bounds__(LM_THREADS) loss_partial_kernel(const T* __res
     }
 }
 
+// Vector path (N % 8 == 0, 16 B aligned rows): 8 pixels per thread per step (one 16 B load of bf16/fp16 logits or two of
+// fp32, two 16 B loads of the target), one exp and one log per pixel (sigmoid and softplus share exp(-|x|)), and only the
+// sums that cannot be derived: FP = sum p - TP and FN = sum t - TP are formed once per block.
+template <typename T> struct Ld8;
+template <> struct Ld8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float* o) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* o) {
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+};
+template <> struct Ld8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+        const uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* o) {
+        uint4 r;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = r;
+    }
+};
+template <> struct Ld8<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float* o) {
+        const uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void st(__half* p, const float* o) {
+        uint4 r;
+        __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = r;
+    }
+};
+// p = sigmoid(x) and softplus(x) = max(x, 0) + log(1 + exp(-|x|)) from one exponential
+__device__ __forceinline__ void sigmoid_softplus(float x, float& p, float& sp) {
+    const float e = __expf(-fabsf(x));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    p = x >= 0.f ? r : e * r;
+    sp = fmaxf(x, 0.f) + __logf(1.0f + e);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LM_THREADS) loss_partial_vec_kernel(const T* __restrict__ logits, const float* __restrict__ target,
+                                                                     int64_t N, float* __restrict__ ws) {
+    __shared__ float sm[(LM_THREADS / 32) * LS];
+    const int b = blockIdx.y;
+    const T* x = logits + (int64_t)b * N;
+    const float* t = target + (int64_t)b * N;
+    float a = 0.f, sp_ = 0.f, tmax = -INFINITY, xt = 0.f, tp = 0.f, stt = 0.f, xtb = 0.f, tpb = 0.f, stb = 0.f;
+    for (int64_t i = ((int64_t)blockIdx.x * LM_THREADS + threadIdx.x) * 8; i < N; i += (int64_t)gridDim.x * LM_THREADS * 8) {
+        float xv[8], tv[8];
+        Ld8<T>::ld(x + i, xv);
+        Ld8<float>::ld(t + i, tv);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            float p, sp;
+            sigmoid_softplus(xv[e], p, sp);
+            const float tb = tv[e] > 127.5f ? 1.f : 0.f;
+            a += sp; sp_ += p; tmax = fmaxf(tmax, tv[e]);
+            xt = fmaf(xv[e], tv[e], xt); tp = fmaf(p, tv[e], tp); stt += tv[e];
+            xtb = fmaf(xv[e], tb, xtb); tpb = fmaf(p, tb, tpb); stb += tb;
+        }
+    }
+    float v[LS];
+#pragma unroll
+    for (int k = 0; k < LS; k++) v[k] = 0.f;
+    v[0] = a; v[1] = sp_; v[2] = tmax;
+    v[4] = xt; v[5] = tp; v[6] = sp_ - tp; v[7] = stt - tp; v[8] = stt;
+    v[10] = xtb; v[11] = tpb; v[12] = sp_ - tpb; v[13] = stb - tpb; v[14] = stb;
+    block_reduce<LS>(v, sm, true);
+    if (threadIdx.x == 0) {
+        float* o = ws + ((int64_t)b * gridDim.x + blockIdx.x) * LS;
+#pragma unroll
+        for (int k = 0; k < LS; k++) o[k] = v[k];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LM_THREADS) loss_bwd_vec_kernel(const T* __restrict__ logits, const float* __restrict__ target,
+                                                                 int64_t N, float alpha, float beta, const float* __restrict__ stats,
+                                                                 const int32_t* __restrict__ flag, const float* __restrict__ gscale,
+                                                                 T* __restrict__ dlogits) {
+    const int b = blockIdx.y;
+    const float* s = stats + (int64_t)b * 8;
+    const float g = gscale ? *gscale : 1.f;
+    const float wb = s[0] * g, mt = s[1] * g, Nn = s[2], D = s[3];
+    const float invD2 = 1.0f / (D * D);
+    const int k = *flag;
+    // dtv = -p' (t D - Nn (t + alpha (1 - t) - beta t)) / D^2 = p' (c0 + c1 t):  c0 = Nn alpha / D^2, c1 = (Nn (1 - alpha - beta) - D) / D^2
+    const float c0 = mt * Nn * alpha * invD2, c1 = mt * (Nn * (1.f - alpha - beta) - D) * invD2;
+    const T* x = logits + (int64_t)b * N;
+    const float* t = target + (int64_t)b * N;
+    T* dx = dlogits + (int64_t)b * N;
+    for (int64_t i = ((int64_t)blockIdx.x * LM_THREADS + threadIdx.x) * 8; i < N; i += (int64_t)gridDim.x * LM_THREADS * 8) {
+        float xv[8], tv[8], o[8];
+        Ld8<T>::ld(x + i, xv);
+        Ld8<float>::ld(t + i, tv);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float tt = k ? (tv[e] > 127.5f ? 1.f : 0.f) : tv[e];
+            const float ex = __expf(-fabsf(xv[e]));
+            const float r = __fdividef(1.0f, 1.0f + ex);
+            const float p = xv[e] >= 0.f ? r : ex * r;
+            const float dp = p * (1.f - p);
+            o[e] = fmaf(wb, p - tt, dp * fmaf(c1, tt, c0));
+        }
+        Ld8<T>::st(dx + i, o);
+    }
+}
+
 // one block: combines partials (fixed order, double), decides the {0,255} interpretation, writes per-sample
 // backward coefficients stats[b] = {w_bce/(N*B), m_b/B, Nn, D, loss_b} and the batch-mean loss.
 __global__ void loss_final_kernel(const float* __restrict__ ws, int B, int nblk, int64_t N, float alpha, float beta,
@@ -79,13 +200,20 @@ __global__ void loss_final_kernel(const float* __restrict__ ws, int B, int nblk,
     }
     const int k = smax[0] > 1.0f ? 1 : 0;  // loss/DynamicLoss.py:87-88
     if (threadIdx.x == 0) *flag = k;
+    // one warp per sample: lanes add the block records (double, fixed lane order), then a shuffle tree
     double acc = 0.0;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        double a = 0, xt = 0, tp = 0, fp = 0, fn = 0, st = 0;
-        for (int j = 0; j < nblk; j++) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarp) {
+        double r6[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = lane; j < nblk; j += 32) {
             const float* r = ws + ((int64_t)b * nblk + j) * LS;
-            a += r[0]; xt += r[4 + 6 * k]; tp += r[5 + 6 * k]; fp += r[6 + 6 * k]; fn += r[7 + 6 * k]; st += r[8 + 6 * k];
+            r6[0] += r[0]; r6[1] += r[4 + 6 * k]; r6[2] += r[5 + 6 * k]; r6[3] += r[6 + 6 * k]; r6[4] += r[7 + 6 * k]; r6[5] += r[8 + 6 * k];
         }
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            for (int o = 16; o > 0; o >>= 1) r6[q] += __shfl_xor_sync(0xffffffffu, r6[q], o);
+        if (lane != 0) continue;
+        const double a = r6[0], xt = r6[1], tp = r6[2], fp = r6[3], fn = r6[4], st = r6[5];
         const float bce = (float)((a - xt) / (double)N);
         const float Nn = (float)tp + TV_SMOOTH;
         const float D = (float)tp + alpha * (float)fp + beta * (float)fn + TV_SMOOTH;
@@ -225,7 +353,11 @@ extern "C" int msu_loss_fwd(int dtype, const void* logits, const float* target, 
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = lm_blocks(N);
     dim3 grid(nblk, B);
-    if (dtype == MSU_F32) loss_partial_kernel<float><<<grid, LM_THREADS, 0, st>>>((const float*)logits, target, N, ws);
+    const bool vec = (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+    if (vec && dtype == MSU_F32) loss_partial_vec_kernel<float><<<grid, LM_THREADS, 0, st>>>((const float*)logits, target, N, ws);
+    else if (vec && dtype == MSU_BF16) loss_partial_vec_kernel<__nv_bfloat16><<<grid, LM_THREADS, 0, st>>>((const __nv_bfloat16*)logits, target, N, ws);
+    else if (vec && dtype == MSU_F16) loss_partial_vec_kernel<__half><<<grid, LM_THREADS, 0, st>>>((const __half*)logits, target, N, ws);
+    else if (dtype == MSU_F32) loss_partial_kernel<float><<<grid, LM_THREADS, 0, st>>>((const float*)logits, target, N, ws);
     else if (dtype == MSU_BF16) loss_partial_kernel<__nv_bfloat16><<<grid, LM_THREADS, 0, st>>>((const __nv_bfloat16*)logits, target, N, ws);
     else if (dtype == MSU_F16) loss_partial_kernel<__half><<<grid, LM_THREADS, 0, st>>>((const __half*)logits, target, N, ws);
     else MSU_REQUIRE(false, "msu_loss_fwd: unsupported dtype %d", dtype);
@@ -241,6 +373,16 @@ extern "C" int msu_loss_bwd(int dtype, const void* logits, const float* target, 
     (void)mix;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)imax(1, imin(4096, (N + LM_THREADS * 4 - 1) / (LM_THREADS * 4))), B);
+    const bool vec = (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;
+    if (vec) {
+        dim3 gv((unsigned)imax(1, imin(2048, (N + LM_THREADS * 8 - 1) / (LM_THREADS * 8))), B);
+        if (dtype == MSU_F32) loss_bwd_vec_kernel<float><<<gv, LM_THREADS, 0, st>>>((const float*)logits, target, N, alpha, beta, stats, flag, gscale, (float*)dlogits);
+        else if (dtype == MSU_BF16) loss_bwd_vec_kernel<__nv_bfloat16><<<gv, LM_THREADS, 0, st>>>((const __nv_bfloat16*)logits, target, N, alpha, beta, stats, flag, gscale, (__nv_bfloat16*)dlogits);
+        else if (dtype == MSU_F16) loss_bwd_vec_kernel<__half><<<gv, LM_THREADS, 0, st>>>((const __half*)logits, target, N, alpha, beta, stats, flag, gscale, (__half*)dlogits);
+        else MSU_REQUIRE(false, "msu_loss_bwd: unsupported dtype %d", dtype);
+        count_launch();
+        return check_launch("msu_loss_bwd");
+    }
     if (dtype == MSU_F32) loss_bwd_kernel<float><<<grid, LM_THREADS, 0, st>>>((const float*)logits, target, N, alpha, beta, stats, flag, gscale, (float*)dlogits);
     else if (dtype == MSU_BF16) loss_bwd_kernel<__nv_bfloat16><<<grid, LM_THREADS, 0, st>>>((const __nv_bfloat16*)logits, target, N, alpha, beta, stats, flag, gscale, (__nv_bfloat16*)dlogits);
     else if (dtype == MSU_F16) loss_bwd_kernel<__half><<<grid, LM_THREADS, 0, st>>>((const __half*)logits, target, N, alpha, beta, stats, flag, gscale, (__half*)dlogits);
