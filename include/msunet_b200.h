@@ -173,6 +173,24 @@ int msu_gather_rows(const MsuOperand* src, void* dst, int64_t M, int64_t N, void
 int msu_cast(int src_dtype, int dst_dtype, const void* src, void* dst, int64_t n, void* stream);
 int msu_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);
 
+/* Fused multi-tensor AdamW (torch.optim.AdamW semantics, amsgrad off; trainer.py:143-152, 315), fp32 parameters / moments.
+ * `table` is a DEVICE array of per-tensor records; block b of the launch updates elements
+ * [blk_chunk[b] * msu_adamw_chunk(), ...) of tensor blk_tensor[b].  Per-tensor scalars are pre-folded by the host:
+ * decay = 1 - lr * weight_decay, step_size = lr / (1 - beta1^t), inv_bias2_sqrt = 1 / sqrt(1 - beta2^t).
+ * inv_scale (optional device scalar) multiplies every gradient (GradScaler unscale); found_inf (optional device scalar):
+ * a non-zero value skips the whole step. */
+typedef struct {
+    void* p;
+    const void* g;
+    void* m;
+    void* v;
+    int64_t n;
+    float decay, step_size, inv_bias2_sqrt, beta1, beta2, eps;
+} MsuAdamTensor;
+int msu_adamw_chunk(void);
+int msu_adamw_step(const MsuAdamTensor* table, const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t n_blocks,
+                   const float* inv_scale, const float* found_inf, void* stream);
+
 int msu_version(void);
 /* sizeof(MsuOperand) (which=0) / sizeof(MsuEpilogue) (which=1): lets a binding verify its struct layout. */
 int msu_struct_size(int which);
