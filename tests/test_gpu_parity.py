@@ -308,3 +308,18 @@ def test_model_attention_dropout_train_vs_eval():
     m.eval(); m0.eval()
     with torch.no_grad():
         assert torch.equal(m(x), m(x)) and torch.equal(m(x), m0(x))
+
+
+@pytest.mark.gpu
+def test_cuda_prefetcher_yields_every_batch_in_order():
+    from semantic_segmentation_of_stylegan2_artifacts_b200.data import CudaPrefetcher
+    dev = torch.device("cuda:0")
+    batches = [{"image": torch.full((2, 3, 8, 8), float(i)), "label": torch.full((2, 8, 8), float(-i)), "case_name": [f"c{i}"]}
+               for i in range(5)]
+    seen = []
+    for b in CudaPrefetcher(batches, dev):
+        assert b["image"].is_cuda and b["label"].is_cuda and b["case_name"][0].startswith("c")
+        seen.append((float(b["image"].mean()), float(b["label"].mean())))
+    assert seen == [(float(i), float(-i)) for i in range(5)]
+    with pytest.raises(RuntimeError):
+        CudaPrefetcher(batches, "cpu")
