@@ -26,11 +26,12 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t saddr) {
     d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
     return d;
 }
-// MN-major, 64B-swizzled descriptor for a [k rows x 32] tile: one 64 B chunk along MN, 8-row k groups 512 B apart
-__device__ __forceinline__ uint64_t make_desc_mnmajor_sw64(uint32_t saddr) {
+// MN-major, 64B-swizzled descriptor for a [k rows x 32] tile: one 64 B chunk along MN, 8-row k groups 512 B apart;
+// `lbo_bytes` = distance to the next 32-column chunk (N = 64: the same rows of the pair's second window, 4 KB further)
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw64(uint32_t saddr, uint32_t lbo_bytes = 16) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                 // LBO unused: a single MN chunk
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)4 << 61;
@@ -109,7 +110,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     const int half = tid >> 6;             // which window of the pair this row belongs to
     const int i = tid & 63;                // token index inside the window (valid if < 49)
     const uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
-    const uint32_t idesc2 = make_idesc_bf16(128, 32, 0, 1);
+    const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
     uint32_t ph_mma = 0;
     const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
 
@@ -134,8 +135,6 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         uint8_t* sK = sQ + 8192;
         uint8_t* sV = sQ + 16384;
         if (tid == 0) {
-            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
-            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
             tma_store_wait_read0();      // the previous unit's output boxes (staged in the P tile) have left shared memory
             tc_fence_after();
@@ -143,6 +142,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
             tc_mma_bf16(tmem, qd, kd, idesc1, 0);
             tc_mma_bf16(tmem, qd + 2, kd + 2, idesc1, 1);   // +32 B: second K=16 slice of the 64 B rows
             tc_commit(bar_mma);
+            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
+            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
         }
         // ---- softmax on this thread's row
         const bool row_ok = (i < WT) && (win < n_windows);
@@ -207,13 +208,12 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
             tc_fence_after();
             const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
-            for (int w = 0; w < 2; w++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {   // 64 own keys = 4 K-steps (+32 B inside the 128 B rows), V_w advances 16 rows = 1 KB
-                    const uint64_t ad = make_desc_kmajor_sw128(pa + k * 32);
-                    const uint64_t bd = make_desc_mnmajor_sw64(va + w * 4096 + k * 1024);
-                    tc_mma_bf16(tmem + w * 32, ad, bd, idesc2, k != 0);
-                }
+            for (int k = 0; k < 4; k++) {   // 64 own keys = 4 K-steps (+32 B inside the 128 B rows), V advances 16 rows = 1 KB;
+                // N = 64: columns 0..31 multiply V_a, 32..63 V_b (second 32-column chunk 4 KB further): rows of window w
+                // hold O_w in columns [32 w, 32 w + 32), the other half of each row is unused
+                const uint64_t ad = make_desc_kmajor_sw128(pa + k * 32);
+                const uint64_t bd = make_desc_mnmajor_sw64(va + k * 1024, 4096);
+                tc_mma_bf16(tmem, ad, bd, idesc2, k != 0);
             }
             tc_commit(bar_mma);
         }
@@ -352,8 +352,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const int nwin_img = g.nwin();
     const int half = tid >> 6, i = tid & 63;
     const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
-    const uint32_t id_kv = make_idesc_bf16(128, 32, 1, 1);     // dV, dK: A MN-major, B MN-major
-    const uint32_t id_q = make_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
+    const uint32_t id_kv = make_idesc_bf16(128, 64, 1, 1);     // dV, dK: A MN-major, B MN-major (both windows' columns)
+    const uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
     uint32_t ph_mma = 0;
     const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
     float acc[WT];
@@ -385,8 +385,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         uint8_t* sD = sV + AB_TILE;                 // dO
         AT_TRACE(0);
         if (tid == 0) {
-            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
-            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
             tma_store_wait_read0();      // the previous unit's output boxes (staged in the P / dS tiles) have left shared memory
             tc_fence_after();
@@ -398,6 +396,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tc_mma_bf16(tmem + 128, dd, vd, id_s, 0);
             tc_mma_bf16(tmem + 128, dd + 2, vd + 2, id_s, 1);
             tc_commit(bar_mma);
+            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
+            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
         }
         const bool row_ok = (i < WT) && (win < n_windows);
         const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
@@ -489,21 +489,19 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             const uint32_t xp = smem_u32(sXP), xs = smem_u32(sXS);
             const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sD);
 #pragma unroll
-            for (int w = 0; w < 2; w++) {
+            for (int k = 0; k < 4; k++) {   // contraction over 16 rows of both windows per step (2 KB of X, 1 KB of B per window)
+                // A: M chunk 0 = keys of window a (rows [16k, 16k+16) of block a), chunk 1 = 8 KB further = block b.
+                // B: N = 64, columns 0..31 from window a's dO / Q rows, 32..63 from window b's (4 KB further): lanes
+                // [64 w, 64 w + 64) hold window w's result in columns [32 w, 32 w + 32), the rest is unused
+                const uint64_t ap = make_desc_mnmajor_sw128(xp + k * 2048, 8192);
+                const uint64_t as = make_desc_mnmajor_sw128(xs + k * 2048, 8192);
+                tc_mma_bf16(tmem, ap, make_desc_mnmajor_sw64(da + k * 1024, 4096), id_kv, k != 0);        // dV
+                tc_mma_bf16(tmem + 64, as, make_desc_mnmajor_sw64(qa + k * 1024, 4096), id_kv, k != 0);   // dK
+            }
 #pragma unroll
-                for (int k = 0; k < 4; k++) {   // contraction over the 64 rows of window w, 16 rows (2 KB of X, 1 KB of B) per step
-                    // M chunk 0 = keys of window a (rows [16k, 16k+16) of block a), chunk 1 = 8 KB further = block b:
-                    // with window w's B rows only lanes [64 w, 64 w + 64) are meaningful
-                    const uint64_t ap = make_desc_mnmajor_sw128(xp + k * 2048, 8192);
-                    const uint64_t as = make_desc_mnmajor_sw128(xs + k * 2048, 8192);
-                    tc_mma_bf16(tmem + w * 32, ap, make_desc_mnmajor_sw64(da + w * 4096 + k * 1024), id_kv, k != 0);       // dV_w
-                    tc_mma_bf16(tmem + 64 + w * 32, as, make_desc_mnmajor_sw64(qa + w * 4096 + k * 1024), id_kv, k != 0);  // dK_w
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {   // contraction over the 64 keys of window w: +32 B per step inside the 128 B rows
-                    const uint64_t as = make_desc_kmajor_sw128(xs + k * 32);
-                    tc_mma_bf16(tmem + 128 + w * 32, as, make_desc_mnmajor_sw64(ka + w * 4096 + k * 1024), id_q, k != 0);  // dQ_w
-                }
+            for (int k = 0; k < 4; k++) {   // contraction over the 64 own keys: +32 B per step inside the 128 B rows
+                const uint64_t as = make_desc_kmajor_sw128(xs + k * 32);
+                tc_mma_bf16(tmem + 128, as, make_desc_mnmajor_sw64(ka + k * 1024, 4096), id_q, k != 0);   // dQ
             }
             tc_commit(bar_mma);
         }
