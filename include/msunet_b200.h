@@ -109,6 +109,12 @@ int msu_ln_bwd(int dtype, const void* dY, const void* X, const float* gamma, con
                const float* mean, const float* rstd, const void* dRes, void* dX, int64_t rows, int32_t C,
                int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,
                void* stream);
+/* As msu_ln_bwd (no row maps) and additionally dXw[pix_to_win(row)] = rowscale[row / rows_per_sample] * dX[row]: the gradient rows
+ * of the attention projection in window order (backward of TV:models/swin_transformer.py:219-227 + stochastic depth) come out of
+ * the LayerNorm backward that produces them.  Padding rows of dXw are never written: the caller zeroes them once. */
+int msu_ln_bwd_dual(int dtype, const void* dY, const void* X, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, const void* dRes, void* dX, void* dXw, int64_t rows, int32_t C, const int32_t* wgeo,
+                    const float* rowscale, int32_t rows_per_sample, float* partial, void* stream);
 int msu_ln_param_reduce(const float* partial, int32_t partial_rows, int32_t C, float* dgamma, float* dbeta,
                         float* ddotw, int accumulate, void* stream);
 

@@ -81,6 +81,7 @@ __device__ __forceinline__ int64_t merge_off(const MergeGeo& mg, int64_t lr, int
 // version issue-bound at ~23 instructions per element: runtime map branches, gamma / beta reloaded per row, IEEE
 // divisions); gamma / beta / the dot weight live in registers for narrow rows, statistics use rsqrtf and a host-side 1/C.
 constexpr int LNM_PLAIN = 0, LNM_WINDOW = 1, LNM_MERGE = 2, LNM_DOT = 3, LNM_UNSHUFFLE = 4;
+constexpr int LNM_DUAL = 5;   // backward only: dX in pixel order AND a per-sample-scaled copy in window order (wg)
 
 __device__ __forceinline__ float group_sum_u(float v, int lpr) {   // branch-free: always five shuffles, selects for lpr < 32
     float t;
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                                                               const T* __restrict__ dRes, T* __restrict__ dX, int64_t rows,
                                                               int C, float invC, int lpr, WinGeo wg, MergeGeo mg,
                                                               const float* __restrict__ dotw, float* __restrict__ partial,
-                                                              MsuOperand ug) {
+                                                              MsuOperand ug, T* __restrict__ dXw, const float* __restrict__ wscale,
+                                                              int rows_per_sample) {
     constexpr bool DOT = MODE == LNM_DOT;
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
@@ -231,6 +233,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
         const float mu = live ? mean[lr] : 0.f, rs = live ? rstd[lr] : 0.f;
         const float nmr = -mu * rs;
         const int64_t dyr = (MODE == LNM_WINDOW && live) ? pix_to_win(wg, lr) : lr;
+        // DUAL: the same gradient row, scaled per sample, also goes to its window-order row (the padding rows of that
+        // buffer are zeroed once by the caller and never written)
+        const int64_t wrow = (MODE == LNM_DUAL && live) ? pix_to_win(wg, lr) : 0;
+        const float wsc = (MODE == LNM_DUAL && live && wscale != nullptr) ? wscale[lr / rows_per_sample] : 1.0f;
         const float dl = (DOT && live) ? to_f<T>(dY[lr]) : 0.f;
         const int64_t rowoff = lr * C;
         uint4 xr[NV], yr[DOT ? 1 : NV], rr[RES ? NV : 1];
@@ -305,6 +311,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                     wo = rc.row * (int64_t)(ug.geo[2] * ug.geo[2] * ug.geo[3]) + rc.col;
                 }
                 VecW<T>::st(dX + wo, dx);
+                if (MODE == LNM_DUAL) {
+#pragma unroll
+                    for (int e = 0; e < VW; e++) dx[e] *= wsc;
+                    VecW<T>::st(dXw + wrow * C + c, dx);
+                }
             }
         }
     }
@@ -411,20 +422,25 @@ static int launch_fwd(const void* X, const float* gamma, const float* beta, void
 template <typename T, int NV>
 static int launch_bwd(const void* dY, const void* X, const float* gamma, const float* beta, const float* mean,
                       const float* rstd, const void* dRes, void* dX, int64_t rows, int C, int lpr, int dy_map, int dx_map,
-                      const int32_t* geo, const float* dotw, float* partial, int grid, cudaStream_t st) {
+                      const int32_t* geo, const float* dotw, float* partial, int grid, cudaStream_t st, void* dXw = nullptr,
+                      const float* wscale = nullptr, int rows_per_sample = 1) {
     WinGeo wg{0, 0, 0, 0, 0, 0};
     MergeGeo mg{0, 0};
-    if (dy_map == MSU_MAP_WINDOW) wg = make_wingeo(geo);
+    if (dy_map == MSU_MAP_WINDOW || dXw != nullptr) wg = make_wingeo(geo);
     if (dx_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
     MsuOperand ug{};
     if (dx_map == MSU_MAP_UNSHUFFLE) for (int k = 0; k < 4; k++) ug.geo[k] = geo[k];
     const float invC = 1.0f / (float)C;
 #define LN_BWD_LAUNCH(MODE, RES)                                                                                           \
     ln_bwd_kernel<T, NV, MODE, RES><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,     \
-                                                                   (const T*)dRes, (T*)dX, rows, C, invC, lpr, wg, mg, dotw, partial, ug)
+                                                                   (const T*)dRes, (T*)dX, rows, C, invC, lpr, wg, mg, dotw, partial, ug, \
+                                                                   (T*)dXw, wscale, rows_per_sample)
     const int nmaps = (dy_map != MSU_MAP_NONE) + (dx_map != MSU_MAP_NONE) + (dotw != nullptr);
     if (nmaps > 1) { set_error("msu_ln_bwd: at most one of dy_map / dx_map / dotw"); return -1; }
-    if (dotw != nullptr) {
+    if (dXw != nullptr) {
+        if (nmaps != 0) { set_error("msu_ln_bwd_dual: no other row map allowed"); return -1; }
+        if (dRes) LN_BWD_LAUNCH(LNM_DUAL, true); else LN_BWD_LAUNCH(LNM_DUAL, false);
+    } else if (dotw != nullptr) {
         if (dRes) LN_BWD_LAUNCH(LNM_DOT, true); else LN_BWD_LAUNCH(LNM_DOT, false);
     } else if (dy_map == MSU_MAP_WINDOW) {
         if (dRes) LN_BWD_LAUNCH(LNM_WINDOW, true); else LN_BWD_LAUNCH(LNM_WINDOW, false);
@@ -508,4 +524,21 @@ extern "C" int msu_ln_param_reduce(const float* partial, int32_t P, int32_t C, f
     ln_param_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, P, C, dgamma, dbeta, ddotw, accumulate);
     count_launch();
     return check_launch("msu_ln_param_reduce");
+}
+
+// LayerNorm backward that also writes scale[sample] * dX in window order (rows pix -> (b, window, i) of wgeo): the operand of the
+// attention projection's dgrad / wgrad, without a separate gather pass.  Padding rows of dXw are not written (keep them zero).
+extern "C" int msu_ln_bwd_dual(int dtype, const void* dY, const void* X, const float* gamma, const float* beta,
+                               const float* mean, const float* rstd, const void* dRes, void* dX, void* dXw, int64_t rows,
+                               int32_t C, const int32_t* wgeo, const float* rowscale, int32_t rows_per_sample,
+                               float* partial, void* stream) {
+    MSU_REQUIRE(dY && X && gamma && beta && mean && rstd && dX && dXw && wgeo && partial, "msu_ln_bwd_dual: null pointer");
+    MSU_REQUIRE(C > 0 && C % (dtype == MSU_F32 ? 4 : 8) == 0, "msu_ln_bwd_dual: C=%d must be a positive multiple of the 16-byte vector width", C);
+    MSU_REQUIRE(rowscale == nullptr || rows_per_sample > 0, "msu_ln_bwd_dual: rows_per_sample required with rowscale");
+    const int grid = msu_ln_bwd_partial_rows(dtype, rows, C) / LN_WARPS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_bwd, float, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, 4), 0, 0, wgeo, nullptr, partial, grid, st, dXw, rowscale, rps);
+    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_bwd, __nv_bfloat16, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, 8), 0, 0, wgeo, nullptr, partial, grid, st, dXw, rowscale, rps);
+    MSU_REQUIRE(false, "msu_ln_bwd_dual: unsupported dtype %d", dtype);
 }

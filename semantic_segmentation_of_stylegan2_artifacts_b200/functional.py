@@ -210,9 +210,15 @@ class SwinBlockFn(Function):
         wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))
         dxn = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
-        dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
-        # ---- attention half: gradient rows gathered into window order (zero rows for the padding tokens)
-        dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
+        # ---- attention half: gradient rows in window order (zero rows for the padding tokens).  bf16: the LayerNorm backward
+        # that produces dx1 writes the scaled window-ordered copy itself (persistent buffer, padding rows zeroed once)
+        if dt == BF16:
+            dyw = ops.window_rows_buffer(Tw, Cd, geo, x)
+            dx1, dn2w, dn2b = ops.ln_bwd_dual(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dx2, dyw, geo, sd1, HW)
+            dy1, dy1t = operand(dyw), operand(dyw, orient=1)
+        else:
+            dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
+            dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
         dbp = torch.empty(Cd, **f32)
         dWp = torch.empty(Cd, Cd, **f32)
         wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))

@@ -192,6 +192,42 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     return dx, dg, db, dw
 
 
+_win_bufs: dict = {}
+
+
+def window_rows_buffer(Tw: int, Cdim: int, geo, like: torch.Tensor) -> torch.Tensor:
+    """Persistent [Tw, C] buffer for window-ordered gradient rows of one (geometry, width): its padding rows are zeroed once
+    and never written again (msu_ln_bwd_dual only writes real pixels), so no per-call memset or gather is needed.  Reuse is
+    stream-safe because every SwinBlockFn.backward joins its side stream before the next block's backward starts."""
+    key = (like.device.index, like.dtype, Tw, Cdim, tuple(geo), torch.cuda.current_stream(like.device).cuda_stream)
+    buf = _win_bufs.get(key)
+    if buf is None:
+        buf = torch.zeros(Tw, Cdim, dtype=like.dtype, device=like.device)
+        _win_bufs[key] = buf
+    return buf
+
+
+def ln_bwd_dual(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int, Cdim: int, dres, dxw: torch.Tensor,
+                wgeo, rowscale, rps: int):
+    """LayerNorm backward that also writes rowscale * dx into the window-ordered rows of `dxw`.  Returns (dx, dgamma, dbeta)."""
+    dev = x.device
+    dx = torch.empty_like(x)
+    P = L.lib().msu_ln_bwd_partial_rows(L.dt(x), rows, Cdim)
+    part = torch.empty(P * 3 * Cdim, dtype=torch.float32, device=dev)
+    g = L.geo6(wgeo)
+    e0 = _p0()
+    L.check(L.lib().msu_ln_bwd_dual(L.dt(x), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), dxw.data_ptr(), rows, Cdim,
+                                    C.cast(g, C.c_void_p), L.ptr(rowscale), int(rps), part.data_ptr(), L.stream_ptr()),
+            "msu_ln_bwd_dual")
+    dg = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    db = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    _off_path(lambda: L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), None, 0,
+                                                          L.stream_ptr()), "msu_ln_param_reduce"), part)
+    _p1(e0, (rows, Cdim, 0, "ln_bwd_dual"), (dy.numel() + 4 * rows * Cdim) * x.element_size())
+    return dx, dg, db
+
+
 def relbias_expand(table: torch.Tensor, nH: int) -> torch.Tensor:
     bias = torch.empty(nH, 49, 49, dtype=torch.float32, device=table.device)
     L.check(L.lib().msu_relbias_expand(table.data_ptr(), bias.data_ptr(), nH, L.stream_ptr()), "msu_relbias_expand")
