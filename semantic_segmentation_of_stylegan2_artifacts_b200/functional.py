@@ -461,31 +461,42 @@ class HeadFn(Function):
         f32 = dict(dtype=torch.float32, device=dev)
         wd = dt if dt == BF16 else torch.float32
         dl = _c(dlogits).view(Mp)
+        wg = _WgradFork(dev)
+        wg.__enter__()
         dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
-        # conv2
+        # conv2 (weight gradients on the side stream: they fill the tails of the dgrad convolutions)
         dc2b = torch.empty(E, **f32)
         dw2r = torch.empty(E, 9 * E, **f32)
-        gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
-             epilogue(dw2r, out_f32=True, colsum=dc2b), E, 9 * E, Mp, dev)
-        dc2w = ops.prep_weight(4, dw2r, E, E, (E, E, 3, 3), torch.float32)
+        dc2w = torch.empty(E, E, 3, 3, **f32)
+
+        def wgrad2():
+            gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+                 epilogue(dw2r, out_f32=True, colsum=dc2b), E, 9 * E, Mp, dev)
+            ops.prep_weight_into(4, dw2r, dc2w, E, E)
+        wg.run(wgrad2)
         w2f = shadow(c2w, 3, E, E, (E, 9 * E), wd)
         dz1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
         # conv1
         dc1b = torch.empty(E, **f32)
         dw1r = torch.empty(E, 9 * E, **f32)
-        gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
-             epilogue(dw1r, out_f32=True, colsum=dc1b), E, 9 * E, Mp, dev)
-        dc1w = ops.prep_weight(4, dw1r, E, E, (E, E, 3, 3), torch.float32)
+        dc1w = torch.empty(E, E, 3, 3, **f32)
+
+        def wgrad1():
+            gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+                 epilogue(dw1r, out_f32=True, colsum=dc1b), E, 9 * E, Mp, dev)
+            ops.prep_weight_into(4, dw1r, dc1w, E, E)
+        wg.run(wgrad1)
         w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
         # conv1 dgrad (x gelu'(h0)) written by the GEMM epilogue in the inverse depth-to-space layout [T, 16E]
         dh0 = torch.empty(T, 16 * E, dtype=dt, device=dev)
         gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f),
              epilogue(dh0, ldc=16 * E, H=h0, ldh=E, map=MAP_UNSHUFFLE, geo=sgeo), Mp, E, 9 * E, dev)
         dew = torch.empty(16 * E, E, **f32)
-        gemm(operand(dh0, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev)
+        wg.run(lambda: gemm(operand(dh0, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev))
         dx = torch.empty(T, E, dtype=dt, device=dev)
         gemm(operand(dh0), w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
+        wg.__exit__()
         return (dx.view(xshape), dew, dc1w, dc1b, dc2w, dc2b, dnw, dnb, dow.view(owshape), None, None)
 
 

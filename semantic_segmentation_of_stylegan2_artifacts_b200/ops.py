@@ -273,6 +273,11 @@ def prep_weight(mode: int, src: torch.Tensor, R: int, Cc: int, out_shape, dtype:
     return out
 
 
+def prep_weight_into(mode: int, src: torch.Tensor, out: torch.Tensor, R: int, Cc: int) -> None:
+    L.check(L.lib().msu_prep_weight(mode, L.dt(out), src.data_ptr(), out.data_ptr(), R, Cc, L.stream_ptr()),
+            "msu_prep_weight")
+
+
 def patchify4(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     B, _, S, _ = img.shape
     out = torch.empty(B * (S // 4) ** 2, 64, dtype=dtype, device=img.device)
