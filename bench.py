@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="T96", choices=["T96", "B128"], help="B128 = config.yaml default (embed 128, depths 2-2-18-2)")
     ap.add_argument("--drop-path", type=float, default=0.1)
     ap.add_argument("--attn-drop", type=float, default=0.0, help="attention dropout (config.yaml of the reference: 0.05)")
     args = ap.parse_args()
@@ -163,7 +164,9 @@ def main():
     B, S = args.batch, args.img
 
     torch.manual_seed(1234)
-    model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, attn_drop_rate=args.attn_drop, **T96).set_precision(args.precision).to(dev).train()
+    arch = T96 if args.model == "T96" else dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32])
+    gflop_img = GFLOP_PER_IMG_FWD_BWD if args.model == "T96" else 1554.3
+    model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, attn_drop_rate=args.attn_drop, **arch).set_precision(args.precision).to(dev).train()
     if world > 1:
         from semantic_segmentation_of_stylegan2_artifacts_b200.dp import DataParallelB200
         model = DataParallelB200(model)
@@ -324,7 +327,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"MS-UNet T96 (embed 96, depths 2-2-6-2, window 7) training step fwd+DynamicLoss+bwd, "
+            "config": {"workload": f"MS-UNet {args.model} ({'embed 96, depths 2-2-6-2' if args.model == 'T96' else 'embed 128, depths 2-2-18-2'}, window 7) training step fwd+DynamicLoss+bwd, "
                                    f"{S}x{S}, batch {B}/GPU (global {B * world}), drop_path {args.drop_path}, attn_drop {args.attn_drop}",
                        "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                        "l2": "working set >> L2: ~10 GB of activations are written and re-read every step",
@@ -332,7 +335,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "model_tflops": value * GFLOP_PER_IMG_FWD_BWD / 1e3 / world,
+            "model_tflops": value * gflop_img / 1e3 / world,
             "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

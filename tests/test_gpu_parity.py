@@ -323,3 +323,32 @@ def test_cuda_prefetcher_yields_every_batch_in_order():
     assert seen == [(float(i), float(-i)) for i in range(5)]
     with pytest.raises(RuntimeError):
         CudaPrefetcher(batches, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_model_embed128_vs_oracle(pkg, prec):
+    """config.yaml's default width (embed 128, heads 4-8-16-32; depths cut to 2-2-2-2 to keep the oracle fast): logits, loss
+    and gradient norms vs the CPU oracle on the same deterministic weights (channel counts 128..1024: other LayerNorm
+    vector counts, GEMM tiles and a 128-channel conv head than T96)."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    kw = dict(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32))
+    cfg = O.Cfg(img_size=128, **kw)
+    sd = O.make_weights(cfg)
+    x, y = O.make_inputs(cfg, 2)
+    ref_logits, ref_loss, ref_grads = O.train_step(sd, x, y, cfg)
+    m = build_model(cfg, prec)
+    logits = m(x.to(DEV))
+    loss = DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)(logits, y.to(DEV))
+    loss.backward()
+    f32 = prec == "fp32"
+    assert relmax(logits.float(), ref_logits) < (1e-3 if f32 else 3e-2)
+    assert abs(loss.item() - ref_loss.item()) < (1e-4 if f32 else 2e-3) * abs(ref_loss.item())
+    params = dict(m.named_parameters())
+    for k, r in ref_grads.items():
+        if r is None:
+            continue
+        g = params[k].grad
+        assert g is not None, k
+        gn, rn = g.double().norm().item(), r.double().norm().item()
+        assert abs(gn - rn) < (1e-3 if f32 else 6e-2) * rn + 1e-7, (k, gn, rn)
