@@ -991,18 +991,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
+            // The issuing thread is the critical resource of this loop (ncu / SASS: ~21 instructions per MMA when every
+            // descriptor was rebuilt): descriptors are built once and advanced by adding to the 14-bit address field
+            // (shared memory < 256 KB, so the field cannot carry): +128 per 16-token K step, +1024 per 128-row M tile.
+            const uint64_t ad0 = make_desc_mnmajor_sw128(smem_u32(sA), WG_BOX_BYTES);
+            const uint64_t bd0 = make_desc_mnmajor_sw128(smem_u32(sB), WG_BOX_BYTES);
+            const uint32_t a_step = (uint32_t)(A_BYTES >> 4), b_step = (uint32_t)(B_BYTES >> 4);
             for (int kb = 0; kb < KB; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)stage * A_BYTES);
-                const uint32_t b_base = smem_u32(sB + (size_t)stage * B_BYTES);
+                const uint64_t ad = ad0 + (uint64_t)(stage * a_step), bd = bd0 + (uint64_t)(stage * b_step);
+                const uint32_t acc0 = kb != 0;
                 for (int mt = 0; mt < p.MT; mt++) {
-#pragma unroll
-                    for (int k = 0; k < WG_BK / 16; k++) {   // 16 tokens = 2048 B per K step
-                        const uint64_t adesc = make_desc_mnmajor_sw128(a_base + mt * 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES);
-                        const uint64_t bdesc = make_desc_mnmajor_sw128(b_base + k * 2048, WG_BOX_BYTES);
-                        tc_mma_bf16(tmem_base + mt * p.BN, adesc, bdesc, idesc, (kb | k) != 0);
-                    }
+                    const uint64_t am = ad + (uint64_t)(mt * (2 * WG_BOX_BYTES >> 4));
+                    const uint32_t d = tmem_base + mt * p.BN;
+                    tc_mma_bf16(d, am, bd, idesc, acc0);                  // 16 tokens = 2048 B per K step
+                    tc_mma_bf16(d, am + 128, bd + 128, idesc, 1);
+                    tc_mma_bf16(d, am + 256, bd + 256, idesc, 1);
+                    tc_mma_bf16(d, am + 384, bd + 384, idesc, 1);
                 }
                 tc_commit(&empty[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -1201,18 +1207,29 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
+            // descriptors built once, advanced through the 14-bit address field (the issuing thread is the critical
+            // resource: ~21 instructions per MMA when they were rebuilt): +128 per 16-pixel K step, +tap_step per tap
+            // (halo: tap t = dx is the slab shifted by t pixel rows = +128 B; the swizzle is address based)
+            const uint64_t ad0 = make_desc_mnmajor_sw128(smem_u32(sA), BOX);
+            const uint64_t bd0 = make_desc_mnmajor_sw128(smem_u32(sB), p.halo ? XBOX : BOX);
+            const uint32_t a_step = (uint32_t)(A_BYTES >> 4), b_step = (uint32_t)(B_BYTES >> 4);
+            const uint32_t tap_step = p.halo ? (128 >> 4) : (uint32_t)((p.boxes * BOX) >> 4);
+            const int ksteps = p.WB / 16;
             for (int kb = 0; kb < KB; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)stage * A_BYTES);
-                const uint32_t b_base = smem_u32(sB + (size_t)stage * B_BYTES);
+                const uint64_t ad = ad0 + (uint64_t)(stage * a_step), bd = bd0 + (uint64_t)(stage * b_step);
+                const uint32_t acc0 = kb != 0;
                 for (int t = 0; t < ntap; t++) {
-                    for (int k = 0; k < p.WB / 16; k++) {
-                        const uint64_t adesc = make_desc_mnmajor_sw128(a_base + k * 2048, BOX);
-                        // halo: tap t = dx is the slab shifted by t pixel rows (+128 B); swizzle is address based
-                        const uint64_t bdesc = p.halo ? make_desc_mnmajor_sw128(b_base + t * 128 + k * 2048, XBOX)
-                                                      : make_desc_mnmajor_sw128(b_base + t * p.boxes * BOX + k * 2048, BOX);
-                        tc_mma_bf16(tmem_base + t * p.BN, adesc, bdesc, idesc, (kb | k) != 0);
+                    const uint64_t bt = bd + (uint64_t)(t * tap_step);
+                    const uint32_t d = tmem_base + t * p.BN;
+                    if (ksteps == 4) {
+                        tc_mma_bf16(d, ad, bt, idesc, acc0);
+                        tc_mma_bf16(d, ad + 128, bt + 128, idesc, 1);
+                        tc_mma_bf16(d, ad + 256, bt + 256, idesc, 1);
+                        tc_mma_bf16(d, ad + 384, bt + 384, idesc, 1);
+                    } else {
+                        for (int k = 0; k < ksteps; k++) tc_mma_bf16(d, ad + (uint64_t)(k * 128), bt + (uint64_t)(k * 128), idesc, (kb | k) != 0);
                     }
                 }
                 tc_commit(&empty[stage]);
