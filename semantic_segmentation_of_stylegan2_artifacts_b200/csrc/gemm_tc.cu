@@ -1319,8 +1319,9 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     while (p.G > 1 && 2 * (p.boxes + p.G * p.boxes) * BOX > 200 * 1024) p.G--;
     p.n_groups = (9 + p.G - 1) / p.G;
     int stage_bytes = (p.boxes + p.G * p.boxes) * BOX;
-    // measured slower than the 5+4 tap grouping on B200 (3.8 vs 2.6 ms per step): opt-in only
-    static const int halo_on = getenv("MSU_WGRAD_HALO") ? atoi(getenv("MSU_WGRAD_HALO")) : 0;
+    // halo slabs (taps grouped by dy) halve the L2 -> SM operand traffic of the 5+4 tap grouping: 1025 vs 1230 us at 16 x 512^2 x 96
+    // once the MMA issue loop was made cheap (MSU_WGRAD_HALO=0 restores the tap grouping)
+    static const int halo_on = getenv("MSU_WGRAD_HALO") ? atoi(getenv("MSU_WGRAD_HALO")) : 1;
     p.halo = (halo_on && p.WB == 64 && 3 * p.BN <= TC_TMEM_COLS) ? 1 : 0;
     if (p.halo) {   // taps grouped by dy: 3 accumulators per CTA, dZ read 3x but X read once per dy (1.8x less L2 traffic)
         p.G = 3;
