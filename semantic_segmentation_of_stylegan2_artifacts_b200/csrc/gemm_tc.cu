@@ -245,14 +245,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage);
                     const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage);
                     if (p.mode == 4) {
-                        const int bb = p.BN * 64;
+                        // one descriptor pair per stage, advanced through the 14-bit address field (the issuing thread is
+                        // close to the critical path at 12 MMAs per K block): pixel shift dx = +64 B = +4 (the swizzle
+                        // follows the address bits), second image row = +TC_HALO32_BYTES, weight tile of tap dx = +BN*64 B
+                        const uint64_t ad = make_desc_kmajor_sw64_g(a_addr), bd = make_desc_kmajor_sw64_g(b_addr);
+                        const uint32_t bstep = (uint32_t)(p.BN * 4);
+                        const uint32_t acc0 = kb != 0;
+#pragma unroll
                         for (int r = 0; r < 2; r++) {
-                            for (int dx = 0; dx < 3; dx++) {   // pixel shift = +64 B (swizzle follows the address bits)
-                                const uint64_t adesc = make_desc_kmajor_sw64_g(a_addr + r * TC_HALO32_BYTES + dx * 64);
-                                const uint64_t bdesc = make_desc_kmajor_sw64_g(b_addr + dx * bb);
-                                tc_mma_bf16(d_tmem + r * 128, adesc, bdesc, idesc, (kb | dx) != 0);
-                                tc_mma_bf16(d_tmem + r * 128, adesc + 2, bdesc + 2, idesc, 1);
-                            }
+                            const uint64_t ar = ad + (uint64_t)(r * (TC_HALO32_BYTES >> 4));
+                            const uint32_t d = d_tmem + r * 128;
+                            tc_mma_bf16(d, ar, bd, idesc, acc0);
+                            tc_mma_bf16(d, ar + 2, bd + 2, idesc, 1);
+                            tc_mma_bf16(d, ar + 4, bd + bstep, idesc, 1);
+                            tc_mma_bf16(d, ar + 6, bd + bstep + 2, idesc, 1);
+                            tc_mma_bf16(d, ar + 8, bd + 2 * bstep, idesc, 1);
+                            tc_mma_bf16(d, ar + 10, bd + 2 * bstep + 2, idesc, 1);
                         }
                     } else if (p.mode == 3) {
                         for (int dx = 0; dx < 3; dx++) {
