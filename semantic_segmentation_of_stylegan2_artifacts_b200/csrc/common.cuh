@@ -207,6 +207,21 @@ inline AttnDrop make_attn_drop(float p, const uint32_t* seed) {
     return d;
 }
 
+// Function attributes (max dynamic shared memory) live per device: one flag per (call site, device) so that several devices
+// driven from one process (nn.DataParallel threads, trainer.py:96-97) each get theirs.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        slot = dev & 63;
+        return !done[slot];
+    }
+    void set() { done[slot] = true; }
+    static thread_local int slot;
+};
+inline thread_local int PerDeviceOnce::slot = 0;
+
 inline int num_sms() {
     static int n = 0;
     if (!n) {

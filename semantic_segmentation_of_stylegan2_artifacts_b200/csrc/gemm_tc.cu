@@ -871,13 +871,13 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             if (E->H != nullptr && !make_map_slab(&tmAux, E->H, M, N, E->ldh)) return 1;   // gelu' operand: unmapped [M, N]
         }
     }
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    static PerDeviceOnce smem_set;
+    if (smem_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPW_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        smem_set = 227 * 1024;
+        smem_set.set();
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -1378,11 +1378,11 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
         }
     }
     const int smem = p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 48 + 4 * 2 * 32 * 8 + 1024;   // + column-sum combine buffer
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("wgrad_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr = true;
+        attr.set();
     }
     wgrad_conv_tc_kernel<<<p.n_groups * splits, WG_THREADS, smem, st>>>(tmZ, tmX, p);
     count_launch();
@@ -1486,11 +1486,11 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
             return 1;
     }
     const int smem = p.stages * stage_bytes + 1024 + 4 * 2 * 4096 + 1024;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr = true;
+        attr.set();
     }
     wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, tmW, p);
     count_launch();

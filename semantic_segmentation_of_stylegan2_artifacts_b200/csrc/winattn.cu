@@ -329,12 +329,12 @@ extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, vo
         if (rc != 1) return rc;
     }
     if (dtype == MSU_F32) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(winattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr = true; }
+        static PerDeviceOnce attr;
+        if (attr.need()) { cudaFuncSetAttribute(winattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr.set(); }
         winattn_fwd_kernel<float><<<grid, AW * 32, FWD_SMEM, st>>>((const float*)qkv, bias, (float*)O, n_windows, nH, g, ad);
     } else if (dtype == MSU_BF16) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(winattn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr = true; }
+        static PerDeviceOnce attr;
+        if (attr.need()) { cudaFuncSetAttribute(winattn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr.set(); }
         winattn_fwd_kernel<__nv_bfloat16><<<grid, AW * 32, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)O, n_windows, nH, g, ad);
     } else {
         MSU_REQUIRE(false, "msu_winattn_fwd: unsupported dtype %d", dtype);
@@ -365,13 +365,13 @@ extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, co
         MSU_REQUIRE(false, "msu_winattn_bwd: tcgen05 path unavailable for these pointers (workspace was sized for it)");
     }
     if (dtype == MSU_F32) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(winattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr = true; }
+        static PerDeviceOnce attr;
+        if (attr.need()) { cudaFuncSetAttribute(winattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr.set(); }
         winattn_bwd_kernel<float><<<grid, AW * 32, BWD_SMEM, st>>>((const float*)qkv, bias, (const float*)O, (const float*)dO,
                                                                   (float*)dqkv, dbias_partial, n_windows, nH, g, ad);
     } else if (dtype == MSU_BF16) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(winattn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr = true; }
+        static PerDeviceOnce attr;
+        if (attr.need()) { cudaFuncSetAttribute(winattn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); attr.set(); }
         winattn_bwd_kernel<__nv_bfloat16><<<grid, AW * 32, BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (const __nv_bfloat16*)O,
                                                                           (const __nv_bfloat16*)dO, (__nv_bfloat16*)dqkv,
                                                                           dbias_partial, n_windows, nH, g, ad);

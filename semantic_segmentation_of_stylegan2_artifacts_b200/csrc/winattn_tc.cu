@@ -280,11 +280,11 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 1;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(winattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
         if (e != cudaSuccess) { set_error("winattn_fwd_tc: %s", cudaGetErrorString(e)); return (int)e; }
-        attr = true;
+        attr.set();
     }
     const int64_t pairs = (n_windows + 1) / 2;
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3 + nH - 1) / nH));
@@ -584,11 +584,11 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
     if (!make_attn_map(&tmQKV, qkv, n_windows * WT, 3 * C) || !make_attn_map(&tmDO, dO, n_windows * WT, C) ||
         !make_attn_map(&tmOut, dqkv, n_windows * WT, 3 * C, WT))
         return 1;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(winattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) { set_error("winattn_bwd_tc: %s", cudaGetErrorString(e)); return (int)e; }
-        attr = true;
+        attr.set();
     }
     dim3 grid(winattn_bwd_tc_grid(n_windows, nH), nH);
     static const int trace_on = getenv("MSU_ATT_TRACE") ? atoi(getenv("MSU_ATT_TRACE")) : 0;

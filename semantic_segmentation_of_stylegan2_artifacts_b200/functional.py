@@ -39,6 +39,14 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _al(*ts):
+    """Parameters as the kernels want them: contiguous and 16-byte aligned (they are read with 128-bit loads).  nn.DataParallel
+    replicas (trainer.py:96-97) are 4-byte-aligned slices of one broadcast buffer: those get an aligned private copy (the
+    gradients still flow to the original tensors: backward returns them by position)."""
+    out = tuple(t if (t is None or (t.is_contiguous() and t.data_ptr() % 16 == 0)) else t.contiguous().clone() for t in ts)
+    return out if len(out) > 1 else out[0]
+
+
 # ----------------------------------------------------------------------------------------------
 # Weight-gradient side stream: dW / db GEMMs (and their split-K reduces) are off the critical path of a block's
 # backward, so they are enqueued on a second stream and overlap the dgrad chain (small reduce kernels fill the SMs a
@@ -77,12 +85,11 @@ class _WgradFork:
         self.keep.clear()
 
     def __enter__(self):
-        self._prev = ops.SIDE
-        ops.SIDE = self if self.on else None
+        self._prev = ops.set_side(self if self.on else None)
         return self
 
     def __exit__(self, *exc):
-        ops.SIDE = self._prev
+        ops.set_side(self._prev)
         self.join()
         return False
 
@@ -146,6 +153,8 @@ class SwinBlockFn(Function):
                 B, H, W, nH, shift, attn_p=0.0, drop_seed=None):
         ops._need_cuda(x, "x")
         x = _c(x)
+        n1w, n1b, qkvw, qkvb, projw, projb, table, n2w, n2b, f1w, f1b, f2w, f2b = _al(
+            n1w, n1b, qkvw, qkvb, projw, projb, table, n2w, n2b, f1w, f1b, f2w, f2b)
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = B * H * W
@@ -244,6 +253,7 @@ class PatchEmbedFn(Function):
     @staticmethod
     def forward(ctx, img, pw, pb, nw, nb, dtype):
         ops._need_cuda(img, "image")
+        pw, pb, nw, nb = _al(pw, pb, nw, nb)
         img = _c(img.float())
         dev = img.device
         B, _, S, _ = img.shape
@@ -281,6 +291,7 @@ class PatchMergeFn(Function):
     @staticmethod
     def forward(ctx, x, nw, nb, rw, B, H, W):
         x = _c(x)
+        nw, nb, rw = _al(nw, nb, rw)
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         Tm = B * (H // 2) * (W // 2)
@@ -316,6 +327,7 @@ class PatchExpandFn(Function):
     @staticmethod
     def forward(ctx, x, ew, nw, nb, B, H, W):
         x = _c(x)
+        ew, nw, nb = _al(ew, nw, nb)
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = B * H * W
@@ -356,6 +368,7 @@ class ConcatLinearFn(Function):
     @staticmethod
     def forward(ctx, x, skip, w, b):
         x, skip = _c(x), _c(skip)
+        w, b = _al(w, b)
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = x.numel() // Cd
@@ -397,6 +410,7 @@ class LayerNormFn(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         x = _c(x)
+        w, b = _al(w, b)
         Cd = x.shape[-1]
         nrows = x.numel() // Cd
         y, mean, rstd = ops.ln_fwd(x, w, b, nrows, Cd)
@@ -421,6 +435,7 @@ class HeadFn(Function):
     @staticmethod
     def forward(ctx, x, ew, c1w, c1b, c2w, c2b, nw, nb, ow, B, r):
         x = _c(x)
+        ew, c1w, c1b, c2w, c2b, nw, nb = _al(ew, c1w, c1b, c2w, c2b, nw, nb)
         dev, dt = x.device, x.dtype
         E = x.shape[-1]
         T = B * r * r
@@ -441,7 +456,7 @@ class HeadFn(Function):
              Mp, E, 9 * E, dev)
         z2 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
-        owv = _c(ow).view(E)
+        owv = _al(_c(ow).view(E))
         logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
         ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd)
         ctx.cfg = (B, r, x.shape, ow.shape)

@@ -84,16 +84,26 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     return e
 
 
-SIDE = None  # functional.py: the active weight-gradient fork (parameter-gradient reduces ride on its side stream)
+import threading as _threading
+
+_tls = _threading.local()   # per-thread: nn.DataParallel runs one autograd thread per device
+
+
+def set_side(fork):
+    """functional.py: the active weight-gradient fork of this thread (parameter-gradient reduces ride on its side stream)."""
+    prev = getattr(_tls, "side", None)
+    _tls.side = fork
+    return prev
 
 
 def _off_path(fn, *keep):
     """Run a launch whose result is only needed after the backward joins (parameter-gradient reductions).
     `keep`: temporaries read by that launch; they must outlive the join (the caching allocator would otherwise hand
     their memory to a later main-stream allocation while the side stream still reads it)."""
-    if SIDE is not None:
-        SIDE.keep.extend(keep)
-        SIDE.run(fn)
+    side = getattr(_tls, "side", None)
+    if side is not None:
+        side.keep.extend(keep)
+        side.run(fn)
     else:
         fn()
 
