@@ -23,3 +23,19 @@ class DynamicLoss(torch.nn.Module):
         if output[0].numel() != target[0].numel():
             raise ValueError(f"target shape {tuple(target.shape)} does not match output {tuple(output.shape)}")
         return DynamicLossFn.apply(output, target, self.alpha, self.beta, self.tversky_bce_mix)
+
+    @torch.no_grad()
+    def per_sample(self, output, target):
+        """Per-image losses [B] (fp32, device-resident, no host sync): what `forward` returns for each image alone — used by the
+        batched validation loop (the reference evaluates one image per call, validation_functions.py:89-104)."""
+        from .. import ops
+        if target.dim() == 3:
+            target = target.unsqueeze(1)
+        B = output.size(0)
+        if B != target.size(0):
+            raise ValueError(f"Batchsize from ouptut {B} not equal to batchsize target {target.size(0)}")
+        ops._need_cuda(output, "logits")
+        lg = output.contiguous().view(B, -1)
+        tg = target.float().contiguous().view(B, -1)
+        _, stats, _ = ops.loss_fwd(lg, tg, self.alpha, self.beta, self.tversky_bce_mix)
+        return stats[:, 4].clone()

@@ -130,14 +130,15 @@ def calculate_metrics(model, logging, testloader, dynamic_loss, csv_all_epoch, c
     confusion_matrix_soft_list, fake_conf_matrix_bin_list, fake_confusion_matrix_soft_list = [], [], []
     accuracy_list_fake, metric_fake_list, accuracy_list, confusion_matrix_bin_list = [], [], [], []
 
+    # Device pass: every batch (any batch size — the reference asserts 1, validation_functions.py:89) is evaluated without a host
+    # synchronisation; losses, integer counts, soft sums and the first `output_num` heat-maps stay on the device until the end.
+    dev_loss, dev_counts, dev_soft, names, kept_pred = [], [], [], [], []
     with torch.inference_mode():
         for i_batch, sampled_batch in tqdm(enumerate(testloader), total=len(testloader)):
             image = sampled_batch["image"].to(device, non_blocking=True)
             loss_label = sampled_batch["label"].to(device, non_blocking=True)
-            case_name = sampled_batch['case_name'][0]
             assert image.ndim == 4
             assert loss_label.ndim in (3, 4)
-            assert image.shape[0] == 1
             B, C, H, W = image.shape
             assert ((H, W) != tuple(patch_size)) == False  # noqa: E712
             image = image.float()
@@ -146,40 +147,50 @@ def calculate_metrics(model, logging, testloader, dynamic_loss, csv_all_epoch, c
             out_logits = model(image)
             if out_logits.shape[1] != 1:
                 raise ValueError(f"Binary task expected 1 logit channel, got {out_logits.shape[1]}")
-            loss_t = dynamic_loss(out_logits, loss_label)
-            counts, soft, pred = image_counts_from_logits(out_logits, label, sig_threshold, want_pred=True)
-            # single device->host hop per image: loss + 4 counts + 8 soft sums
-            val_loss = float(loss_t)
-            c = counts.cpu().tolist()[0]
-            s = soft.cpu().tolist()[0]
-            pred = pred[0]
-            has_artifact = (c[0] + c[2]) > 0  # ground_truth.any()  (tp + fn = |gt|)
+            if hasattr(dynamic_loss, "per_sample"):
+                loss_b = dynamic_loss.per_sample(out_logits, loss_label)
+            else:   # a foreign loss object: one call per image, as the reference does
+                loss_b = torch.stack([dynamic_loss(out_logits[b:b + 1], loss_label[b:b + 1]).float().reshape(()) for b in range(B)])
+            want_pred = len(kept_pred) < output_num
+            counts, soft, pred = image_counts_from_logits(out_logits, label, sig_threshold, want_pred=want_pred)
+            dev_loss.append(loss_b.float())
+            dev_counts.append(counts)
+            dev_soft.append(soft)
+            case_names = sampled_batch['case_name']
+            for b in range(B):
+                names.append(case_names[b] if b < len(case_names) else f"{case_names[0]}_{b}")
+                if len(kept_pred) < output_num and pred is not None:
+                    kept_pred.append((names[-1], pred[b]))
+    # one device -> host hop for the whole split
+    all_loss = torch.cat(dev_loss).cpu().tolist() if dev_loss else []
+    all_counts = torch.cat(dev_counts).cpu().tolist() if dev_counts else []
+    all_soft = torch.cat(dev_soft).cpu().tolist() if dev_soft else []
+    output_saver = [(n, p.detach().cpu()) for n, p in kept_pred]
 
-            if not has_artifact:
-                real_image_counter += 1
-                confusion_matrix_bin, confusion_matrix_soft, accuracy, FRP = _real_from_counts(c, s)
-                confusion_matrix_bin_list.append(confusion_matrix_bin)
-                real_conf_matrix_bin_list.append(confusion_matrix_bin)
-                real_confusion_matrix_soft_list.append(confusion_matrix_soft)
-                confusion_matrix_soft_list.append(confusion_matrix_soft)
-                accuracy_list.append((accuracy, float(val_loss)))
-                accuracy_list_real.append((accuracy, float(val_loss)))
-                FRP_list.append(float(FRP))
-            else:
-                (bin_accuracy, bin_recall, bin_precision, bin_IoU, bin_dice, bin_f1, confusion_matrix_bin,
-                 confusion_matrix_soft, i_soft_dice, i_soft_iou) = _fake_from_counts(c, s)
-                metric_fake_list.append([bin_accuracy, bin_recall, bin_precision, bin_IoU, bin_dice, bin_f1,
-                                         i_soft_dice, i_soft_iou])
-                confusion_matrix_bin_list.append(confusion_matrix_bin)
-                fake_conf_matrix_bin_list.append(confusion_matrix_bin)
-                confusion_matrix_soft_list.append(confusion_matrix_soft)
-                fake_confusion_matrix_soft_list.append(confusion_matrix_soft)
-                accuracy_list.append((bin_accuracy, float(val_loss)))
-                accuracy_list_fake.append((bin_accuracy, float(val_loss)))
-
-            if i_batch < output_num:
-                output_saver.append((case_name, pred.detach().cpu()))
-            num_cases += 1
+    for val_loss, c, s in zip(all_loss, all_counts, all_soft):
+        has_artifact = (c[0] + c[2]) > 0  # ground_truth.any()  (tp + fn = |gt|)
+        if not has_artifact:
+            real_image_counter += 1
+            confusion_matrix_bin, confusion_matrix_soft, accuracy, FRP = _real_from_counts(c, s)
+            confusion_matrix_bin_list.append(confusion_matrix_bin)
+            real_conf_matrix_bin_list.append(confusion_matrix_bin)
+            real_confusion_matrix_soft_list.append(confusion_matrix_soft)
+            confusion_matrix_soft_list.append(confusion_matrix_soft)
+            accuracy_list.append((accuracy, float(val_loss)))
+            accuracy_list_real.append((accuracy, float(val_loss)))
+            FRP_list.append(float(FRP))
+        else:
+            (bin_accuracy, bin_recall, bin_precision, bin_IoU, bin_dice, bin_f1, confusion_matrix_bin,
+             confusion_matrix_soft, i_soft_dice, i_soft_iou) = _fake_from_counts(c, s)
+            metric_fake_list.append([bin_accuracy, bin_recall, bin_precision, bin_IoU, bin_dice, bin_f1,
+                                     i_soft_dice, i_soft_iou])
+            confusion_matrix_bin_list.append(confusion_matrix_bin)
+            fake_conf_matrix_bin_list.append(confusion_matrix_bin)
+            confusion_matrix_soft_list.append(confusion_matrix_soft)
+            fake_confusion_matrix_soft_list.append(confusion_matrix_soft)
+            accuracy_list.append((bin_accuracy, float(val_loss)))
+            accuracy_list_fake.append((bin_accuracy, float(val_loss)))
+        num_cases += 1
 
     if num_cases == 0:
         logging.error(f"No {split} cases processed. Check your dataset/split.")

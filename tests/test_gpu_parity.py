@@ -352,3 +352,59 @@ def test_model_embed128_vs_oracle(pkg, prec):
         assert g is not None, k
         gn, rn = g.double().norm().item(), r.double().norm().item()
         assert abs(gn - rn) < (1e-3 if f32 else 6e-2) * rn + 1e-7, (k, gn, rn)
+
+
+class _Rows:
+    def __init__(self):
+        self.rows = []
+
+    def writerow(self, r):
+        self.rows.append(r)
+
+
+@pytest.mark.gpu
+def test_calculate_metrics_batched_equals_per_image_and_oracle(pkg):
+    """The validation loop (scripts/validation_functions.py:37-211): batch-3 loader == batch-1 loader (the reference's only mode),
+    and the aggregated soft Dice / FPR / Score equal the oracle formulas applied image by image to the same logits."""
+    import logging
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.scripts import validation_functions as VF
+    cfg = O.Cfg(img_size=96, **O.T32)
+    # fp32 mode: in bf16 the tiny 96-px maps switch GEMM backends with the batch size (M < 64 rows takes the fp32-FMA engine,
+    # whose GELU is erff instead of the tanh form), which moves a handful of borderline pixels
+    m = build_model(cfg, "fp32").eval()
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand(6, 3, 96, 96, generator=g)
+    labels = (torch.rand(6, 96, 96, generator=g) > 0.85).float() * 255.0
+    labels[1] = 0
+    labels[4] = 0
+    names = [f"case{i}" for i in range(6)]
+
+    def loader(bs):
+        return [{"image": imgs[i:i + bs], "label": labels[i:i + bs], "case_name": names[i:i + bs]} for i in range(0, 6, bs)]
+
+    outs = {}
+    for bs in (1, 3):
+        rows = [_Rows() for _ in range(5)]
+        res = VF.calculate_metrics(m, logging, loader(bs), DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45), *rows, 0.5, 7,
+                                   device=DEV, split="val", img_size=96, sig_threshold=0.5, output_num=2)
+        outs[bs] = (res, [r.rows for r in rows])
+    (d1, s1, sc1, f1), r1 = outs[1]
+    (d3, s3, sc3, f3), r3 = outs[3]
+    assert abs(d1 - d3) < 1e-5 and abs(sc1 - sc3) < 1e-3 and abs(f1 - f3) < 1e-4
+    assert [n for n, _ in s1] == [n for n, _ in s3] == names[:2]
+    assert all(float((a[1].float() - b[1].float()).abs().max()) < 1e-4 for a, b in zip(s1, s3))
+    assert [len(a) for a in r1] == [len(b) for b in r3]
+    # oracle: the same logits, image by image
+    with torch.no_grad():
+        logits = torch.cat([m(imgs[i:i + 3].to(DEV)) for i in range(0, 6, 3)])
+    pred = torch.sigmoid(logits.squeeze(1))
+    pb, gt = (pred > 0.5), (labels.to(DEV) > 0)
+    dice, fpr = [], []
+    for i in range(6):
+        if bool(gt[i].any()):
+            dice.append(O.metrics_fake(pb[i].cpu().numpy(), pred[i].float().cpu().numpy(), gt[i].cpu().numpy())[8])
+        else:
+            fpr.append(O.metrics_real(pb[i].cpu().numpy(), pred[i].float().cpu().numpy(), gt[i].cpu().numpy())[3])
+    assert abs(d3 - float(np.mean(dice))) < 1e-5 and abs(f3 - float(np.mean(fpr))) < 1e-4
+    assert abs(sc3 - (float(np.mean(dice)) - 10 * float(np.mean(fpr)))) < 1e-3
