@@ -123,3 +123,21 @@ def test_dropin_overlay_resolves_reference_imports(built):
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert all(m.startswith(PKG + ".") for m in out.stdout.split()), out.stdout
+
+
+def test_checkpoint_roundtrip_legacy_format(built, tmp_path):
+    """best_model.pth interchange (trainer.py:372-379 saves, test.py:97-109 loads with strict=True): a state_dict written in
+    the legacy (non-zip) serialisation and in the default one loads back bit-identically, keys in the reference's order."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    kw = dict(img_size=64, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8])
+    m = MSUNetSys(**kw)
+    sd = m.state_dict()
+    for legacy in (True, False):
+        f = tmp_path / f"best_model_{legacy}.pth"
+        torch.save({"epoch": 3, "model": sd}, f, _use_new_zipfile_serialization=not legacy)
+        ck = torch.load(f, map_location="cpu", weights_only=False)
+        m2 = MSUNetSys(**kw)
+        missing = m2.load_state_dict(ck["model"], strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        assert list(m2.state_dict().keys()) == list(sd.keys())
+        assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))
