@@ -1451,7 +1451,10 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return 1;
     const int base_ctas = p.n_super * p.n_q_tiles;
-    int splits = (num_sms() + base_ctas - 1) / base_ctas;
+    // whole waves: one CTA per SM is resident (shared memory), so splits * base_ctas must not spill a few CTAs into a second
+    // wave (13 splits x 12 tiles = 156 CTAs cost 43 us where 8 x 12 took 32 us at 16384 x 1536 x 384)
+    int splits = num_sms() / base_ctas;
+    if (splits < 1) splits = 1;
     if (env_splits) splits = env_splits;
     const int64_t max_splits_t = (T + 511) / 512;
     if (splits > max_splits_t) splits = (int)max_splits_t;
