@@ -287,7 +287,8 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
         attr.set();
     }
     const int64_t pairs = (n_windows + 1) / 2;
-    const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3 + nH - 1) / nH));
+    // whole waves: 3 CTAs per SM are resident; a few CTAs more would start late and double the tail
+    const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3) / nH));
     dim3 grid(gx, nH);
     winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tmO, bias, n_windows, nH, g, ad);
     count_launch();
@@ -571,7 +572,7 @@ static bool make_attn_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_
 
 int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
     const int64_t pairs = (n_windows + 1) / 2;
-    return (int)imax(1, imin(pairs, ((int64_t)num_sms() * 2 + nH - 1) / nH));
+    return (int)imax(1, imin(pairs, ((int64_t)num_sms() * 2) / nH));   // whole waves of the 2 resident CTAs per SM
 }
 
 // returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
