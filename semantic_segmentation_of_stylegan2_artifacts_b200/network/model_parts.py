@@ -71,8 +71,13 @@ class SwinTransformerBlock(nn.Module):
 
     def forward(self, x):  # x [B, H, W, C]
         B, H, W, _ = x.shape
-        sd1 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
-        sd2 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
+        pool = getattr(self, "_sd_pool", None)      # rows pre-drawn for the whole forward by MSUNetSys (3 launches instead of 88)
+        if pool is not None and pool[0].shape[0] == B and self.training:
+            sd1, sd2 = pool
+            self._sd_pool = None
+        else:
+            sd1 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
+            sd2 = Fn.drop_path_noise(self.sd_prob, self.training, B, x.device)
         a, m = self.attn, self.mlp
         # attention dropout (TV:models/swin_transformer.py:205): two fresh 32-bit words per call from PyTorch's generator
         # (a device tensor, so CUDA-graph replays draw new masks); the kernels hash (seed, window, head, query, key)
@@ -345,9 +350,25 @@ class MSUNetSys(nn.Module):
         return Fn.HeadFn.apply(x, u.expand.weight, u.refine1.weight, u.refine1.bias, u.refine2.weight, u.refine2.bias,
                                u.norm.weight, u.norm.bias, self.output.weight, B, H)
 
+    def _draw_drop_path(self, B, device):
+        """Stochastic-depth noise Bernoulli(1-p)/(1-p) per sample for every block of this forward in one shot
+        (TV:ops/stochastic_depth.py:35-44 draws it block by block: ~90 tiny launches per step)."""
+        blocks = [m for m in self.modules() if isinstance(m, SwinTransformerBlock) and m.sd_prob > 0.0]
+        if not blocks:
+            return
+        keep = getattr(self, "_sd_keep", None)
+        if keep is None or keep.device != device or keep.numel() != 2 * len(blocks):
+            keep = torch.tensor([1.0 - b.sd_prob for b in blocks for _ in range(2)], dtype=torch.float32, device=device)
+            self._sd_keep = keep
+        noise = (torch.rand(2 * len(blocks), B, device=device) < keep[:, None]).float() / keep[:, None]
+        for i, b in enumerate(blocks):
+            b._sd_pool = (noise[2 * i], noise[2 * i + 1])
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("MSUNet (B200) runs on CUDA only: there is no CPU fallback for the hot path")
+        if self.training:
+            self._draw_drop_path(x.shape[0], x.device)
         x, x_downsample = self.forward_features(x)
         x = self.forward_up_features(x, x_downsample)
         return self.up_x4(x)
