@@ -197,6 +197,28 @@ int msu_adamw_chunk(void);
 int msu_adamw_step(const MsuAdamTensor* table, const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t n_blocks,
                    const float* inv_scale, const float* found_inf, void* stream);
 
+/* Every weight shadow of a model in one launch (the per-tensor form is msu_prep_weight).  A job of mode 0 reads the fp32 master
+ * [R, C] once and writes the plain cast `dst` [R, C] and / or the transposed cast `dst_t` [C, R] (either may be NULL); modes 2, 3, 5
+ * are msu_prep_weight's conv / patch-embed re-layouts into `dst`.  blk_job / blk_tile map each block to (job, tile); a job owns
+ * msu_shadow_blocks(mode, R, C) consecutive tiles 0..n-1.  All pointers are device pointers. */
+typedef struct {
+    const float* src;
+    void* dst;
+    void* dst_t;
+    int64_t R, C;
+    int32_t mode;
+    int32_t dtype;      /* MSU_F32 / MSU_BF16 of dst and dst_t */
+} MsuShadowJob;
+int msu_shadow_blocks(int mode, int64_t R, int64_t C);
+int msu_refresh_shadows(const MsuShadowJob* jobs, const int32_t* blk_job, const int32_t* blk_tile, int32_t n_blocks, void* stream);
+
+/* Device-side input staging = the tail of the reference's per-sample transform for a whole batch,
+ * dataset/dataset.py:13-16 (horizontal flip of image and label) and :49-63 (uint8 HWC -> float32 / 255 in CHW; label -> (label > 127)
+ * as float32).  img_hwc [B,H,W,3] u8, label [B,H,W] u8 or NULL (then label_out NULL), flip [B] u8 (non-zero = flip that sample) or
+ * NULL; image_out [B,3,H,W] f32, label_out [B,H,W] f32.  Bit-exact against the numpy formulas. */
+int msu_stage_u8(const uint8_t* img_hwc, const uint8_t* label, const uint8_t* flip, float* image_out, float* label_out,
+                 int32_t B, int32_t H, int32_t W, void* stream);
+
 int msu_version(void);
 /* sizeof(MsuOperand) (which=0) / sizeof(MsuEpilogue) (which=1): lets a binding verify its struct layout. */
 int msu_struct_size(int which);

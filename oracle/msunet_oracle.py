@@ -465,3 +465,19 @@ def train_step(sd, x, y, cfg: Cfg, alpha=0.2, beta=0.8, mix=0.45, run_dead=False
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.is_floating_point()}
     return logits.detach(), loss.detach(), grads
+
+
+# ----------------------------------------------------------------------------------------------
+# Input staging: the tail of the per-sample transform, for a batch
+# ----------------------------------------------------------------------------------------------
+def stage_batch(images_u8: np.ndarray, labels_u8: np.ndarray, flips: np.ndarray):
+    """dataset/dataset.py:13-16 (flip of image and label along W), :62 (`astype(float32) / 255.0`), :63 (`label > 127`),
+    :83-84 (HWC -> CHW, label as float32), stacked over the batch like the DataLoader's default collate.
+    images_u8 [B,H,W,3] u8, labels_u8 [B,H,W] u8, flips [B] -> float32 [B,3,H,W], float32 [B,H,W]."""
+    imgs, labs = [], []
+    for im, lb, f in zip(images_u8, labels_u8, flips):
+        if f:
+            im, lb = np.flip(im, axis=1), np.flip(lb, axis=1)
+        imgs.append(np.transpose(im.astype(np.float32) / 255.0, (2, 0, 1)))
+        labs.append((lb > 127).astype(np.uint8).astype(np.float32))
+    return np.stack(imgs), np.stack(labs)

@@ -48,6 +48,9 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _SIGS = {
     "msu_adamw_chunk": [],
     "msu_adamw_step": [_P, _P, _P, _I32, _P, _P, _P],
+    "msu_shadow_blocks": [C.c_int, _I64, _I64],
+    "msu_refresh_shadows": [_P, _P, _P, _I32, _P],
+    "msu_stage_u8": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "msu_gemm": [C.POINTER(MsuOperand), C.POINTER(MsuOperand), C.POINTER(MsuEpilogue), _I64, _I64, _I64, _P, _I64,
                  C.c_int, _P],
     "msu_colsum": [C.POINTER(MsuOperand), _I64, _I64, _P, C.c_int, _P, _I64, _P],

@@ -59,6 +59,78 @@ __global__ void prep_grad_kernel(int mode, const float* __restrict__ src, float*
     }
 }
 
+// ---- every weight shadow of a model in ONE launch ------------------------------------------------------------------------------
+// block -> (job, tile) through device maps (like the AdamW step).  Pair jobs (mode 0) read a 32 x 128 tile of the fp32 master once
+// and write both the plain cast [R, C] and the transposed cast [C, R] (through shared memory, both coalesced); the few re-laid-out
+// tensors (conv / patch-embed weights, modes 2 / 3 / 5 of msu_prep_weight) go through the same index formulas, SH_CHUNK outputs
+// per block.
+constexpr int SH_TR = 32, SH_TC = 128, SH_CHUNK = 4096, SH_THREADS = 256;
+
+__device__ __forceinline__ void shadow_store(void* dst, int dtype, int64_t i, float v) {
+    if (dtype == MSU_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dst)[i] = v;
+}
+
+__global__ void __launch_bounds__(SH_THREADS) refresh_shadows_kernel(const MsuShadowJob* __restrict__ jobs,
+                                                                    const int32_t* __restrict__ blk_job,
+                                                                    const int32_t* __restrict__ blk_tile) {
+    __shared__ float tile[SH_TR][SH_TC + 1];
+    const MsuShadowJob j = jobs[blk_job[blockIdx.x]];
+    const int t = blk_tile[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t R = j.R, C = j.C;
+    if (j.mode == 0) {
+        const int tiles_c = (int)((C + SH_TC - 1) / SH_TC);
+        const int64_t r0 = (int64_t)(t / tiles_c) * SH_TR, c0 = (int64_t)(t % tiles_c) * SH_TC;
+#pragma unroll
+        for (int i = 0; i < SH_TR / 8; i++) {
+            const int rr = warp + 8 * i;
+            const int64_t r = r0 + rr;
+#pragma unroll
+            for (int q = 0; q < SH_TC / 32; q++) {
+                const int cc = lane + 32 * q;
+                const int64_t c = c0 + cc;
+                const bool in = r < R && c < C;
+                const float v = in ? __ldg(j.src + r * C + c) : 0.f;
+                tile[rr][cc] = v;
+                if (in && j.dst != nullptr) shadow_store(j.dst, j.dtype, r * C + c, v);
+            }
+        }
+        __syncthreads();
+        if (j.dst_t != nullptr) {
+            const int64_t r = r0 + lane;
+#pragma unroll 4
+            for (int i = 0; i < SH_TC / 8; i++) {
+                const int cc = warp + 8 * i;
+                const int64_t c = c0 + cc;
+                if (c < C && r < R) shadow_store(j.dst_t, j.dtype, c * R + r, tile[lane][cc]);
+            }
+        }
+        return;
+    }
+    const int64_t n = j.mode == 5 ? R * 64 : R * C * 9;
+    const int64_t base = (int64_t)t * SH_CHUNK;
+    for (int k = 0; k < SH_CHUNK / SH_THREADS; k++) {
+        const int64_t idx = base + k * SH_THREADS + threadIdx.x;
+        if (idx >= n) break;
+        float v;
+        if (j.mode == 2) {          // conv [co=R, ci=C, 3,3] -> [co, (tap ci)]
+            const int64_t co = idx / (9 * C);
+            const int rem = (int)(idx % (9 * C)), tap = rem / (int)C, ci = rem % (int)C;
+            v = j.src[(co * C + ci) * 9 + tap];
+        } else if (j.mode == 3) {   // conv -> [ci, (tap' co)], tap' = 8 - tap
+            const int64_t ci = idx / (9 * R);
+            const int rem = (int)(idx % (9 * R)), tapf = rem / (int)R, co = rem % (int)R;
+            v = j.src[((int64_t)co * C + ci) * 9 + (8 - tapf)];
+        } else {                    // patch-embed [E=R, 48] -> [E, 64], zero padded K
+            const int64_t e = idx / 64;
+            const int kk = (int)(idx % 64);
+            v = kk < 48 ? j.src[e * 48 + kk] : 0.f;
+        }
+        shadow_store(j.dst, j.dtype, idx, v);
+    }
+}
+
 // image [B,3,S,S] NCHW fp32 -> rows [(b, py, px), 64]; col = c*16 + ky*4 + kx (Conv2d weight order), cols 48..63 zero
 template <typename T>
 __global__ void patchify4_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int S) {
@@ -136,6 +208,25 @@ extern "C" int msu_prep_weight(int mode, int dst_dtype, const float* src, void* 
     else MSU_REQUIRE(false, "msu_prep_weight: bad dtype %d", dst_dtype);
     count_launch();
     return check_launch("msu_prep_weight");
+}
+
+extern "C" int msu_shadow_blocks(int mode, int64_t R, int64_t C) {
+    if (R <= 0 || C <= 0) return -1;
+    int64_t nb;
+    if (mode == 0) nb = ((R + SH_TR - 1) / SH_TR) * ((C + SH_TC - 1) / SH_TC);
+    else if (mode == 2 || mode == 3) nb = (R * C * 9 + SH_CHUNK - 1) / SH_CHUNK;
+    else if (mode == 5) nb = (R * 64 + SH_CHUNK - 1) / SH_CHUNK;
+    else return -1;
+    return nb < (1ll << 30) ? (int)nb : -1;
+}
+
+extern "C" int msu_refresh_shadows(const MsuShadowJob* jobs, const int32_t* blk_job, const int32_t* blk_tile, int32_t n_blocks,
+                                   void* stream) {
+    MSU_REQUIRE(jobs && blk_job && blk_tile && n_blocks >= 0, "msu_refresh_shadows: bad arguments");
+    if (n_blocks == 0) return 0;
+    refresh_shadows_kernel<<<n_blocks, SH_THREADS, 0, (cudaStream_t)stream>>>(jobs, blk_job, blk_tile);
+    count_launch();
+    return check_launch("msu_refresh_shadows");
 }
 
 extern "C" int msu_patchify4(int dst_dtype, const float* img, void* out, int32_t B, int32_t S, void* stream) {

@@ -97,24 +97,115 @@ class _WgradFork:
 # ----------------------------------------------------------------------------------------------
 # bf16 weight shadows (caller-owned tensors, refreshed when the fp32 master changes)
 # ----------------------------------------------------------------------------------------------
-_shadows: dict = {}
+_shadows: dict = {}        # (id(param), mode, dtype) -> [weakref(param), version tag, shadow tensor, (R, Cc)]
+_shadow_gen = [0]          # bumped whenever an entry is (re)allocated or dropped: refresh plans are rebuilt lazily
+_cap_token = [None]        # identity of the most recent in-capture refresh (see refresh_shadows)
+
+
+def _drop_shadow(key):
+    _shadows.pop(key, None)
+    _shadow_gen[0] += 1
 
 
 def shadow(p: torch.Tensor, mode: int, R: int, Cc: int, shape, dtype=BF16) -> torch.Tensor:
-    """prep_weight(mode) of parameter `p`, cached on (parameter identity, version, storage)."""
+    """prep_weight(mode) of parameter `p`, cached on (parameter identity, version, storage).  While a CUDA graph is being captured
+    an entry only counts as fresh if `refresh_shadows` re-derived it inside this capture (the master may change between replays)."""
     key = (id(p), mode, dtype)
-    ver = (p._version, p.data_ptr())
     ent = _shadows.get(key)
-    capturing = torch.cuda.is_current_stream_capturing()
-    if ent is not None and ent[0]() is p and ent[1] == ver and not capturing:
-        return ent[2]
+    if ent is not None and ent[0]() is p:
+        if torch.cuda.is_current_stream_capturing():
+            if ent[1] == ("captured", _cap_token[0]):
+                return ent[2]
+        elif ent[1] == (p._version, p.data_ptr()):
+            return ent[2]
     t = ops.prep_weight(mode, p, R, Cc, shape, dtype)
     try:
-        ref = weakref.ref(p, lambda _r, k=key: _shadows.pop(k, None))
+        ref = weakref.ref(p, lambda _r, k=key: _drop_shadow(k))
     except TypeError:  # pragma: no cover
         ref = (lambda q=p: q)
-    _shadows[key] = (ref, ver, t)
+    # a shadow made during capture lives in the graph's pool and is re-derived by every replay: never valid for eager use
+    ver = ("captured", None) if torch.cuda.is_current_stream_capturing() else (p._version, p.data_ptr())
+    _shadows[key] = [ref, ver, t, (R, Cc)]
+    _shadow_gen[0] += 1
     return t
+
+
+def _shadow_plan(params, state: dict):
+    """Job table of every registered shadow of `params` (device-resident, rebuilt only when the registry changes)."""
+    import numpy as np
+    from . import _lib as L
+    plan = state.get("plan")
+    if plan is not None and plan["gen"] == _shadow_gen[0]:
+        return plan
+    rec = np.dtype([("src", "<u8"), ("dst", "<u8"), ("dst_t", "<u8"), ("R", "<i8"), ("C", "<i8"), ("mode", "<i4"), ("dtype", "<i4")])
+    jobs, ents, plist = [], [], []
+    for p in params:
+        mine = {}
+        for mode in (0, 1, 2, 3, 5):
+            for dt in (BF16, torch.float32):
+                e = _shadows.get((id(p), mode, dt))
+                if e is not None and e[0]() is p and e[2].device == p.device:
+                    mine[(mode, dt)] = e
+        if not mine:
+            continue
+        plist.append(p)
+        for dt in (BF16, torch.float32):
+            e0, e1 = mine.get((0, dt)), mine.get((1, dt))
+            if e0 is not None or e1 is not None:
+                R, Cc = (e0 or e1)[3]
+                jobs.append((p.data_ptr(), e0[2].data_ptr() if e0 else 0, e1[2].data_ptr() if e1 else 0, R, Cc, 0, L.dt(e0[2] if e0 else e1[2])))
+                ents += [(e, p) for e in (e0, e1) if e is not None]
+            for mode in (2, 3, 5):
+                e = mine.get((mode, dt))
+                if e is not None:
+                    jobs.append((p.data_ptr(), e[2].data_ptr(), 0, e[3][0], e[3][1], mode, L.dt(e[2])))
+                    ents.append((e, p))
+    plan = {"gen": _shadow_gen[0], "ents": ents, "plist": plist, "ptrs": [p.data_ptr() for p in plist], "n_blocks": 0}
+    if jobs:
+        dev = plist[0].device
+        table = np.array(jobs, dtype=rec)
+        bj, bt = [], []
+        for i, j in enumerate(jobs):
+            nb = int(L.lib().msu_shadow_blocks(int(j[5]), int(j[3]), int(j[4])))
+            if nb <= 0:
+                raise RuntimeError("msu_shadow_blocks rejected a weight shadow job")
+            bj.append(np.full(nb, i, dtype=np.int32))
+            bt.append(np.arange(nb, dtype=np.int32))
+        plan.update(table=torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).to(dev),
+                    bj=torch.from_numpy(np.concatenate(bj)).to(dev), bt=torch.from_numpy(np.concatenate(bt)).to(dev),
+                    n_blocks=int(sum(len(x) for x in bj)))
+    state["plan"] = plan
+    return plan
+
+
+def refresh_shadows(params, state: dict) -> None:
+    """Re-derive every registered shadow of `params` in ONE launch (`msu_refresh_shadows`) if any master changed since the shadows
+    were made — after an optimizer step that is all of them, which the per-tensor path would redo as ~230 small launches.  During
+    CUDA-graph capture the refresh is always recorded (replays must see the current masters) and marks the entries it covered as
+    fresh for this capture.  Shadows that are not registered yet (first forward) are made lazily by `shadow()` as before.
+    `state` is a caller-owned dict (one per model) holding the cached job table."""
+    from . import _lib as L
+    capturing = torch.cuda.is_current_stream_capturing()
+    plan = state.get("plan")
+    fresh_plan = plan is not None and plan["gen"] == _shadow_gen[0] and all(p.data_ptr() == q for p, q in zip(plan["plist"], plan["ptrs"]))
+    if not fresh_plan:
+        if capturing:
+            return            # building the table needs host -> device copies: leave this capture to the per-tensor path
+        state.pop("plan", None)
+        plan = _shadow_plan(params, state)
+    if plan["n_blocks"] == 0:
+        return
+    if not capturing and all(e[1] == (p._version, p.data_ptr()) for e, p in plan["ents"]):
+        return
+    L.check(L.lib().msu_refresh_shadows(plan["table"].data_ptr(), plan["bj"].data_ptr(), plan["bt"].data_ptr(), plan["n_blocks"],
+                                        L.stream_ptr()), "msu_refresh_shadows")
+    if capturing:
+        _cap_token[0] = tok = object()
+        for e, _p in plan["ents"]:
+            e[1] = ("captured", tok)
+    else:
+        for e, p in plan["ents"]:
+            e[1] = (p._version, p.data_ptr())
 
 
 def w_fwd(w: torch.Tensor, dt):

@@ -12,11 +12,14 @@ from __future__ import annotations
 import os
 import sys
 import warnings
+import weakref
 
 import torch
 import torch.nn as nn
 
 from .. import functional as Fn
+
+_SHADOW_STATE = weakref.WeakKeyDictionary()     # model -> cached weight-shadow refresh plan (functional.refresh_shadows)
 
 _PREC = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
 
@@ -369,6 +372,11 @@ class MSUNetSys(nn.Module):
             raise RuntimeError("MSUNet (B200) runs on CUDA only: there is no CPU fallback for the hot path")
         if self.training:
             self._draw_drop_path(x.shape[0], x.device)
+        if not getattr(self, "_is_replica", False):        # nn.DataParallel replicas get new parameter tensors every forward
+            st = _SHADOW_STATE.get(self)
+            if st is None:
+                st = _SHADOW_STATE[self] = {"params": list(self.parameters())}
+            Fn.refresh_shadows(st["params"], st)
         x, x_downsample = self.forward_features(x)
         x = self.forward_up_features(x, x_downsample)
         return self.up_x4(x)

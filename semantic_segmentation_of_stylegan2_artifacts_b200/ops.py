@@ -295,6 +295,32 @@ def patchify4(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
+def stage_u8(img_hwc: torch.Tensor, label: torch.Tensor | None = None, flip: torch.Tensor | None = None):
+    """dataset/dataset.py:13-16, 49-63 for a batch on the device: uint8 [B,H,W,3] (+ uint8 [B,H,W] label, + uint8 [B] flip flags) ->
+    float32 [B,3,H,W] image / 255 and float32 [B,H,W] (label > 127)."""
+    if img_hwc.dtype != torch.uint8 or img_hwc.dim() != 4 or img_hwc.shape[-1] != 3:
+        raise ValueError(f"stage_u8: image must be uint8 [B,H,W,3], got {img_hwc.dtype} {tuple(img_hwc.shape)}")
+    _need_cuda(img_hwc, "stage_u8 image")
+    B, H, W, _ = img_hwc.shape
+    img_hwc = img_hwc.contiguous()
+    if label is not None:
+        if label.dtype != torch.uint8 or tuple(label.shape) != (B, H, W):
+            raise ValueError(f"stage_u8: label must be uint8 [{B},{H},{W}], got {label.dtype} {tuple(label.shape)}")
+        label = label.contiguous()
+    if flip is not None:
+        if flip.dtype not in (torch.uint8, torch.bool) or flip.numel() != B:
+            raise ValueError("stage_u8: flip must be uint8 / bool [B]")
+        flip = flip.contiguous().view(torch.uint8)
+    out = torch.empty(B, 3, H, W, dtype=torch.float32, device=img_hwc.device)
+    lab = torch.empty(B, H, W, dtype=torch.float32, device=img_hwc.device) if label is not None else None
+    if B == 0:
+        return out, lab
+    L.check(L.lib().msu_stage_u8(img_hwc.data_ptr(), label.data_ptr() if label is not None else None,
+                                 flip.data_ptr() if flip is not None else None, out.data_ptr(),
+                                 lab.data_ptr() if lab is not None else None, B, H, W, L.stream_ptr()), "msu_stage_u8")
+    return out, lab
+
+
 def gather_rows(src: MsuOperand, M: int, N: int, like: torch.Tensor) -> torch.Tensor:
     """Dense [M, N] copy of a mapped / scaled operand (same dtype as `like`)."""
     out = torch.empty(M, N, dtype=like.dtype, device=like.device)

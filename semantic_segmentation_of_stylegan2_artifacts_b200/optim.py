@@ -157,6 +157,9 @@ class FusedAdamW(torch.optim.Optimizer):
         lay["ev"][k] = ev
         L.check(L.lib().msu_adamw_step(lay["devt"][k].data_ptr(), lay["bt"].data_ptr(), lay["bc"].data_ptr(),
                                        int(lay["bt"].numel()), None, None, L.stream_ptr()), "msu_adamw_step")
+        # the kernel wrote through raw pointers: bump the autograd version counters so that everything keyed on them
+        # (the bf16 weight shadows of functional.shadow, saved-tensor checks) sees the update
+        torch.autograd.graph.increment_version(plist)
         self._keep = grads                      # contiguous gradient copies stay alive until the next step
         return loss
 

@@ -67,3 +67,97 @@ def test_fused_adamw_rejects_cpu_and_amsgrad():
     p.grad = torch.ones(3)
     with pytest.raises(RuntimeError):
         FusedAdamW([p]).step()
+
+
+def _small_model(seed=0):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    torch.manual_seed(seed)
+    m = MSUNetSys(img_size=64, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], drop_path_rate=0.0).to(DEV)
+    m.set_precision("bf16")
+    return m.train()
+
+
+def _batch(seed=3, B=2, S=64):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, S, S, generator=g).to(DEV)
+    y = (torch.rand(B, S, S, generator=g) > 0.7).float().to(DEV)
+    return x, y
+
+
+def test_weight_shadows_follow_the_optimizer():
+    """Training in bf16 with FusedAdamW tracks the same run with torch.optim.AdamW: the raw-pointer update bumps the version
+    counters, so the bf16 weight shadows are re-derived (one msu_refresh_shadows launch) before the next forward."""
+    import semantic_segmentation_of_stylegan2_artifacts_b200 as pkg
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW
+    ma, mb = _small_model(0), _small_model(0)
+    oa = FusedAdamW(ma.parameters(), lr=2e-3, weight_decay=0.01)
+    ob = torch.optim.AdamW(mb.parameters(), lr=2e-3, weight_decay=0.01, foreach=False, fused=False)
+    crit = DynamicLoss()
+    x, y = _batch()
+    la, lb = [], []
+    for _ in range(4):
+        for m, o, ls in ((ma, oa, la), (mb, ob, lb)):
+            o.zero_grad(set_to_none=True)
+            loss = crit(m(x), y)
+            loss.backward()
+            o.step()
+            ls.append(float(loss))
+    assert abs(la[0] - lb[0]) < 1e-6                       # identical first step
+    assert la[3] < la[0] - 1e-3                            # the updates reach the forward pass (stale shadows would freeze the loss)
+    assert all(abs(a - b) < 0.02 * abs(b) + 1e-3 for a, b in zip(la, lb)), (la, lb)
+    # the refresh is one launch: a forward right after an optimizer step launches no per-tensor msu_prep_weight kernels
+    n0 = pkg.launch_count()
+    with torch.no_grad():
+        ma(x)
+    n_after_step = pkg.launch_count() - n0
+    n0 = pkg.launch_count()
+    with torch.no_grad():
+        ma(x)
+    assert n_after_step == (pkg.launch_count() - n0) + 1
+
+
+def test_refresh_shadows_bit_exact_vs_per_tensor_prep_and_under_graph_replay():
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import functional as Fn, ops
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    m = _small_model(1)
+    crit = DynamicLoss()
+    x, y = _batch(5)
+    for _ in range(2):                                     # registers forward (modes 0, 2, 5) and backward (modes 1, 3) shadows
+        m.zero_grad(set_to_none=True)
+        crit(m(x), y).backward()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.25).add_(0.01)                        # in-place: version counters move, storage stays
+        logits = m(x)                                      # one refresh launch covers every registered shadow
+    seen = set()
+    for (pid, mode, dt), ent in list(Fn._shadows.items()):
+        p = ent[0]()
+        if p is None or not any(p is q for q in m.parameters()):
+            continue
+        R, Cc = ent[3]
+        want = ops.prep_weight(mode, p, R, Cc, tuple(ent[2].shape), dt)
+        assert ent[1] == (p._version, p.data_ptr()) and torch.equal(ent[2], want), (mode, tuple(p.shape))
+        seen.add(mode)
+    assert seen >= {0, 1, 2, 3, 5}
+    # graph capture: the refresh is recorded, so a replay after an in-place weight change equals the eager forward after it
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s), torch.no_grad():
+        m(x)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            out = m(x)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, logits)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(0.9)
+    g.replay()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        eager = m(x)
+    assert torch.equal(out, eager) and not torch.equal(eager, logits)

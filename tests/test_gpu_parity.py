@@ -408,3 +408,54 @@ def test_calculate_metrics_batched_equals_per_image_and_oracle(pkg):
             fpr.append(O.metrics_real(pb[i].cpu().numpy(), pred[i].float().cpu().numpy(), gt[i].cpu().numpy())[3])
     assert abs(d3 - float(np.mean(dice))) < 1e-5 and abs(f3 - float(np.mean(fpr))) < 1e-4
     assert abs(sc3 - (float(np.mean(dice)) - 10 * float(np.mean(fpr)))) < 1e-3
+
+
+@pytest.mark.gpu
+def test_stage_u8_bit_exact_vs_reference_fixture_and_oracle():
+    """§8f.2: uint8 HWC -> /255 CHW float, flip, label > 127 (dataset/dataset.py:13-16, 49-63) on the device, bit-exact against
+    the reference's own transform (fixture) and the oracle on ragged widths (scalar kernel), no label, no flips, empty batch."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops
+    from oracle import msunet_oracle as O
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(GOLDEN, "staging.npz"))
+    img, lab = ops.stage_u8(torch.from_numpy(g["images"]).to(dev), torch.from_numpy(g["labels"]).to(dev),
+                            torch.from_numpy(g["flips"]).to(dev))
+    assert np.array_equal(img.cpu().numpy(), g["out_image"]) and np.array_equal(lab.cpu().numpy(), g["out_label"])
+    rng = np.random.default_rng(5)
+    for (B, H, W) in ((3, 7, 13), (2, 16, 512), (5, 33, 36), (1, 4, 1028), (2, 3, 4)):
+        im = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+        lb = rng.integers(0, 256, size=(B, H, W), dtype=np.uint8)
+        fl = rng.integers(0, 2, size=B).astype(np.uint8)
+        ri, rl = O.stage_batch(im, lb, fl)
+        a, b = ops.stage_u8(torch.from_numpy(im).to(dev), torch.from_numpy(lb).to(dev), torch.from_numpy(fl).to(dev))
+        assert np.array_equal(a.cpu().numpy(), ri) and np.array_equal(b.cpu().numpy(), rl), (B, H, W)
+        a, b = ops.stage_u8(torch.from_numpy(im).to(dev), None, torch.from_numpy(fl.astype(bool)).to(dev))
+        assert b is None and np.array_equal(a.cpu().numpy(), ri)
+        a, b = ops.stage_u8(torch.from_numpy(im).to(dev), torch.from_numpy(lb).to(dev))
+        r0, l0 = O.stage_batch(im, lb, np.zeros(B, np.uint8))
+        assert np.array_equal(a.cpu().numpy(), r0) and np.array_equal(b.cpu().numpy(), l0)
+    a, b = ops.stage_u8(torch.zeros(0, 8, 8, 3, dtype=torch.uint8, device=dev), torch.zeros(0, 8, 8, dtype=torch.uint8, device=dev))
+    assert a.shape == (0, 3, 8, 8) and b.shape == (0, 8, 8)
+    with pytest.raises(ValueError):
+        ops.stage_u8(torch.zeros(1, 3, 8, 8, dtype=torch.uint8, device=dev))
+    with pytest.raises(RuntimeError):
+        ops.stage_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
+
+
+@pytest.mark.gpu
+def test_cuda_prefetcher_uint8_staging_equals_host_transform():
+    from semantic_segmentation_of_stylegan2_artifacts_b200.data import CudaPrefetcher
+    from oracle import msunet_oracle as O
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    raw = [{"image": torch.from_numpy(rng.integers(0, 256, size=(4, 32, 32, 3), dtype=np.uint8)),
+            "label": torch.from_numpy(rng.integers(0, 256, size=(4, 32, 32), dtype=np.uint8)),
+            "flip": torch.from_numpy(rng.integers(0, 2, size=4).astype(bool)), "case_name": [f"c{i}"]} for i in range(4)]
+    n = 0
+    for b, r in zip(CudaPrefetcher(raw, dev, stage_uint8=True), raw):
+        ri, rl = O.stage_batch(r["image"].numpy(), r["label"].numpy(), r["flip"].numpy())
+        assert "flip" not in b and b["case_name"] == r["case_name"]
+        assert b["image"].dtype == torch.float32 and tuple(b["image"].shape) == (4, 3, 32, 32)
+        assert np.array_equal(b["image"].cpu().numpy(), ri) and np.array_equal(b["label"].cpu().numpy(), rl)
+        n += 1
+    assert n == 4

@@ -107,3 +107,12 @@ def test_metrics_match_reference(name):
             assert np.array_equal(np.array(cb), g[f"real{i}_cm_bin"])
             np.testing.assert_allclose(np.array(cs), g[f"real{i}_cm_soft"], rtol=2e-6)
             np.testing.assert_allclose([acc, fpr], g[f"real{i}_scalars"], rtol=1e-12)
+
+
+def test_staging_matches_reference_transform():
+    """oracle.stage_batch vs tensors returned by the reference's RandomGenerator (oracle/make_staging_golden.py): bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "staging.npz"))
+    img, lab = O.stage_batch(g["images"], g["labels"], g["flips"])
+    assert img.dtype == np.float32 and lab.dtype == np.float32
+    assert np.array_equal(img, g["out_image"]) and np.array_equal(lab, g["out_label"])
+    assert g["flips"].any() and not g["flips"].all()
