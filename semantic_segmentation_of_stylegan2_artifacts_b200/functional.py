@@ -178,12 +178,14 @@ def _shadow_plan(params, state: dict):
     return plan
 
 
-def refresh_shadows(params, state: dict) -> None:
+def refresh_shadows(params, state: dict, force: bool = False) -> None:
     """Re-derive every registered shadow of `params` in ONE launch (`msu_refresh_shadows`) if any master changed since the shadows
     were made — after an optimizer step that is all of them, which the per-tensor path would redo as ~230 small launches.  During
     CUDA-graph capture the refresh is always recorded (replays must see the current masters) and marks the entries it covered as
     fresh for this capture.  Shadows that are not registered yet (first forward) are made lazily by `shadow()` as before.
-    `state` is a caller-owned dict (one per model) holding the cached job table."""
+    `state` is a caller-owned dict (one per model) holding the cached job table.  `force` refreshes without consulting the
+    version counters: fused optimizers (`torch.optim.AdamW(fused=True)`, anything writing through raw pointers) update parameters
+    without bumping them, so a training forward never trusts them."""
     from . import _lib as L
     capturing = torch.cuda.is_current_stream_capturing()
     plan = state.get("plan")
@@ -195,7 +197,7 @@ def refresh_shadows(params, state: dict) -> None:
         plan = _shadow_plan(params, state)
     if plan["n_blocks"] == 0:
         return
-    if not capturing and all(e[1] == (p._version, p.data_ptr()) for e, p in plan["ents"]):
+    if not capturing and not force and all(e[1] == (p._version, p.data_ptr()) for e, p in plan["ents"]):
         return
     L.check(L.lib().msu_refresh_shadows(plan["table"].data_ptr(), plan["bj"].data_ptr(), plan["bt"].data_ptr(), plan["n_blocks"],
                                         L.stream_ptr()), "msu_refresh_shadows")

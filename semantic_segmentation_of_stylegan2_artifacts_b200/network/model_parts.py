@@ -376,7 +376,11 @@ class MSUNetSys(nn.Module):
             st = _SHADOW_STATE.get(self)
             if st is None:
                 st = _SHADOW_STATE[self] = {"params": list(self.parameters())}
-            Fn.refresh_shadows(st["params"], st)
+            # a training forward re-derives the bf16 weight shadows unconditionally (one launch): optimizers may update the
+            # masters without touching their version counters; the first forward after training does the same once
+            train = self.training and torch.is_grad_enabled()
+            Fn.refresh_shadows(st["params"], st, force=train or st.get("dirty", False))
+            st["dirty"] = train
         x, x_downsample = self.forward_features(x)
         x = self.forward_up_features(x, x_downsample)
         return self.up_x4(x)

@@ -90,22 +90,27 @@ def test_weight_shadows_follow_the_optimizer():
     import semantic_segmentation_of_stylegan2_artifacts_b200 as pkg
     from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
     from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW
-    ma, mb = _small_model(0), _small_model(0)
+    ma, mb, mc = _small_model(0), _small_model(0), _small_model(0)
     oa = FusedAdamW(ma.parameters(), lr=2e-3, weight_decay=0.01)
     ob = torch.optim.AdamW(mb.parameters(), lr=2e-3, weight_decay=0.01, foreach=False, fused=False)
+    oc = torch.optim.AdamW(mc.parameters(), lr=2e-3, weight_decay=0.01, fused=True)   # never bumps the version counters
     crit = DynamicLoss()
     x, y = _batch()
-    la, lb = [], []
+    la, lb, lc = [], [], []
     for _ in range(4):
-        for m, o, ls in ((ma, oa, la), (mb, ob, lb)):
+        for m, o, ls in ((ma, oa, la), (mb, ob, lb), (mc, oc, lc)):
             o.zero_grad(set_to_none=True)
             loss = crit(m(x), y)
             loss.backward()
             o.step()
-            ls.append(float(loss))
+            ls.append(float(loss.detach()))
     assert abs(la[0] - lb[0]) < 1e-6                       # identical first step
     assert la[3] < la[0] - 1e-3                            # the updates reach the forward pass (stale shadows would freeze the loss)
     assert all(abs(a - b) < 0.02 * abs(b) + 1e-3 for a, b in zip(la, lb)), (la, lb)
+    assert all(abs(c - b) < 0.02 * abs(b) + 1e-3 for c, b in zip(lc, lb)), (lc, lb)
+    mb.eval(); mc.eval()
+    with torch.no_grad():                                  # the first forward after training sees the last update too
+        assert (mb(x).float() - mc(x).float()).abs().max() < 0.05
     # the refresh is one launch: a forward right after an optimizer step launches no per-tensor msu_prep_weight kernels
     n0 = pkg.launch_count()
     with torch.no_grad():

@@ -8,7 +8,7 @@
   infer  : config 4 — MS-UNet T96 inference at 1024x1024, batch 8, eval mode + fused sigmoid/threshold/TP-FP-FN-TN
            counting (img/s), counts checked bit-exactly against the reference formulas on the same logits.
 
-Usage: python tools/microbench.py [attn|loss|infer|all] [--quick]
+Usage: python tools/microbench.py [attn|loss|stage|infer|all] [--quick]
 """
 import json
 import os
@@ -100,6 +100,17 @@ def loss_case(Bn, S):
             "frac_of_measured_hbm_peak": round(byts / t / 1e6 / PEAKS["hbm_gbs"], 4)}
 
 
+def stage_case(Bn, S):
+    """uint8 HWC batch -> fp32 CHW / 255 + flip + label > 127: 4 B read + 16 B written per pixel."""
+    img = torch.randint(0, 256, (Bn, S, S, 3), dtype=torch.uint8, device=dev)
+    lab = torch.randint(0, 256, (Bn, S, S), dtype=torch.uint8, device=dev)
+    flip = (torch.arange(Bn, device=dev) % 2).to(torch.uint8)
+    t = timed(lambda: ops.stage_u8(img, lab, flip))
+    byts = 20 * Bn * S * S
+    return {"bench": "stage_u8", "B": Bn, "S": S, "ms": round(t, 4), "GBps": round(byts / t / 1e6, 1),
+            "frac_of_measured_hbm_peak": round(byts / t / 1e6 / PEAKS["hbm_gbs"], 4)}
+
+
 def infer_case(Bn=8, S=1024, steps=5):
     torch.manual_seed(1234)
     m = MSUNetSys(img_size=S, drop_path_rate=0.1, **T96).to(dev).eval()
@@ -143,6 +154,9 @@ def main():
         for S in (224, 512, 1024):
             for Bn in ((1, 16, 64) if not quick else (16,)):
                 print(json.dumps(loss_case(Bn, S)), flush=True)
+    if what in ("stage", "all"):
+        for Bn, S in ((16, 512), (64, 512), (16, 1024)):
+            print(json.dumps(stage_case(Bn, S)), flush=True)
     if what in ("infer", "all"):
         print(json.dumps(infer_case()), flush=True)
 
