@@ -1147,6 +1147,10 @@ struct WcParams {
     int64_t slabs, slabs_per_split;
     int stages;
     int halo;                 // 1: one (WB+2)-pixel halo slab per dy, the three dx taps are row-shifted views of it
+    int c32;                  // halo only: operands staged as 32-channel chunks (64 B rows, 64B swizzle) instead of 64-channel boxes:
+                              // E = 96 is 3 chunks exactly, while a second 64-channel box is half out of range and made the TMA
+                              // unit fetch 1.5x the bytes from L2 (ncu: 7.4 GB of sectors for 4.9 GB of operands)
+    int coll;                 // 1: K step outermost, the taps of a slice share dZ through the A collector (MSU_WGRAD_COLL=0: off)
     float* ws;
     float* bws;               // bias-gradient partials [split][E] (column sums of dZ), or nullptr
 };
@@ -1160,9 +1164,11 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int split = blockIdx.x / p.n_groups;
     const int tap0 = grp * p.G;
     const int ntap = (9 - tap0) < p.G ? (9 - tap0) : p.G;
-    const int A_BYTES = p.boxes * BOX;
+    const int nch = p.E / 32;                                                  // c32: chunks per operand
+    const int ACH = p.WB * 64, XCH = ((p.WB + 2) * 64 + 511) / 512 * 512;      // c32: chunk bytes (512 B = swizzle period)
+    const int A_BYTES = p.c32 ? nch * ACH : p.boxes * BOX;
     const int XBOX = p.halo ? ((p.WB + 2) * 128 + 1023) / 1024 * 1024 : BOX;   // halo slab box, 1 KB aligned
-    const int B_BYTES = p.halo ? p.boxes * XBOX : p.G * p.boxes * BOX;
+    const int B_BYTES = p.c32 ? nch * XCH : (p.halo ? p.boxes * XBOX : p.G * p.boxes * BOX);
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
@@ -1172,7 +1178,8 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     float2* sComb = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [4 warps][2 boxes][32 pairs]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // conv bias gradient = column sums of dZ: added up from the dZ tiles by the epilogue warps while the MMAs run
-    const bool do_bias = (p.bws != nullptr) && (grp == p.n_groups - 1);   // the last tap group has the fewest taps
+    // the last tap group has the fewest taps; c32 (three groups, three chunks): every group sums its own chunk
+    const bool do_bias = (p.bws != nullptr) && (grp == p.n_groups - 1 || (p.c32 && nch == p.n_groups));
     const int64_t s0 = (int64_t)split * p.slabs_per_split;
     int64_t s1 = s0 + p.slabs_per_split;
     if (s1 > p.slabs) s1 = p.slabs;
@@ -1202,9 +1209,16 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 const int64_t row = slab / slabs_per_row;
                 const int y = (int)(row % p.H), b = (int)(row / p.H);
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], p.halo ? A_BYTES + p.boxes * (p.WB + 2) * 128 : A_BYTES + ntap * p.boxes * BOX);
                 uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
                 uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+                if (p.c32) {
+                    mbar_arrive_expect_tx(&full[stage], nch * (ACH + (p.WB + 2) * 64));
+                    for (int c = 0; c < nch; c++) tma_load_4d(a_dst + c * ACH, &tmZ, &full[stage], c * 32, x0, y, b);
+                    for (int c = 0; c < nch; c++) tma_load_4d(b_dst + c * XCH, &tmX, &full[stage], c * 32, x0 - 1, y + grp - 1, b);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
+                mbar_arrive_expect_tx(&full[stage], p.halo ? A_BYTES + p.boxes * (p.WB + 2) * 128 : A_BYTES + ntap * p.boxes * BOX);
                 for (int bx = 0; bx < p.boxes; bx++) tma_load_4d(a_dst + bx * BOX, &tmZ, &full[stage], bx * 64, x0, y, b);
                 if (p.halo) {   // group = dy; pixels x0-1 .. x0+WB of row y+dy-1 (zero fill outside the image)
                     for (int bx = 0; bx < p.boxes; bx++)
@@ -1225,26 +1239,44 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
             // descriptors built once, advanced through the 14-bit address field (the issuing thread is the critical
             // resource: ~21 instructions per MMA when they were rebuilt): +128 per 16-pixel K step, +tap_step per tap
             // (halo: tap t = dx is the slab shifted by t pixel rows = +128 B; the swizzle is address based)
-            const uint64_t ad0 = make_desc_mnmajor_sw128(smem_u32(sA), BOX);
-            const uint64_t bd0 = make_desc_mnmajor_sw128(smem_u32(sB), p.halo ? XBOX : BOX);
+            // c32: 64 B rows, so a 16-pixel K step is +1024 B and a one-pixel tap shift +64 B; M = 128 reads a fourth chunk of dZ
+            // (whatever follows in shared memory: it only reaches accumulator rows >= E, which nobody reads)
+            const uint64_t ad0 = p.c32 ? make_desc_mnmajor_sw64_lbo(smem_u32(sA), ACH) : make_desc_mnmajor_sw128(smem_u32(sA), BOX);
+            const uint64_t bd0 = p.c32 ? make_desc_mnmajor_sw64_lbo(smem_u32(sB), XCH)
+                                       : make_desc_mnmajor_sw128(smem_u32(sB), p.halo ? XBOX : BOX);
             const uint32_t a_step = (uint32_t)(A_BYTES >> 4), b_step = (uint32_t)(B_BYTES >> 4);
-            const uint32_t tap_step = p.halo ? (128 >> 4) : (uint32_t)((p.boxes * BOX) >> 4);
+            const uint32_t tap_step = p.c32 ? (64 >> 4) : (p.halo ? (128 >> 4) : (uint32_t)((p.boxes * BOX) >> 4));
+            const uint32_t kst = p.c32 ? 64 : 128;                                   // K step of 16 pixels, in 16 B units
             const int ksteps = p.WB / 16;
+            const bool coll_on = p.coll != 0;
             for (int kb = 0; kb < KB; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint64_t ad = ad0 + (uint64_t)(stage * a_step), bd = bd0 + (uint64_t)(stage * b_step);
                 const uint32_t acc0 = kb != 0;
+                if (ntap == 3 && ksteps == 4 && coll_on) {
+                    // K step outermost: the three taps' MMAs of one 16-pixel slice share their dZ tile through the A collector
+                    // (one shared-memory read instead of three: the loop is bound by shared-memory bandwidth, not by the tensor pipe)
+                    const uint64_t b1 = bd + (uint64_t)tap_step, b2 = bd + (uint64_t)(2 * tap_step);
+                    const uint32_t d1 = tmem_base + p.BN, d2 = tmem_base + 2 * p.BN;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t en = k == 0 ? acc0 : 1u;
+                        tc_mma_bf16_coll<TC_COLL_FILL>(tmem_base, ad + (uint64_t)(k * kst), bd + (uint64_t)(k * kst), idesc, en);
+                        tc_mma_bf16_coll<TC_COLL_USE>(d1, ad + (uint64_t)(k * kst), b1 + (uint64_t)(k * kst), idesc, en);
+                        tc_mma_bf16_coll<TC_COLL_LASTUSE>(d2, ad + (uint64_t)(k * kst), b2 + (uint64_t)(k * kst), idesc, en);
+                    }
+                } else
                 for (int t = 0; t < ntap; t++) {
                     const uint64_t bt = bd + (uint64_t)(t * tap_step);
                     const uint32_t d = tmem_base + t * p.BN;
                     if (ksteps == 4) {
                         tc_mma_bf16(d, ad, bt, idesc, acc0);
-                        tc_mma_bf16(d, ad + 128, bt + 128, idesc, 1);
-                        tc_mma_bf16(d, ad + 256, bt + 256, idesc, 1);
-                        tc_mma_bf16(d, ad + 384, bt + 384, idesc, 1);
+                        tc_mma_bf16(d, ad + kst, bt + kst, idesc, 1);
+                        tc_mma_bf16(d, ad + 2 * kst, bt + 2 * kst, idesc, 1);
+                        tc_mma_bf16(d, ad + 3 * kst, bt + 3 * kst, idesc, 1);
                     } else {
-                        for (int k = 0; k < ksteps; k++) tc_mma_bf16(d, ad + (uint64_t)(k * 128), bt + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+                        for (int k = 0; k < ksteps; k++) tc_mma_bf16(d, ad + (uint64_t)(k * kst), bt + (uint64_t)(k * kst), idesc, (kb | k) != 0);
                     }
                 }
                 tc_commit(&empty[stage]);
@@ -1254,7 +1286,40 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         }
     } else {
         const int quad = warp & 3;
-        if (do_bias) {
+        if (do_bias && p.c32) {
+            // Three dy groups, three 32-channel chunks: group g adds up chunk g, so every CTA carries a third of the column-sum
+            // work (the kernel ends with its slowest CTA; one group doing all of it cost +150 us).  64 B rows: a warp covers two
+            // pixels per load (half-warp = pixel parity, lane & 15 = channel pair of the chunk).  Fixed order => deterministic.
+            const int ew = warp - 2, tpw = p.WB / 4;
+            const int hp = lane >> 4, pr = lane & 15;
+            float2 acc = make_float2(0.f, 0.f);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&full[stage], phase);
+                const uint8_t* src = sA + (size_t)stage * A_BYTES + grp * ACH;
+#pragma unroll 4
+                for (int tt = 0; tt < tpw; tt += 2) {
+                    const int t = ew * tpw + tt + hp;
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(src + t * 64 + (((pr >> 2) ^ ((t >> 1) & 3)) << 4) + (pr & 3) * 4);
+                    acc.x += bf16lo_f(u);
+                    acc.y += bf16hi_f(u);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+            if (lane < 16) sComb[ew * 16 + lane] = acc;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (ew == 0 && lane < 16) {
+                float2 t = sComb[lane];
+                for (int w = 1; w < 4; w++) { const float2 u = sComb[w * 16 + lane]; t.x += u.x; t.y += u.y; }
+                const int ch = grp * 32 + lane * 2;
+                p.bws[(int64_t)split * p.E + ch] = t.x;
+                p.bws[(int64_t)split * p.E + ch + 1] = t.y;
+            }
+        } else if (do_bias) {
             const int ew = warp - 2, tpw = p.WB / 4;               // tokens of a slab per warp
             float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             int stage = 0; uint32_t phase = 0;
@@ -1338,11 +1403,16 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     // once the MMA issue loop was made cheap (MSU_WGRAD_HALO=0 restores the tap grouping)
     static const int halo_on = getenv("MSU_WGRAD_HALO") ? atoi(getenv("MSU_WGRAD_HALO")) : 1;
     p.halo = (halo_on && p.WB == 64 && 3 * p.BN <= TC_TMEM_COLS) ? 1 : 0;
+    static const int c32_on = getenv("MSU_WGRAD_C32") ? atoi(getenv("MSU_WGRAD_C32")) : 1;
+    p.c32 = (p.halo && c32_on && Ec == 96) ? 1 : 0;   // three chunks = three dy groups (the bias sums are split that way)
     if (p.halo) {   // taps grouped by dy: 3 accumulators per CTA, dZ read 3x but X read once per dy (1.8x less L2 traffic)
         p.G = 3;
         p.n_groups = 3;
         stage_bytes = p.boxes * BOX + p.boxes * (((p.WB + 2) * 128 + 1023) / 1024 * 1024);
+        if (p.c32) stage_bytes = (Ec / 32) * (p.WB * 64 + ((p.WB + 2) * 64 + 511) / 512 * 512);
     }
+    static const int coll_on = getenv("MSU_WGRAD_COLL") ? atoi(getenv("MSU_WGRAD_COLL")) : 1;
+    p.coll = coll_on;
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 6) p.stages = 6;
     static const int env_wstages = getenv("MSU_WGRAD_STAGES") ? atoi(getenv("MSU_WGRAD_STAGES")) : 0;
@@ -1364,16 +1434,17 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
     p.splits = splits;
     p.bws = want_bias ? ws + (int64_t)splits * I * J : nullptr;
     CUtensorMap tmZ, tmX;
+    static const int l2promo = getenv("MSU_WGRAD_L2PROMO") ? atoi(getenv("MSU_WGRAD_L2PROMO")) : (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)Ec, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Bn};
         cuuint64_t gstr[3] = {(cuuint64_t)Ec * 2, (cuuint64_t)W * Ec * 2, (cuuint64_t)H * W * Ec * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.WB, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)(p.c32 ? 32 : 64), (cuuint32_t)p.WB, 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         for (int k = 0; k < 2; k++) {
             box[1] = (cuuint32_t)((k == 1 && p.halo) ? p.WB + 2 : p.WB);
             if (get_encode()(k ? &tmX : &tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k ? B->ptr : A->ptr), gdim, gstr,
-                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, p.c32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                             (CUtensorMapL2promotion)l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return 1;
         }
     }

@@ -71,6 +71,23 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
+// The same with an A-operand collector tag: consecutive MMAs that share their A tile (several accumulators fed by one A slice)
+// read it from shared memory once — FILL on the first, USE in between, LASTUSE on the last.  Measured (tools/mma_rate_bench.cu):
+// M=128, N=96 goes from 56 clk (= 7 KB of operands / 128 B/clk of shared-memory bandwidth) to 48 clk (the tensor-pipe rate).
+// The tag must be a compile-time choice: a predicated-off tcgen05.mma still costs the issuing thread its slot.
+enum { TC_COLL_NONE = 0, TC_COLL_FILL = 1, TC_COLL_USE = 2, TC_COLL_LASTUSE = 3 };
+template <int COLL>
+__device__ __forceinline__ void tc_mma_bf16_coll(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#define MSU_TC_MMA_ASM(QUAL)                                                                                                        \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                                \
+                 "tcgen05.mma.cta_group::1.kind::f16" QUAL " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),         \
+                 "r"(idesc), "r"(accumulate) : "memory")
+    if constexpr (COLL == TC_COLL_FILL) MSU_TC_MMA_ASM(".collector::a::fill");
+    else if constexpr (COLL == TC_COLL_USE) MSU_TC_MMA_ASM(".collector::a::use");
+    else if constexpr (COLL == TC_COLL_LASTUSE) MSU_TC_MMA_ASM(".collector::a::lastuse");
+    else MSU_TC_MMA_ASM("");
+#undef MSU_TC_MMA_ASM
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -127,6 +144,17 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr, uint
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// MN-major, 64B-swizzled descriptor: 32-channel chunks (64 B rows) `lbo` bytes apart, 8-token groups 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw64_lbo(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 

@@ -49,6 +49,62 @@ __global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int iters
     }
 }
 
+// A-operand collector reuse: groups of 3 MMAs share one A tile (different B tiles and accumulators), as the conv weight-gradient
+// kernel issues them (A = dZ slice, B = X slab shifted per tap).  coll=1 tags them fill / use / lastuse.
+#define MMA_COLL(QUAL)                                                                                                       \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                         \
+                 "tcgen05.mma.cta_group::1.kind::f16" QUAL " [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), \
+                 "r"(1u) : "memory")
+template <int coll, int same_d>
+__global__ void __launch_bounds__(128, 1) k3(int N, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+        const uint64_t ad0 = make_desc_mnmajor_sw128(smem_u32(smem), 8192), bd0 = make_desc_mnmajor_sw128(smem_u32(smem + 48 * 1024), 8192);
+        long long t0 = clock64();
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const uint64_t ad = ad0 + (uint64_t)(ks * 128);
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const uint64_t bd = bd0 + (uint64_t)(ks * 128 + t * 8);
+                    const uint32_t d = same_d ? tmem : tmem + t * N;
+                    if (!coll) MMA_COLL("");
+                    else if (t == 0) MMA_COLL(".collector::a::fill");
+                    else if (t == 1) MMA_COLL(".collector::a::use");
+                    else MMA_COLL(".collector::a::lastuse");
+                }
+            }
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
 int main() {
     long long* d;
     cudaMalloc(&d, 8);
@@ -64,6 +120,20 @@ int main() {
             const double clk = (double)h / (iters * 4);
             printf("N=%3d A %s B %s : %7.1f clk/MMA  (ideal %5.1f)  %s\n", N, a_mn ? "MN-major" : "K-major ", b_mn ? "MN-major" : "K-major ", clk,
                    128.0 * N * 16 * 2 / 8192, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+    }
+    for (int N : {32, 96, 128, 160}) {
+        for (int v = 0; v < 4; v++) {
+            auto kern = v == 0 ? k3<0, 0> : v == 1 ? k3<1, 0> : v == 2 ? k3<0, 1> : k3<1, 1>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            kern<<<148, 128, 100 * 1024>>>(N, iters, d);
+            long long h = 0;
+            cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaGetLastError();
+            printf("3 MMAs per A tile, N=%3d, %s, collector %s : %7.1f clk/MMA  (MMA ideal %5.1f, smem ideal %5.1f / %5.1f with reuse)  %s\n", N,
+                   (v & 2) ? "one accumulator   " : "three accumulators", (v & 1) ? "fill/use/lastuse" : "default         ",
+                   (double)h / (iters * 12), 128.0 * N * 16 * 2 / 8192, (4096.0 + N * 32) / 128, (4096.0 / 3 + N * 32) / 128,
+                   e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
     }
     return 0;
