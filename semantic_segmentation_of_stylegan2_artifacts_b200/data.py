@@ -7,7 +7,8 @@ step i runs; `next()` hands out device tensors after making the compute stream w
 
 With `stage_uint8=True` the loader yields the RAW arrays of dataset/dataset.py:41-42 — {'image': uint8 [B,H,W,3], 'label': uint8
 [B,H,W]} and optionally 'flip': bool [B] — and the `/255`, CHW transpose, flip and `>127` of dataset.py:13-16, 49-63 run on the
-device (`ops.stage_u8`, one launch on the copy stream): 4 bytes per pixel cross PCIe instead of 16, and the batch that comes out is
+device (`ops.stage_u8`, one launch on the compute stream when the batch is handed out): 4 bytes per pixel cross PCIe instead of 16,
+and the batch that comes out is
 bit-identical to what the reference's transform would have produced on the host."""
 from __future__ import annotations
 
@@ -60,6 +61,8 @@ class CudaPrefetcher:
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
             _record(batch, cur)               # memory allocated on the copy stream is used on the compute stream
+            if self.stage_uint8:              # 15 us on the compute stream: its outputs live in that stream's allocator pool
+                batch = self._stage_u8(batch)
             nxt = self._stage(it)             # start the next copy before the caller launches this step
             yield batch
 
@@ -71,8 +74,6 @@ class CudaPrefetcher:
         keep: list = []
         with torch.cuda.stream(self.stream):
             batch = _to_device(host, self.device, keep)
-            if self.stage_uint8:
-                batch = self._stage_u8(batch)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return batch, ev, keep
