@@ -159,6 +159,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        # stdout carries exactly one JSON line: NCCL's own log lines (a version banner when NCCL_DEBUG is set) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     W = max(3, args.warmup)
     B, S = args.batch, args.img
