@@ -102,7 +102,7 @@ def cpu_reference_step_factory(img, batch):
     return step, torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -117,7 +117,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     v = sample_b / dt
     sample = f"T96 {IMG}x{IMG} fwd+DynamicLoss+bwd on {sample_b} image/step, {steps} timed steps (bounded sample of batch {PER_GPU_BATCH})"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -142,8 +142,17 @@ def main():
     ap.add_argument("--drop-path", type=float, default=0.1)
     ap.add_argument("--attn-drop", type=float, default=0.0, help="attention dropout (config.yaml of the reference: 0.05)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else written to file descriptor 1 during the run (NCCL's version banner,
+    # library chatter) is sent to stderr, and the result line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -353,7 +362,7 @@ def main():
                "sample": f"T96 {S}x{S} fwd+DynamicLoss+bwd on 1 image/step, {n} timed steps after 1 warm-up"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
