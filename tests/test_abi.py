@@ -92,6 +92,14 @@ def test_errors_and_no_cpu_fallback(built):
         DynamicLoss()(torch.zeros(2, 1, 8, 8), torch.zeros(3, 8, 8))   # loss/DynamicLoss.py:93-94
     with pytest.raises(RuntimeError):
         DynamicLoss()(torch.zeros(2, 1, 8, 8), torch.zeros(2, 8, 8))
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import ops
+    from semantic_segmentation_of_stylegan2_artifacts_b200.data import CudaPrefetcher
+    with pytest.raises(RuntimeError):
+        ops.stage_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))          # input staging: CUDA only as well
+    with pytest.raises(ValueError):
+        ops.stage_u8(torch.zeros(1, 8, 8, 3))                             # dataset/dataset.py:41 hands over uint8
+    with pytest.raises(RuntimeError):
+        CudaPrefetcher([], "cpu")
     m.freeze_encoder(True)
     assert not any(p.requires_grad for p in m.ms_unet.layers.parameters())
     m.unfreeze_encoder(0)
