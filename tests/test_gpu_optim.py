@@ -166,3 +166,37 @@ def test_refresh_shadows_bit_exact_vs_per_tensor_prep_and_under_graph_replay():
     with torch.no_grad():
         eager = m(x)
     assert torch.equal(out, eager) and not torch.equal(eager, logits)
+
+
+def test_graphed_step_matches_eager_training():
+    """graphs.GraphedStep (fwd + DynamicLoss + bwd replayed from one CUDA graph, optimizer eager) follows the eager loop: same
+    losses step by step, gradients in p.grad, zero_grad(set_to_none=True) between steps is harmless, shape changes are refused."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.graphs import GraphedStep
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW
+    ma, mb = _small_model(2), _small_model(2)
+    oa = FusedAdamW(ma.parameters(), lr=2e-3, weight_decay=0.01)
+    ob = FusedAdamW(mb.parameters(), lr=2e-3, weight_decay=0.01)
+    crit = DynamicLoss()
+    batches = [_batch(10 + i) for i in range(4)]
+    sd0 = {k: v.clone() for k, v in ma.state_dict().items()}
+    step = GraphedStep(ma, crit, *batches[0], warmup=2)
+    ma.load_state_dict(sd0)                                # the warm-up ran no optimizer, but be explicit about the start point
+    la, lb = [], []
+    for x, y in batches:
+        la.append(float(step(x, y)))
+        has_a = [p.grad is not None for p in ma.parameters()]
+        oa.step()
+        oa.zero_grad(set_to_none=True)
+        ob.zero_grad(set_to_none=True)
+        loss = crit(mb(x), y)
+        loss.backward()
+        assert has_a == [p.grad is not None for p in mb.parameters()] and sum(has_a) > 100   # (dead decoder branches have none)
+        ob.step()
+        lb.append(float(loss.detach()))
+    assert abs(la[0] - lb[0]) < 1e-6 and la[-1] != la[0]
+    assert all(abs(a - b) < 0.02 * abs(b) + 1e-3 for a, b in zip(la, lb)), (la, lb)
+    with pytest.raises(ValueError):
+        step(batches[0][0][:1], batches[0][1][:1])
+    with pytest.raises(RuntimeError):
+        GraphedStep(ma, crit, batches[0][0].cpu(), batches[0][1].cpu())
