@@ -12,6 +12,7 @@ from bench import T96, synth_batch  # noqa: E402
 import semantic_segmentation_of_stylegan2_artifacts_b200 as pkg  # noqa: E402
 from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss  # noqa: E402
 from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys  # noqa: E402
+from semantic_segmentation_of_stylegan2_artifacts_b200.graphs import GraphedStep  # noqa: E402
 from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -37,27 +38,16 @@ for name, mk in (("msu FusedAdamW", lambda ps: FusedAdamW(ps, lr=1e-4, weight_de
     for _ in range(3):
         it()
     torch.cuda.synchronize()
-    for mode in ("eager", "graph + eager optimizer"):
+    for mode in ("eager", "GraphedStep + optimizer"):
         if mode != "eager":
-            params = list(m.parameters())
-
-            def fb():
-                for p in params:
-                    p.grad = None
-                l = crit(m(x), y)
-                l.backward()
-                return l
-
             loss = None                       # drop the last eager autograd graph (its AccumulateGrad nodes pin the legacy stream)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                gl = fb()
+            gstep = GraphedStep(m, crit, x, y, warmup=1)        # the public helper: fwd + loss + bwd in one CUDA graph
 
             def it():
-                g.replay()
+                l = gstep(x, y)
                 if opt is not None:
                     opt.step()
-                return gl
+                return l
 
             for _ in range(2):
                 it()
