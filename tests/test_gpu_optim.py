@@ -122,10 +122,12 @@ def test_weight_shadows_follow_the_optimizer():
     assert n_after_step == (pkg.launch_count() - n0) + 1
 
 
-def test_refresh_shadows_bit_exact_vs_per_tensor_prep_and_under_graph_replay():
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_refresh_shadows_bit_exact_vs_per_tensor_prep_and_under_graph_replay(prec):
     from semantic_segmentation_of_stylegan2_artifacts_b200 import functional as Fn, ops
     from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
     m = _small_model(1)
+    m.set_precision(prec)
     crit = DynamicLoss()
     x, y = _batch(5)
     for _ in range(2):                                     # registers forward (modes 0, 2, 5) and backward (modes 1, 3) shadows
@@ -144,7 +146,7 @@ def test_refresh_shadows_bit_exact_vs_per_tensor_prep_and_under_graph_replay():
         want = ops.prep_weight(mode, p, R, Cc, tuple(ent[2].shape), dt)
         assert ent[1] == (p._version, p.data_ptr()) and torch.equal(ent[2], want), (mode, tuple(p.shape))
         seen.add(mode)
-    assert seen >= {0, 1, 2, 3, 5}
+    assert seen >= ({0, 1, 2, 3, 5} if prec == "bf16" else {2, 3, 5})      # fp32 mode reads the linear weights directly
     # graph capture: the refresh is recorded, so a replay after an in-place weight change equals the eager forward after it
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
