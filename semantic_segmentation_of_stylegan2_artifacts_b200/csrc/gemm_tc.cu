@@ -1150,6 +1150,9 @@ struct WcParams {
     int c32;                  // halo only: operands staged as 32-channel chunks (64 B rows, 64B swizzle) instead of 64-channel boxes:
                               // E = 96 is 3 chunks exactly, while a second 64-channel box is half out of range and made the TMA
                               // unit fetch 1.5x the bytes from L2 (ncu: 7.4 GB of sectors for 4.9 GB of operands)
+    int onebox;               // c32 only: the three chunks of an operand arrive as ONE 5-D TMA box (chunk = outermost box dimension).
+                              // The TMA unit serves a box of <= 8 KB in ~222 clk whatever its size (tools/tma_load_bench.cu), so six
+                              // 4 KB boxes per K step (1330 clk) were the bound of this kernel, not bytes.
     int coll;                 // 1: K step outermost, the taps of a slice share dZ through the A collector (MSU_WGRAD_COLL=0: off)
     float* ws;
     float* bws;               // bias-gradient partials [split][E] (column sums of dZ), or nullptr
@@ -1165,10 +1168,11 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int tap0 = grp * p.G;
     const int ntap = (9 - tap0) < p.G ? (9 - tap0) : p.G;
     const int nch = p.E / 32;                                                  // c32: chunks per operand
-    const int ACH = p.WB * 64, XCH = ((p.WB + 2) * 64 + 511) / 512 * 512;      // c32: chunk bytes (512 B = swizzle period)
+    const int ACH = p.WB * 64;                                                 // c32: chunk bytes (512 B = swizzle period)
+    const int XCH = p.onebox ? (p.WB + 2) * 64 : ((p.WB + 2) * 64 + 511) / 512 * 512;
     const int A_BYTES = p.c32 ? nch * ACH : p.boxes * BOX;
     const int XBOX = p.halo ? ((p.WB + 2) * 128 + 1023) / 1024 * 1024 : BOX;   // halo slab box, 1 KB aligned
-    const int B_BYTES = p.c32 ? nch * XCH : (p.halo ? p.boxes * XBOX : p.G * p.boxes * BOX);
+    const int B_BYTES = p.c32 ? (nch * XCH + 511) / 512 * 512 : (p.halo ? p.boxes * XBOX : p.G * p.boxes * BOX);
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_BYTES);
@@ -1213,8 +1217,13 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
                 if (p.c32) {
                     mbar_arrive_expect_tx(&full[stage], nch * (ACH + (p.WB + 2) * 64));
-                    for (int c = 0; c < nch; c++) tma_load_4d(a_dst + c * ACH, &tmZ, &full[stage], c * 32, x0, y, b);
-                    for (int c = 0; c < nch; c++) tma_load_4d(b_dst + c * XCH, &tmX, &full[stage], c * 32, x0 - 1, y + grp - 1, b);
+                    if (p.onebox) {
+                        tma_load_5d(a_dst, &tmZ, &full[stage], 0, x0, y, b, 0);
+                        tma_load_5d(b_dst, &tmX, &full[stage], 0, x0 - 1, y + grp - 1, b, 0);
+                    } else {
+                        for (int c = 0; c < nch; c++) tma_load_4d(a_dst + c * ACH, &tmZ, &full[stage], c * 32, x0, y, b);
+                        for (int c = 0; c < nch; c++) tma_load_4d(b_dst + c * XCH, &tmX, &full[stage], c * 32, x0 - 1, y + grp - 1, b);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     continue;
                 }
@@ -1409,7 +1418,10 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
         p.G = 3;
         p.n_groups = 3;
         stage_bytes = p.boxes * BOX + p.boxes * (((p.WB + 2) * 128 + 1023) / 1024 * 1024);
+        static const int onebox_on = getenv("MSU_WGRAD_1BOX") ? atoi(getenv("MSU_WGRAD_1BOX")) : 1;
+        p.onebox = (p.c32 && onebox_on) ? 1 : 0;
         if (p.c32) stage_bytes = (Ec / 32) * (p.WB * 64 + ((p.WB + 2) * 64 + 511) / 512 * 512);
+        if (p.onebox) stage_bytes = (Ec / 32) * p.WB * 64 + ((Ec / 32) * (p.WB + 2) * 64 + 511) / 512 * 512;
     }
     static const int coll_on = getenv("MSU_WGRAD_COLL") ? atoi(getenv("MSU_WGRAD_COLL")) : 1;
     p.coll = coll_on;
@@ -1440,7 +1452,19 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
         cuuint64_t gstr[3] = {(cuuint64_t)Ec * 2, (cuuint64_t)W * Ec * 2, (cuuint64_t)H * W * Ec * 2};
         cuuint32_t box[4] = {(cuuint32_t)(p.c32 ? 32 : 64), (cuuint32_t)p.WB, 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        for (int k = 0; k < 2; k++) {
+        if (p.onebox) {   // 5-D view: the 32-channel chunk index is the outermost dimension (64 B apart in memory)
+            cuuint64_t gdim5[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Bn, (cuuint64_t)(Ec / 32)};
+            cuuint64_t gstr5[4] = {(cuuint64_t)Ec * 2, (cuuint64_t)W * Ec * 2, (cuuint64_t)H * W * Ec * 2, 64};
+            cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+            for (int k = 0; k < 2 && p.onebox; k++) {
+                cuuint32_t box5[5] = {32, (cuuint32_t)(k ? p.WB + 2 : p.WB), 1, 1, (cuuint32_t)(Ec / 32)};
+                if (get_encode()(k ? &tmX : &tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(k ? B->ptr : A->ptr), gdim5, gstr5,
+                                 box5, estr5, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 (CUtensorMapL2promotion)l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return 1;
+            }
+        }
+        for (int k = 0; k < 2 && !p.onebox; k++) {
             box[1] = (cuuint32_t)((k == 1 && p.halo) ? p.WB + 2 : p.WB);
             if (get_encode()(k ? &tmX : &tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k ? B->ptr : A->ptr), gdim, gstr,
                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, p.c32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,

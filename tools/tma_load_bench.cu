@@ -79,6 +79,13 @@ int main() {
         {1536, 128, 148, 8, 0, 16384, "C=1536 box 128 rows, L2 resident"},
         {1536, 64, 148, 16, 0, 16384, "C=1536 box 64 rows, L2 resident, depth 16"},
         {1536, 64, 148, 4, 0, 16384, "C=1536 box 64 rows, L2 resident, depth 4"},
+        {1536, 256, 148, 4, 0, 16384, "C=1536 box 256 rows, L2 resident, depth 4"},
+        {1536, 128, 148, 4, 0, 16384, "C=1536 box 128 rows, L2 resident, depth 4"},
+        {1536, 32, 148, 8, 0, 16384, "C=1536 box 32 rows, L2 resident"},
+        {1536, 16, 148, 8, 0, 16384, "C=1536 box 16 rows, L2 resident"},
+        {96, 128, 148, 8, 0, 131072, "C=96  box 128 rows, 25 MB (L2 resident)"},
+        {96, 256, 148, 4, 0, 131072, "C=96  box 256 rows, 25 MB (L2 resident), depth 4"},
+        {96, 32, 148, 8, 0, 131072, "C=96  box 32 rows, 25 MB (L2 resident)"},
     };
     for (const Cfg& c : cfgs) {
         CUtensorMap tm = make(buf, c.rows, c.C, c.box_rows);
