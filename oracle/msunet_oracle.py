@@ -481,3 +481,27 @@ def stage_batch(images_u8: np.ndarray, labels_u8: np.ndarray, flips: np.ndarray)
         imgs.append(np.transpose(im.astype(np.float32) / 255.0, (2, 0, 1)))
         labs.append((lb > 127).astype(np.uint8).astype(np.float32))
     return np.stack(imgs), np.stack(labs)
+
+
+# ----------------------------------------------------------------------------------------------
+# Pretrained-encoder interchange: synthetic SegFace / torchvision-style checkpoints
+# ----------------------------------------------------------------------------------------------
+def encoder_checkpoint(state_dict, root: str):
+    """A checkpoint in the naming network/MSUNet.py:83-146 (SegFace, root 'backbone.0.') and :167-227 (ImageNet, root 'features.')
+    expect, covering every encoder entry of `state_dict` (patch_embed.*, layers.*): stage L blocks live under `{2L+1}.{i}`, its
+    downsample under `{2L+2}`, the patch embedding under `0.0` / `0.2`.  Entry number n is filled with the value n + 1, so a loaded
+    model tells which checkpoint tensor ended up where.  Returns (checkpoint dict, {model key: checkpoint key})."""
+    ckpt, where = {}, {}
+    for k, v in state_dict.items():
+        parts = k.split(".")
+        if parts[0] == "patch_embed":
+            nk = root + {"proj": "0.0", "norm": "0.2"}[parts[1]] + "." + ".".join(parts[2:])
+        elif parts[0] == "layers" and parts[2] == "blocks":
+            nk = root + f"{2 * int(parts[1]) + 1}.{parts[3]}." + ".".join(parts[4:])
+        elif parts[0] == "layers" and parts[2] == "downsample":
+            nk = root + f"{2 * int(parts[1]) + 2}." + ".".join(parts[3:])
+        else:
+            continue
+        ckpt[nk] = torch.full(tuple(v.shape), float(len(ckpt) + 1), dtype=v.dtype)
+        where[k] = nk
+    return ckpt, where

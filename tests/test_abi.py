@@ -149,3 +149,63 @@ def test_checkpoint_roundtrip_legacy_format(built, tmp_path):
         assert not missing.missing_keys and not missing.unexpected_keys
         assert list(m2.state_dict().keys()) == list(sd.keys())
         assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))
+
+
+@pytest.mark.parametrize("what,root,wrap", [("segface", "backbone.0.", "state_dict_backbone"), ("imagenet", "features.", None)])
+def test_pretrained_encoder_interchange_matches_reference(built, tmp_path, what, root, wrap):
+    """load_segface_weight / load_IMAGENET1K_weight (network/MSUNet.py:63-240) put every checkpoint tensor where the
+    reference's loaders put it (fixture recorded by running them: oracle/make_remap_golden.py), leave the decoder alone, skip the
+    SegFace head, and fail like the reference on unknown keys, mismatching shapes and a missing wrapper key."""
+    import json
+    import logging
+    from types import SimpleNamespace as NS
+    from oracle import msunet_oracle as O
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.MSUNet import MSUNet
+    g = json.load(open(os.path.join(GOLDEN, "encoder_remap.json")))
+    path = str(tmp_path / (what + ".pth"))
+
+    def cfg():
+        return NS(MODEL=NS(SWIN=NS(PATCH_SIZE=4, IN_CHANS=3, EMBED_DIM=g["embed_dim"], DEPTHS=g["depths"], NUM_HEADS=g["num_heads"],
+                                   WINDOW_SIZE=7, MLP_RATIO=4.0, QKV_BIAS=True, APE=False, PATCH_NORM=True),
+                           DROP_RATE=0.0, DROP_PATH_RATE=0.1, ATTN_DROP_RATE=0.0, PRETRAIN_SEGFACE=path, PRETRAIN_IMAGENET1K=path),
+                  TRAIN=NS(USE_CHECKPOINT=False))
+
+    def fresh():
+        m = MSUNet(cfg(), img_size=g["img_size"], num_classes=1)
+        with torch.no_grad():
+            for v in m.ms_unet.state_dict().values():
+                v.fill_(-1)
+        return m
+
+    def load(m):
+        (m.load_segface_weight if what == "segface" else m.load_IMAGENET1K_weight)(cfg(), logging)
+
+    m = fresh()
+    ckpt, where = O.encoder_checkpoint(m.ms_unet.state_dict(), root)
+    extra = "backbone.1.classifier.weight" if what == "segface" else "head.weight"       # SegFace head / classifier: ignored
+    ckpt[extra] = torch.zeros(3)
+    by_id = {int(v.flatten()[0]): k for k, v in ckpt.items() if k.startswith(root)}
+    torch.save({wrap: ckpt} if wrap else ckpt, path)
+    load(m)
+    got = {k: (by_id[int(v.flatten()[0])] if float(v.flatten()[0]) > 0 else None) for k, v in m.ms_unet.state_dict().items()}
+    assert got == g[what]
+    assert sum(v is not None for v in got.values()) == len(where) and all(got[k] == nk for k, nk in where.items())
+    # error behaviour of the reference
+    bad = dict(ckpt)
+    bad[root + "9.0.norm1.weight"] = torch.zeros(3)                                        # no such stage
+    torch.save({wrap: bad} if wrap else bad, path)
+    with pytest.raises(ValueError):
+        load(fresh())
+    bad = dict(ckpt)
+    k0 = next(k for k in bad if k.endswith("qkv.weight"))
+    bad[k0] = torch.zeros(5, 5)
+    torch.save({wrap: bad} if wrap else bad, path)
+    with pytest.raises(ValueError):
+        load(fresh())
+    if wrap:
+        torch.save(ckpt, path)                                                             # wrapper key missing
+        with pytest.raises(KeyError):
+            load(fresh())
+    torch.save({wrap: {"other.weight": torch.zeros(1)}} if wrap else {"other.weight": torch.zeros(1)}, path)
+    with pytest.raises(ValueError):                                                        # "No new keys from backbone!!"
+        load(fresh())
