@@ -36,6 +36,9 @@ struct TcParams {
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
     int stages;               // operand pipeline depth
+    int box2;                 // mode 4, MSU_CONV_2BOX=1: the two halo rows arrive as one TMA box and the three weight tiles as one 3-D
+                              // box (2 boxes per K block instead of 5).  Parity-tested, but measured the same 687 us: with the box
+                              // rate out of the way the kernel sits on its shared-memory bandwidth bound, so it stays off
     int epi_tma;              // 1: per-warp swizzled slabs + TMA stores (Cpre out / R or H in through TMA too); depth-to-space maps
                               //    ride on a 5-D tensor map of the output (the TMA unit does the scatter)
     int epi_bytes;            // shared memory per epilogue warp
@@ -192,6 +195,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int dyi = kb / p.cblocks, c0 = (kb % p.cblocks) * 32;
                         const int bb = p.BN * 64;
                         mbar_arrive_expect_tx(&full[stage], 2 * 130 * 64 + 3 * bb);
+                        if (p.box2) {
+                            tma_load_4d(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);            // rows y+dy-1, y+dy
+                            tma_load_3d(b_dst, &tmB, &full[stage], dyi * 3 * p.C + c0, nt * p.BN, 0);        // taps dx = 0, 1, 2
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         tma_load_4d(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
                         tma_load_4d(a_dst + TC_HALO32_BYTES, &tmA, &full[stage], c0, cx - 1, cy + dyi, cb);
                         for (int dx = 0; dx < 3; dx++)
@@ -253,10 +262,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // follows the address bits), second image row = +TC_HALO32_BYTES, weight tile of tap dx = +BN*64 B
                         const uint64_t ad = make_desc_kmajor_sw64_g(a_addr), bd = make_desc_kmajor_sw64_g(b_addr);
                         const uint32_t bstep = (uint32_t)(p.BN * 4);
+                        const uint32_t rstep = p.box2 ? (130 * 64) >> 4 : TC_HALO32_BYTES >> 4;   // one box: the rows are contiguous
                         const uint32_t acc0 = kb != 0;
 #pragma unroll
                         for (int r = 0; r < 2; r++) {
-                            const uint64_t ar = ad + (uint64_t)(r * (TC_HALO32_BYTES >> 4));
+                            const uint64_t ar = ad + (uint64_t)(r * rstep);
                             const uint32_t d = d_tmem + r * 128;
                             tc_mma_bf16(d, ar, bd, idesc, acc0);
                             tc_mma_bf16(d, ar + 2, bd + 2, idesc, 1);
@@ -772,7 +782,9 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             p.kb1 = 3 * p.cblocks;
             cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bn};
             cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-            cuuint32_t box[4] = {32, 130, 1, 1};
+            static const int box2_on = getenv("MSU_CONV_2BOX") ? atoi(getenv("MSU_CONV_2BOX")) : 0;
+            p.box2 = box2_on;
+            cuuint32_t box[4] = {32, 130, (cuuint32_t)(p.box2 ? 2 : 1), 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             if (get_encode()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(A->ptr), gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -801,7 +813,16 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             tmA2 = tmA;
         }
     }
-    if (p.mode == 4) {   // weight tiles [BN rows, 32 k] with the 64B swizzle of the halo rows
+    if (p.mode == 4 && p.box2) {   // the three dx tiles of (dy, channel block) as one box: third dimension = tap, C columns apart
+        cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
+        cuuint64_t gstr[2] = {(cuuint64_t)B->ld * 2, (cuuint64_t)p.C * 2};
+        cuuint32_t box[3] = {32, (cuuint32_t)p.BN, 3};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (get_encode()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(B->ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    } else if (p.mode == 4) {   // weight tiles [BN rows, 32 k] with the 64B swizzle of the halo rows
         cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
         cuuint64_t gstr[1] = {(cuuint64_t)B->ld * 2};
         cuuint32_t box[2] = {32, (cuuint32_t)p.BN};
