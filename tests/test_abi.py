@@ -209,3 +209,25 @@ def test_pretrained_encoder_interchange_matches_reference(built, tmp_path, what,
     torch.save({wrap: {"other.weight": torch.zeros(1)}} if wrap else {"other.weight": torch.zeros(1)}, path)
     with pytest.raises(ValueError):                                                        # "No new keys from backbone!!"
         load(fresh())
+
+
+def test_host_helpers_refuse_cpu(built):
+    """optim.FusedAdamW and graphs.GraphedStep are CUDA-only like the hot path itself."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.graphs import GraphedStep
+    from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW, patch_torch_adamw
+    p = torch.zeros(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        FusedAdamW([p]).step()
+    with pytest.raises(NotImplementedError):
+        FusedAdamW([p], amsgrad=True)
+    with pytest.raises(ValueError):
+        FusedAdamW([p], lr=-1.0)
+    with pytest.raises(RuntimeError):
+        GraphedStep(torch.nn.Linear(2, 2), lambda a, b: a.sum(), torch.zeros(1, 2), torch.zeros(1))
+    keep = torch.optim.AdamW
+    try:
+        patch_torch_adamw()
+        assert torch.optim.AdamW is FusedAdamW
+    finally:
+        torch.optim.AdamW = keep
