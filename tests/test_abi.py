@@ -231,3 +231,21 @@ def test_host_helpers_refuse_cpu(built):
         assert torch.optim.AdamW is FusedAdamW
     finally:
         torch.optim.AdamW = keep
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): exactly one stdout line, the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    ours = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
+    assert (d["metric"], d["unit"]) == (ours["metric"], ours["unit"])
