@@ -116,3 +116,27 @@ def test_staging_matches_reference_transform():
     assert img.dtype == np.float32 and lab.dtype == np.float32
     assert np.array_equal(img, g["out_image"]) and np.array_equal(lab, g["out_label"])
     assert g["flips"].any() and not g["flips"].all()
+
+
+def test_attention_dropout_mask_restatement():
+    """oracle.attn_drop_keep (the counter-hash mask the CUDA kernels regenerate in forward and backward): integer hash vs plain
+    Python arithmetic, keep rate, determinism, seed sensitivity, p = 0."""
+    def lowbias32(x):
+        x ^= x >> 16; x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x ^= x >> 15; x = (x * 0x846CA68B) & 0xFFFFFFFF
+        return x ^ (x >> 16)
+    xs = [0, 1, 2, 0xFFFFFFFF, 0x12345678, 0x9E3779B1]
+    assert [int(v) for v in O._lowbias32(np.array(xs, dtype=np.uint64))] == [lowbias32(x) for x in xs]
+    p, s0, s1 = 0.05, 123456789, 987654321
+    k = O.attn_drop_keep(6, 3, p, s0, s1)
+    assert k.dtype == torch.bool and tuple(k.shape) == (6, 3, 49, 49)
+    thr = int(p * 65536.0 + 0.5)
+    for (w, h, i, j) in ((0, 0, 0, 0), (5, 2, 48, 48), (3, 1, 17, 30), (2, 0, 9, 11)):      # element by element, from the definition
+        rowkey = (w * 3 + h) * 49 + i
+        x = ((((rowkey << 5) & 0xFFFFFFFF) + (j >> 1) + s0) & 0xFFFFFFFF) * 0x9E3779B1 & 0xFFFFFFFF
+        hsh = lowbias32(x ^ s1)
+        half = (hsh >> 16) if (j & 1) else (hsh & 0xFFFF)
+        assert bool(k[w, h, i, j]) == (half >= thr)
+    assert abs(float((~k).float().mean()) - p) < 0.01
+    assert torch.equal(k, O.attn_drop_keep(6, 3, p, s0, s1)) and not torch.equal(k, O.attn_drop_keep(6, 3, p, s0 + 1, s1))
+    assert bool(O.attn_drop_keep(2, 1, 0.0, 1, 2).all())
