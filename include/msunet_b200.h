@@ -197,7 +197,8 @@ int msu_adamw_chunk(void);
 int msu_adamw_step(const MsuAdamTensor* table, const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t n_blocks,
                    const float* inv_scale, const float* found_inf, void* stream);
 
-/* Every weight shadow of a model in one launch (the per-tensor form is msu_prep_weight).  A job of mode 0 reads the fp32 master
+/* Every weight shadow of a model in one launch (the per-tensor form is msu_prep_weight).  Replaces the per-layer weight casts that
+ * CUDA autocast performs inside every forward of the reference (trainer.py:308, scripts/validation_functions.py:78, 324).  A job of mode 0 reads the fp32 master
  * [R, C] once and writes the plain cast `dst` [R, C] and / or the transposed cast `dst_t` [C, R] (either may be NULL); modes 2, 3, 5
  * are msu_prep_weight's conv / patch-embed re-layouts into `dst`.  blk_job / blk_tile map each block to (job, tile); a job owns
  * msu_shadow_blocks(mode, R, C) consecutive tiles 0..n-1.  All pointers are device pointers. */
