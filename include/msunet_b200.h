@@ -161,11 +161,19 @@ int msu_loss_bwd(int dtype, const void* logits, const float* target, int32_t B, 
                  float beta, float mix, const float* stats, const int32_t* flag, const float* gscale,
                  void* dlogits, void* stream);
 
+/* Per-image DynamicLoss values for batched validation: image b is evaluated as a batch of one, including ITS OWN {0,255}
+ * label decision (the reference calls the loss once per image, scripts/validation_functions.py:89-104 with
+ * loss/DynamicLoss.py:87-88).  stats[b*8 + 4] = loss of image b (other slots as msu_loss_fwd, with B = 1 scaling not applied). */
+int msu_loss_per_sample(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha, float beta,
+                        float mix, float* ws /* >= B*64*16 floats */, float* stats /* [B,8] */, void* stream);
+
 /* Dice/IoU counting (scripts/validation_functions.py:106-108, 219-227, 267-292).
  * from_logits=1: pred = sigmoid(logit) rounded to `dtype`, pred_bin = pred > thr, gt = label > 0.
+ * from_logits=2: pred = sigmoid(logit) kept in fp32 whatever `dtype` is (the reference thresholds an fp16 / fp32 sigmoid,
+ *                validation_functions.py:78, 106-107; a bf16-rounded one would move the 0.5 boundary by 2^-9); pred_out is float.
  * from_logits=0: `in` is pred (dtype), pred_bin uint8 given, gt uint8 given.
  * counts int64 [B,4] = tp, fp, fn, tn (bit exact); soft fp64 [B,8] = TP, FP, FN, TN, sum p^2, sum g^2, sum p, sum g.
- * pred_out (optional, dtype) receives the probabilities. */
+ * pred_out (optional; dtype, or float for from_logits=2) receives the probabilities. */
 int msu_metrics(int dtype, int from_logits, const void* in, const void* label_or_gt, const uint8_t* pred_bin,
                 int32_t B, int64_t N, float thr, long long* ws_counts /* >= B*64*4 */, double* ws_soft /* >= B*64*8 */,
                 long long* counts, double* soft, void* pred_out, void* stream);

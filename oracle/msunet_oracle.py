@@ -289,19 +289,58 @@ def _ln(x, sd, p):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], LN_EPS)
 
 
-def swin_block(x, sd, p: str, nH: int, shift: int):
-    x = x + window_attention(_ln(x, sd, p + ".norm1"), sd, p, nH, shift)
+def _sd(branch, noise):
+    """StochasticDepth(p, "row") with the noise handed in (TV:ops/stochastic_depth.py:35-44: `noise` is one
+    Bernoulli(1-p)/(1-p) value per sample, broadcast over [1,1,1]; None = eval mode or p == 0)."""
+    return branch if noise is None else branch * noise.to(branch.dtype).view(-1, 1, 1, 1)
+
+
+def swin_block(x, sd, p: str, nH: int, shift: int, noise=None):
+    """TV:models/swin_transformer.py:452-455.  `noise` = (attention-branch noise [B], MLP-branch noise [B]) or None."""
+    n1, n2 = noise if noise is not None else (None, None)
+    x = x + _sd(window_attention(_ln(x, sd, p + ".norm1"), sd, p, nH, shift), n1)
     h = _ln(x, sd, p + ".norm2") @ sd[p + ".mlp.0.weight"].t() + sd[p + ".mlp.0.bias"]
     h = F.gelu(h)  # exact erf GELU, TV:ops/misc.py:264-305 with nn.GELU
-    return x + (h @ sd[p + ".mlp.3.weight"].t() + sd[p + ".mlp.3.bias"])
+    return x + _sd(h @ sd[p + ".mlp.3.weight"].t() + sd[p + ".mlp.3.bias"], n2)
 
 
-def stage(x, sd, p: str, depth: int, nH: int, res: int):
+def stage(x, sd, p: str, depth: int, nH: int, res: int, sd_noise=None):
     B, L, C = x.shape
     x = x.view(B, res, res, C)
     for j in range(depth):
-        x = swin_block(x, sd, f"{p}.blocks.{j}", nH, 0 if j % 2 == 0 else WS // 2)
+        blk = f"{p}.blocks.{j}"
+        x = swin_block(x, sd, blk, nH, 0 if j % 2 == 0 else WS // 2, sd_noise.get(blk) if sd_noise else None)
     return x
+
+
+def block_drop_probs(cfg: Cfg, drop_path_rate: float) -> Dict[str, float]:
+    """Stochastic-depth probability of every Swin block by module name: dpr = linspace(0, rate, sum(depths))
+    (network/model_parts.py:610); encoder stage k takes dpr[sum(depths[:k]) : sum(depths[:k+1])] (:618-632) and every decoder
+    stack working at stage k re-uses the same slice (:648-660, :676-690, :706-720)."""
+    d = cfg.depths
+    dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(d))]
+    out: Dict[str, float] = {}
+    for prefix, k in (("layers.0", 0), ("layers.1", 1), ("layers.2", 2), ("layers.3", 3),
+                      ("layers_up.1", 2), ("layers_up.2", 1), ("layers_up.3", 0),
+                      ("layers_cent1.1", 1), ("layers_cent1.2", 0), ("layers_cent2.1", 0)):
+        for j in range(d[k]):
+            out[f"{prefix}.blocks.{j}"] = dpr[sum(d[:k]) + j]
+    return out
+
+
+def draw_sd_noise(cfg: Cfg, batch: int, drop_path_rate: float, seed: int = 99) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+    """One (attention, MLP) pair of row-mode noise vectors per block, from a private CPU generator: the values a training
+    forward would draw (TV:ops/stochastic_depth.py:38-42), made reproducible so that the CUDA path and the oracle see the same."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, p in block_drop_probs(cfg, drop_path_rate).items():
+        keep = 1.0 - p
+        pair = []
+        for _ in range(2):
+            n = torch.empty(batch).bernoulli_(keep, generator=g)
+            pair.append(n / keep if keep > 0 else n)
+        out[name] = tuple(pair) if p > 0 else None
+    return {k: v for k, v in out.items() if v is not None}
 
 
 def patch_merging(x, sd, p: str):
@@ -339,9 +378,11 @@ def head(x, sd, cfg: Cfg):
     return F.conv2d(x.permute(0, 3, 1, 2), sd["output.weight"])
 
 
-def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: Cfg, run_dead: bool = False):
+def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: Cfg, run_dead: bool = False, sd_noise=None):
     """MSUNetSys.forward (model_parts.py:775-855).  `run_dead` also evaluates the two decoder
-    stacks whose outputs the reference discards (:794-795, :806-807); logits are identical."""
+    stacks whose outputs the reference discards (:794-795, :806-807); logits are identical.
+    `sd_noise`: {block module name: (noise1 [B], noise2 [B])} = the stochastic-depth noise of a training forward (see
+    `draw_sd_noise`); None = eval mode / drop_path_rate 0."""
     if x.size(1) != 3:
         raise ValueError(f"Expected 3 channels, but got {x.size(1)}")  # network/MSUNet.py:48-51
     assert x.shape[2] == cfg.img_size and x.shape[3] == cfg.img_size
@@ -350,31 +391,31 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: Cfg, run_dead: bo
     t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=4)
     P = _ln(t.flatten(2).transpose(1, 2), sd, "patch_embed.norm")
     # encoder stage 0
-    A1 = patch_merging(stage(P, sd, "layers.0", d[0], nh[0], r), sd, "layers.0.downsample")
+    A1 = patch_merging(stage(P, sd, "layers.0", d[0], nh[0], r, sd_noise), sd, "layers.0.downsample")
     # central decoder 2
     U = patch_expand(A1, sd, "layers_cent2.0", r // 2)
     F0 = _cbd(U, P, sd, 3)
     if run_dead:
-        stage(F0, sd, "layers_cent2.1", d[0], nh[0], r)
-    A2 = patch_merging(stage(A1, sd, "layers.1", d[1], nh[1], r // 2), sd, "layers.1.downsample")
+        stage(F0, sd, "layers_cent2.1", d[0], nh[0], r, sd_noise)
+    A2 = patch_merging(stage(A1, sd, "layers.1", d[1], nh[1], r // 2, sd_noise), sd, "layers.1.downsample")
     # central decoder 1
     V = patch_expand(A2, sd, "layers_cent1.0", r // 4)
     F1 = _cbd(V, A1, sd, 2)
-    Wd = patch_expand(stage(F1, sd, "layers_cent1.1", d[1], nh[1], r // 2), sd,
+    Wd = patch_expand(stage(F1, sd, "layers_cent1.1", d[1], nh[1], r // 2, sd_noise), sd,
                       "layers_cent1.1.upsample", r // 2)
     F0b = _cbd(Wd, F0, sd, 3)
     if run_dead:
-        stage(F0b, sd, "layers_cent1.2", d[0], nh[0], r)
-    A3 = patch_merging(stage(A2, sd, "layers.2", d[2], nh[2], r // 4), sd, "layers.2.downsample")
-    A4 = stage(A3, sd, "layers.3", d[3], nh[3], r // 8)
+        stage(F0b, sd, "layers_cent1.2", d[0], nh[0], r, sd_noise)
+    A3 = patch_merging(stage(A2, sd, "layers.2", d[2], nh[2], r // 4, sd_noise), sd, "layers.2.downsample")
+    A4 = stage(A3, sd, "layers.3", d[3], nh[3], r // 8, sd_noise)
     bott = _ln(A4, sd, "norm")
     # decoder
     D0 = patch_expand(bott, sd, "layers_up.0", r // 8)
-    D1 = patch_expand(stage(_cbd(D0, A2, sd, 1), sd, "layers_up.1", d[2], nh[2], r // 4), sd,
+    D1 = patch_expand(stage(_cbd(D0, A2, sd, 1), sd, "layers_up.1", d[2], nh[2], r // 4, sd_noise), sd,
                       "layers_up.1.upsample", r // 4)
-    D2 = patch_expand(stage(_cbd(D1, F1, sd, 2), sd, "layers_up.2", d[1], nh[1], r // 2), sd,
+    D2 = patch_expand(stage(_cbd(D1, F1, sd, 2), sd, "layers_up.2", d[1], nh[1], r // 2, sd_noise), sd,
                       "layers_up.2.upsample", r // 2)
-    D3 = stage(_cbd(D2, F0b, sd, 3), sd, "layers_up.3", d[0], nh[0], r)
+    D3 = stage(_cbd(D2, F0b, sd, 3), sd, "layers_up.3", d[0], nh[0], r, sd_noise)
     up = _ln(D3, sd, "norm_up").reshape(B, r * r, E)
     return head(up, sd, cfg)
 
@@ -457,10 +498,10 @@ def metrics_real(pred_bin, pred, gt):
 # ----------------------------------------------------------------------------------------------
 # convenience: one fwd+loss+bwd step on CPU (used by bench.py cpu_baseline and the parity tests)
 # ----------------------------------------------------------------------------------------------
-def train_step(sd, x, y, cfg: Cfg, alpha=0.2, beta=0.8, mix=0.45, run_dead=False):
+def train_step(sd, x, y, cfg: Cfg, alpha=0.2, beta=0.8, mix=0.45, run_dead=False, sd_noise=None):
     leaves = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v)
               for k, v in sd.items()}
-    logits = forward(leaves, x, cfg, run_dead=run_dead)
+    logits = forward(leaves, x, cfg, run_dead=run_dead, sd_noise=sd_noise)
     loss = dynamic_loss(logits, y, alpha, beta, mix)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.is_floating_point()}

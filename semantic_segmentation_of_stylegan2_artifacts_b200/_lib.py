@@ -68,6 +68,7 @@ _SIGS = {
     "msu_prep_weight": [C.c_int, C.c_int, _P, _P, _I64, _I64, _P],
     "msu_patchify4": [C.c_int, _P, _P, _I32, _I32, _P],
     "msu_loss_fwd": [C.c_int, _P, _P, _I32, _I64, _F, _F, _F, _P, _P, _P, _P, _P],
+    "msu_loss_per_sample": [C.c_int, _P, _P, _I32, _I64, _F, _F, _F, _P, _P, _P],
     "msu_loss_bwd": [C.c_int, _P, _P, _I32, _I64, _F, _F, _F, _P, _P, _P, _P, _P],
     "msu_metrics": [C.c_int, C.c_int, _P, _P, _P, _I32, _I64, _F, _P, _P, _P, _P, _P, _P],
     "msu_gather_rows": [C.POINTER(MsuOperand), _P, _I64, _I64, _P],

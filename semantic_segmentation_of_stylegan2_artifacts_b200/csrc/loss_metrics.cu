@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(LM_THREADS) loss_bwd_vec_kernel(const T* __res
 
 // one block: combines partials (fixed order, double), decides the {0,255} interpretation, writes per-sample
 // backward coefficients stats[b] = {w_bce/(N*B), m_b/B, Nn, D, loss_b} and the batch-mean loss.
+// per_sample != 0: every image decides its own {0,255} interpretation and is a batch of one (the reference validates one
+// image per DynamicLoss call, validation_functions.py:89-104), flag / loss may be null.
 __global__ void loss_final_kernel(const float* __restrict__ ws, int B, int nblk, int64_t N, float alpha, float beta,
-                                  float mix, float* __restrict__ stats, int32_t* __restrict__ flag, float* __restrict__ loss) {
+                                  float mix, float* __restrict__ stats, int32_t* __restrict__ flag, float* __restrict__ loss,
+                                  int per_sample) {
     __shared__ float smax[256];
     __shared__ double sloss[256];
     float mx = -INFINITY;
@@ -198,13 +201,20 @@ __global__ void loss_final_kernel(const float* __restrict__ ws, int B, int nblk,
         if (threadIdx.x < s) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
         __syncthreads();
     }
-    const int k = smax[0] > 1.0f ? 1 : 0;  // loss/DynamicLoss.py:87-88
-    if (threadIdx.x == 0) *flag = k;
+    const int kg = smax[0] > 1.0f ? 1 : 0;  // loss/DynamicLoss.py:87-88
+    if (threadIdx.x == 0 && flag) *flag = kg;
     // one warp per sample: lanes add the block records (double, fixed lane order), then a shuffle tree
     double acc = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int b = warp; b < B; b += nwarp) {
         double r6[6] = {0, 0, 0, 0, 0, 0};
+        int k = kg;
+        if (per_sample) {
+            float m1 = -INFINITY;
+            for (int j = lane; j < nblk; j += 32) m1 = fmaxf(m1, ws[((int64_t)b * nblk + j) * LS + 2]);
+            for (int o = 16; o > 0; o >>= 1) m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            k = m1 > 1.0f ? 1 : 0;
+        }
         for (int j = lane; j < nblk; j += 32) {
             const float* r = ws + ((int64_t)b * nblk + j) * LS;
             r6[0] += r[0]; r6[1] += r[4 + 6 * k]; r6[2] += r[5 + 6 * k]; r6[3] += r[6 + 6 * k]; r6[4] += r[7 + 6 * k]; r6[5] += r[8 + 6 * k];
@@ -238,7 +248,7 @@ __global__ void loss_final_kernel(const float* __restrict__ ws, int B, int nblk,
         if (threadIdx.x < s) sloss[threadIdx.x] += sloss[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *loss = (float)(sloss[0] / (double)B);
+    if (threadIdx.x == 0 && loss) *loss = (float)(sloss[0] / (double)B);
 }
 
 template <typename T>
@@ -284,7 +294,14 @@ __global__ void __launch_bounds__(LM_THREADS) metrics_partial_kernel(int from_lo
     for (int64_t i = (int64_t)blockIdx.x * LM_THREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * LM_THREADS) {
         float p;
         bool pb, g;
-        if (from_logits) {
+        if (from_logits == 2) {
+            // probabilities kept in fp32 whatever the logits dtype (the reference thresholds an fp16 / fp32 sigmoid,
+            // validation_functions.py:78,106-107: rounding it to bf16 would move the 0.5 boundary by 2^-9); pred_out is float
+            p = sigmoid_f(to_f<T>(x[i]));
+            pb = p > thr;
+            g = reinterpret_cast<const float*>(label_or_gt)[(int64_t)b * N + i] > 0.f;
+            if (pred_out) reinterpret_cast<float*>(pred_out)[(int64_t)b * N + i] = p;
+        } else if (from_logits) {
             // sigmoid in fp32 rounded to the logits dtype, THEN compared
             p = to_f<T>(from_f<T>(sigmoid_f(to_f<T>(x[i]))));
             pb = p > thr;
@@ -346,9 +363,9 @@ static int lm_blocks(int64_t N) { return (int)imax(1, imin(LM_BLOCKS, (N + LM_TH
 using namespace msu;
 
 /* ws: fp32, at least B*64*16 floats */
-extern "C" int msu_loss_fwd(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
-                            float beta, float mix, float* ws, float* stats, int32_t* flag, float* loss, void* stream) {
-    MSU_REQUIRE(logits && target && ws && stats && flag && loss, "msu_loss_fwd: null pointer");
+static int loss_fwd_impl(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
+                         float beta, float mix, float* ws, float* stats, int32_t* flag, float* loss, int per_sample, void* stream) {
+    MSU_REQUIRE(logits && target && ws && stats && (per_sample || (flag && loss)), "msu_loss_fwd: null pointer");
     MSU_REQUIRE(B > 0 && N > 0 && B <= 65535, "msu_loss_fwd: bad shape B=%d N=%lld", B, (long long)N);
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = lm_blocks(N);
@@ -361,9 +378,19 @@ extern "C" int msu_loss_fwd(int dtype, const void* logits, const float* target, 
     else if (dtype == MSU_BF16) loss_partial_kernel<__nv_bfloat16><<<grid, LM_THREADS, 0, st>>>((const __nv_bfloat16*)logits, target, N, ws);
     else if (dtype == MSU_F16) loss_partial_kernel<__half><<<grid, LM_THREADS, 0, st>>>((const __half*)logits, target, N, ws);
     else MSU_REQUIRE(false, "msu_loss_fwd: unsupported dtype %d", dtype);
-    loss_final_kernel<<<1, 256, 0, st>>>(ws, B, nblk, N, alpha, beta, mix, stats, flag, loss);
+    loss_final_kernel<<<1, 256, 0, st>>>(ws, B, nblk, N, alpha, beta, mix, stats, flag, loss, per_sample);
     count_launch(2);
     return check_launch("msu_loss_fwd");
+}
+
+extern "C" int msu_loss_fwd(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
+                            float beta, float mix, float* ws, float* stats, int32_t* flag, float* loss, void* stream) {
+    return loss_fwd_impl(dtype, logits, target, B, N, alpha, beta, mix, ws, stats, flag, loss, 0, stream);
+}
+
+extern "C" int msu_loss_per_sample(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,
+                                   float beta, float mix, float* ws, float* stats, void* stream) {
+    return loss_fwd_impl(dtype, logits, target, B, N, alpha, beta, mix, ws, stats, nullptr, nullptr, 1, stream);
 }
 
 extern "C" int msu_loss_bwd(int dtype, const void* logits, const float* target, int32_t B, int64_t N, float alpha,

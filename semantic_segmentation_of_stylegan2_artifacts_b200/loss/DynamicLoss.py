@@ -27,7 +27,8 @@ class DynamicLoss(torch.nn.Module):
     @torch.no_grad()
     def per_sample(self, output, target):
         """Per-image losses [B] (fp32, device-resident, no host sync): what `forward` returns for each image alone — used by the
-        batched validation loop (the reference evaluates one image per call, validation_functions.py:89-104)."""
+        batched validation loop (the reference evaluates one image per call, validation_functions.py:89-104), so the
+        {0,255} label decision of :87-88 is taken per image, not per batch."""
         from .. import ops
         if target.dim() == 3:
             target = target.unsqueeze(1)
@@ -37,5 +38,4 @@ class DynamicLoss(torch.nn.Module):
         ops._need_cuda(output, "logits")
         lg = output.contiguous().view(B, -1)
         tg = target.float().contiguous().view(B, -1)
-        _, stats, _ = ops.loss_fwd(lg, tg, self.alpha, self.beta, self.tversky_bce_mix)
-        return stats[:, 4].clone()
+        return ops.loss_per_sample(lg, tg, self.alpha, self.beta, self.tversky_bce_mix)

@@ -356,6 +356,14 @@ class MSUNetSys(nn.Module):
     def _draw_drop_path(self, B, device):
         """Stochastic-depth noise Bernoulli(1-p)/(1-p) per sample for every block of this forward in one shot
         (TV:ops/stochastic_depth.py:35-44 draws it block by block: ~90 tiny launches per step)."""
+        inject = getattr(self, "_sd_inject", None)
+        if inject is not None:
+            for name, m in self.named_modules():
+                if isinstance(m, SwinTransformerBlock) and m.sd_prob > 0.0:
+                    n1, n2 = inject[name]           # KeyError: the injected set must cover every block that drops
+                    m._sd_pool = (n1.to(device=device, dtype=torch.float32).contiguous(),
+                                  n2.to(device=device, dtype=torch.float32).contiguous())
+            return
         blocks = [m for m in self.modules() if isinstance(m, SwinTransformerBlock) and m.sd_prob > 0.0]
         if not blocks:
             return
@@ -366,6 +374,13 @@ class MSUNetSys(nn.Module):
         noise = (torch.rand(2 * len(blocks), B, device=device) < keep[:, None]).float() / keep[:, None]
         for i, b in enumerate(blocks):
             b._sd_pool = (noise[2 * i], noise[2 * i + 1])
+
+    def inject_drop_path_noise(self, noise):
+        """Parity hook: `noise` = {block module name: (attention-branch noise [B], MLP-branch noise [B])} replaces the
+        Bernoulli draws of the following training forwards (the values torchvision's StochasticDepth would have drawn,
+        TV:ops/stochastic_depth.py:38-42); None goes back to drawing."""
+        self._sd_inject = noise
+        return self
 
     def forward(self, x):
         if not x.is_cuda:

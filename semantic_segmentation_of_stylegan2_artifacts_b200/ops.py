@@ -360,6 +360,17 @@ def loss_fwd(logits: torch.Tensor, target: torch.Tensor, alpha: float, beta: flo
     return loss, stats, flag
 
 
+def loss_per_sample(logits: torch.Tensor, target: torch.Tensor, alpha: float, beta: float, mix: float) -> torch.Tensor:
+    """Per-image losses [B]: every image evaluated as its own batch of one, with its own {0,255} label decision."""
+    B, N = logits.shape
+    dev = logits.device
+    ws = torch.empty(B * 64 * 16, dtype=torch.float32, device=dev)
+    stats = torch.empty(B, 8, dtype=torch.float32, device=dev)
+    L.check(L.lib().msu_loss_per_sample(L.dt(logits), logits.data_ptr(), target.data_ptr(), B, N, alpha, beta, mix,
+                                        ws.data_ptr(), stats.data_ptr(), L.stream_ptr()), "msu_loss_per_sample")
+    return stats[:, 4].clone()
+
+
 def loss_bwd(logits, target, alpha, beta, mix, stats, flag, gscale: torch.Tensor) -> torch.Tensor:
     B, N = logits.shape
     d = torch.empty_like(logits)
@@ -370,16 +381,19 @@ def loss_bwd(logits, target, alpha, beta, mix, stats, flag, gscale: torch.Tensor
 
 
 def metrics(inp: torch.Tensor, label_or_gt: torch.Tensor, pred_bin: Optional[torch.Tensor], from_logits: bool,
-            thr: float, want_pred: bool = False):
-    """inp [B, N]; returns (counts int64 [B,4] = tp,fp,fn,tn, soft float64 [B,8], pred|None)."""
+            thr: float, want_pred: bool = False, prob_f32: bool = False):
+    """inp [B, N]; returns (counts int64 [B,4] = tp,fp,fn,tn, soft float64 [B,8], pred|None).
+    from_logits: pred = sigmoid(inp) rounded to inp's dtype before the threshold (torch.sigmoid semantics on that dtype), or —
+    `prob_f32` — kept in fp32 (pred comes back as fp32)."""
     B, N = inp.shape
     dev = inp.device
     wc = torch.empty(B * 64 * 4, dtype=torch.int64, device=dev)
     wsf = torch.empty(B * 64 * 8, dtype=torch.float64, device=dev)
     counts = torch.empty(B, 4, dtype=torch.int64, device=dev)
     soft = torch.empty(B, 8, dtype=torch.float64, device=dev)
-    pred = torch.empty_like(inp) if (want_pred and from_logits) else None
-    L.check(L.lib().msu_metrics(L.dt(inp), 1 if from_logits else 0, inp.data_ptr(), label_or_gt.data_ptr(),
+    f32p = bool(from_logits and prob_f32)
+    pred = torch.empty(inp.shape, dtype=torch.float32 if f32p else inp.dtype, device=dev) if (want_pred and from_logits) else None
+    L.check(L.lib().msu_metrics(L.dt(inp), (2 if f32p else 1) if from_logits else 0, inp.data_ptr(), label_or_gt.data_ptr(),
                                 L.ptr(pred_bin), B, N, thr, wc.data_ptr(), wsf.data_ptr(), counts.data_ptr(),
                                 soft.data_ptr(), L.ptr(pred), L.stream_ptr()), "msu_metrics")
     return counts, soft, pred

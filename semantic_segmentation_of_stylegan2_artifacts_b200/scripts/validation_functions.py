@@ -38,14 +38,17 @@ def _count(pred_bin, pred, ground_truth):
 
 
 def image_counts_from_logits(out_logits: torch.Tensor, label: torch.Tensor, sig_threshold: float = 0.5,
-                             want_pred: bool = True):
+                             want_pred: bool = True, prob_f32: bool = True):
     """Batched fused path: logits [B,1,H,W] + label [B,H,W] -> (counts int64 [B,4], soft float64 [B,8], pred).
-    pred = sigmoid rounded to the logits dtype, pred_bin = pred > thr, gt = label > 0
-    (scripts/validation_functions.py:106-108) — all inside one kernel, device-resident results."""
+    pred = sigmoid(logits) in fp32 whatever the logits dtype, pred_bin = pred > thr, gt = label > 0
+    (scripts/validation_functions.py:106-108) — all inside one kernel, device-resident results.  The reference evaluates under
+    fp16 autocast (:78): its sigmoid has 11 bits below 0.5's ulp; bf16 logits rounded to a bf16 sigmoid would move the decision
+    boundary (ulp 2^-9 above 0.5) and shift the soft Dice / IoU that feed `Score`, so probabilities stay fp32 here
+    (`prob_f32=False`: torch.sigmoid semantics on the logits dtype, i.e. rounded to it before the threshold)."""
     B = out_logits.shape[0]
     lg = out_logits.contiguous().view(B, -1)
     lb = label.contiguous().float().view(B, -1)
-    counts, soft, pred = ops.metrics(lg, lb, None, from_logits=True, thr=float(sig_threshold), want_pred=want_pred)
+    counts, soft, pred = ops.metrics(lg, lb, None, from_logits=True, thr=float(sig_threshold), want_pred=want_pred, prob_f32=prob_f32)
     if pred is not None:
         pred = pred.view(B, *out_logits.shape[2:])
     return counts, soft, pred

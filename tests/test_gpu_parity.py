@@ -187,9 +187,18 @@ def test_metric_counts_bit_exact(pkg, dtype):
     label = (torch.rand(B, S, S) > 0.7).float()
     label[2] = 0
     lgd = lg.to(DEV).to(dtype)
-    counts, soft, pred = VF.image_counts_from_logits(lgd, label.to(DEV), 0.5)
+    # default: probabilities in fp32 whatever the logits dtype (what the validation loop uses)
+    c32, s32, p32 = VF.image_counts_from_logits(lgd, label.to(DEV), 0.5)
+    ref32 = torch.sigmoid(lgd.float()).squeeze(1)
+    assert p32.dtype == torch.float32 and torch.equal(p32, ref32)
+    for i in range(B):
+        assert c32[i].tolist() == list(O.confusion_counts((ref32[i] > 0.5).cpu().numpy(), (label[i] > 0).numpy()))
+        np.testing.assert_allclose(s32[i].cpu().numpy(), np.array(O.soft_sums(ref32[i].cpu().numpy(), (label[i] > 0).numpy())), rtol=1e-6)
+    counts, soft, pred = VF.image_counts_from_logits(lgd, label.to(DEV), 0.5, prob_f32=False)
     ref_pred = torch.sigmoid(lgd).squeeze(1)          # the reference's own expression on the same device/dtype
     assert torch.equal(pred, ref_pred)
+    if dtype == torch.bfloat16:      # the bf16-rounded sigmoid moves borderline pixels: the reason the loop keeps fp32 probabilities
+        assert not torch.equal(c32, counts)
     pb, gt = (ref_pred > 0.5), (label.to(DEV) > 0)
     for i in range(B):
         tp, fp, fn, tn = O.confusion_counts(pb[i].cpu().numpy(), gt[i].cpu().numpy())

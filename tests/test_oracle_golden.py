@@ -47,6 +47,60 @@ def test_forward_backward_matches_reference(name):
             assert relmax(grads[k].numpy(), g[key]) < tol, k
 
 
+SD_CASES = {"t32_160_sd": (O.T32, 160, 4), "t96_512_sd": (O.T96, 512, 2)}
+
+
+def load_sd_noise(g):
+    """{block name: (noise1 [B], noise2 [B])} as the reference drew it (recorded by oracle/make_golden.py:run_sd_case)."""
+    return {str(k): (torch.from_numpy(n[0].copy()), torch.from_numpy(n[1].copy())) for k, n in zip(g["noise_names"], g["noise"])}
+
+
+@pytest.mark.parametrize("name", list(SD_CASES))
+def test_stochastic_depth_matches_reference(name):
+    """Training forward + backward WITH stochastic depth (drop_path 0.3 on small padded maps; drop_path 0.1 at the benchmarked
+    512x512 T96 shape): the oracle fed the noise the reference drew reproduces the reference's logits, loss and gradients."""
+    kw, img, batch = SD_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = O.Cfg(img_size=img, **kw)
+    sd = O.make_weights(cfg)
+    noise = load_sd_noise(g)
+    probs = O.block_drop_probs(cfg, float(g["drop_path_rate"]))
+    assert set(noise) == {k for k, p in probs.items() if p > 0}
+    for k, (n1, n2) in noise.items():       # every value is 0 or 1/(1-p) of ITS block
+        for v in torch.cat([n1, n2]).tolist():
+            assert v == 0.0 or abs(v - 1.0 / (1.0 - probs[k])) < 1e-6, (k, v)
+    x, y = O.make_inputs(cfg, batch)
+    logits, loss, grads = O.train_step(sd, x, y, cfg, sd_noise=noise)
+    st = int(g["stride"])
+    assert relmax(logits[:, :, ::st, ::st].numpy(), g["logits_strided"]) < 2e-5
+    assert abs(logits.double().norm().item() - float(g["logits_l2"])) < 1e-5 * float(g["logits_l2"])
+    assert abs(logits.double().sum().item() - float(g["logits_sum"])) < 1e-5 * float(g["logits_abs_sum"])
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * abs(float(g["loss"])) + 1e-7
+    for k, n in zip(g["grad_names"], g["grad_norms"]):
+        gn = grads[k].double().norm().item()
+        assert abs(gn - n) < (1e-4 if "attn.qkv.bias" in k else 2e-4) * n + 1e-5, (k, gn, n)
+    for key in g.files:
+        if key.startswith("grad::"):
+            k = key[6:]
+            assert relmax(grads[k].numpy(), g[key]) < (5e-4 if "qkv.bias" not in k else 2e-3), k
+    # and the noise matters: without it the logits differ
+    assert relmax(O.forward(sd, x[:1], cfg)[:, :, ::st, ::st].numpy(), g["logits_strided"][:1]) > 1e-3
+
+
+def test_draw_sd_noise_is_row_mode_bernoulli():
+    cfg = O.Cfg(img_size=64, **O.T32)
+    n = O.draw_sd_noise(cfg, 64, 0.5, seed=3)
+    probs = O.block_drop_probs(cfg, 0.5)
+    assert "layers.0.blocks.0" not in n and probs["layers.0.blocks.0"] == 0.0          # dpr starts at 0
+    assert abs(probs["layers.3.blocks.1"] - 0.5) < 1e-7 and probs["layers_up.3.blocks.1"] == probs["layers.0.blocks.1"]
+    for k, (a, b) in n.items():
+        keep = 1.0 - probs[k]
+        for v in (a, b):
+            assert set(v.tolist()) <= {0.0, float(torch.tensor(1.0) / keep)}
+    allv = torch.cat([torch.cat(v) for v in n.values()])
+    assert 0.1 < float((allv == 0).float().mean()) < 0.45
+
+
 def test_dead_branches_do_not_change_logits():
     cfg = O.Cfg(img_size=96, **O.T32)
     sd = O.make_weights(cfg)
