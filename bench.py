@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the MS-UNet hot path (BASELINE.json): train img/s, fwd + DynamicLoss + bwd, T96 @ 512x512.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
-    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU), 16 images / GPU
+    python bench.py --gpus N --global-batch 128               # SURVEY config 3: equal GLOBAL batch (128 / N per GPU, micro-batches)
+    python bench.py --img 1024 --batch 4                      # the 1024x1024 rows of the north star
+    python bench.py --impl reference --steps K --warmup W     # the reference's own modules on the host CPU cores
+    python bench.py --impl reference-gpu                      # the reference's own modules, PyTorch eager fp16 autocast, on cuda:0
 
 One JSON line on stdout (rank 0).  Keys follow the driver contract: `value` = whole-job img/s with inputs
 resident in HBM (device-timed, max over ranks); `e2e` = the same through the public API with pinned-host
@@ -24,9 +27,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train_img_per_s_512x512_msunet_fwd_bwd"
 UNIT = "img/s"
+
+
+def metric_name(S):
+    return METRIC if S == 512 else f"train_img_per_s_{S}x{S}_msunet_fwd_bwd"
+
 IMG, PER_GPU_BATCH = 512, 16
 T96 = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24])
 GFLOP_PER_IMG_FWD_BWD = 594.2  # BASELINE.md, T96 @ 512^2, live graph
+GFLOP_TABLE = {("T96", 224): 109.8, ("T96", 512): 594.2, ("T96", 1024): 2345.5,
+               ("B128", 224): 284.5, ("B128", 512): 1554.3, ("B128", 1024): 6162.8}
 
 
 def synth_batch(B, S, seed):
@@ -87,27 +97,74 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_step_factory(img, batch):
-    """The reference algorithm (oracle port, CPU fp32, all host threads) on a bounded sample of the workload."""
+def load_reference_modules():
+    """(MSUNetSys, DynamicLoss) of the UNMODIFIED reference from baseline/_ref (tools/install_reference.py copies it there; it
+    travels to the GPU box), with the timm.layers stand-in of oracle/_shims; None when the copy is absent."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "network", "model_parts.py")):
+        return None
+    for p in (os.path.join(ROOT, "oracle", "_shims"), ref):
+        if p not in sys.path:
+            sys.path.append(p)
+    try:
+        from network.model_parts import MSUNetSys as RefNet      # noqa: the reference's own module
+        from loss.DynamicLoss import DynamicLoss as RefLoss
+    except Exception as e:  # pragma: no cover
+        print(f"[bench] reference modules not importable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        return None
+    return RefNet, RefLoss
+
+
+def cpu_reference_step_factory(img, batch, device="cpu", autocast=None):
+    """One fwd + DynamicLoss + bwd of the reference on `device`: the reference's own modules (kind "reference") when
+    baseline/_ref is present, else the oracle port (kind "port").  Returns (step, threads, kind)."""
+    import contextlib
     import torch
     from oracle import msunet_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = O.Cfg(img_size=img, embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24))
     sd = O.make_weights(cfg)
     x, y = synth_batch(batch, img, 4321)
+    x, y = x.to(device), y.to(device)
+    ctx = (lambda: torch.amp.autocast("cuda", dtype=autocast)) if autocast is not None else contextlib.nullcontext
+    mods = load_reference_modules()
+    if mods is not None:
+        RefNet, RefLoss = mods
+        with contextlib.redirect_stdout(sys.stderr):
+            m = RefNet(img_size=img, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+                       drop_path_rate=0.1, attn_drop_rate=0.0, drop_rate=0.0)
+        m.load_state_dict(sd, strict=True)
+        m.to(device).train()
+        crit = RefLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)
+        scaler = torch.amp.GradScaler("cuda") if autocast == torch.float16 else None
+
+        def step():
+            for p in m.parameters():
+                p.grad = None
+            with ctx():
+                loss = crit(m(x), y)
+            (scaler.scale(loss) if scaler is not None else loss).backward()
+            return float(loss)
+        return step, torch.get_num_threads(), "reference"
+    if device != "cpu":
+        sd = {k: v.to(device) for k, v in sd.items()}
 
     def step():
-        _, loss, _ = O.train_step(sd, x, y, cfg)
+        with ctx():
+            _, loss, _ = O.train_step(sd, x, y, cfg)
         return float(loss)
-    return step, torch.get_num_threads()
+    return step, torch.get_num_threads(), "port"
 
 
 def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    S = args.img
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args, emit)
     sample_b = 1
-    step, cores = cpu_reference_step_factory(IMG, sample_b)
+    step, cores, kind = cpu_reference_step_factory(S, sample_b)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
     steps = max(1, min(args.steps, 3))
@@ -116,15 +173,59 @@ def run_reference(args, emit):
         step()
     dt = (time.perf_counter() - t0) / steps
     v = sample_b / dt
-    sample = f"T96 {IMG}x{IMG} fwd+DynamicLoss+bwd on {sample_b} image/step, {steps} timed steps (bounded sample of batch {PER_GPU_BATCH})"
+    sample = (f"T96 {S}x{S} fwd+DynamicLoss+bwd on {sample_b} image/step, {steps} timed steps (bounded sample of batch "
+              f"{PER_GPU_BATCH}); {'the reference modules from baseline/_ref' if kind == 'reference' else 'oracle port'}, fp32")
     emit(({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric_name(S), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MS-UNet T96 training step {IMG}x{IMG} (reference algorithm, CPU)", "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"MS-UNet T96 training step {S}x{S} (reference, CPU)", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_reference_gpu(args, emit):
+    """BASELINE.md plan item 5: the reference's own modules in PyTorch eager on ONE B200, fp16 autocast + GradScaler exactly as
+    trainer.py:182, 308-314 runs them (cuDNN / cuBLAS kernels; none of this repo's kernels).  The eager graph keeps every
+    intermediate (~1.5 GiB / image under autocast at 512x512), so the batch is the largest of 16 / 8 / 4 / 2
+    that fits."""
+    import torch
+    S = args.img
+    dev = "cuda:0"
+    torch.backends.cuda.matmul.allow_tf32 = True          # train.py:20-21
+    torch.backends.cudnn.allow_tf32 = True
+    last = None
+    for B in (args.batch, 8, 4, 2, 1):
+        if B > args.batch:
+            continue
+        try:
+            step, _, kind = cpu_reference_step_factory(S, B, device=dev, autocast=torch.float16)
+            for _ in range(max(2, min(args.warmup, 3))):
+                step()
+            torch.cuda.synchronize()
+            steps = max(1, min(args.steps, 10))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            v = B / (ms / 1e3)
+            sample = (f"T96 {S}x{S} fwd+DynamicLoss+bwd, batch {B}, PyTorch eager fp16 autocast + GradScaler on one B200 "
+                      f"({'reference modules from baseline/_ref' if kind == 'reference' else 'oracle port'}), {steps} timed steps; "
+                      f"peak memory {torch.cuda.max_memory_allocated() / 2 ** 30:.1f} GiB")
+            emit({"impl": "reference-gpu", "metric": metric_name(S), "value": v, "unit": UNIT, "n_gpus": 1, "steps": steps,
+                  "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": "f16", "data": "synthetic",
+                  "config": {"workload": f"MS-UNet T96 training step {S}x{S}, batch {B} (reference, GPU eager)", "sample": sample},
+                  "gpu_eager_baseline": {"value": v, "unit": UNIT, "kind": kind, "batch": B, "sample": sample}})
+            return
+        except torch.OutOfMemoryError as e:
+            last = e
+            torch.cuda.empty_cache()
+    emit({"impl": "reference-gpu", "unavailable": f"out of memory at every batch size: {last}"})
 
 
 def main():
@@ -141,6 +242,13 @@ def main():
     ap.add_argument("--model", default="T96", choices=["T96", "B128"], help="B128 = config.yaml default (embed 128, depths 2-2-18-2)")
     ap.add_argument("--drop-path", type=float, default=0.1)
     ap.add_argument("--attn-drop", type=float, default=0.0, help="attention dropout (config.yaml of the reference: 0.05)")
+    ap.add_argument("--global-batch", type=int, default=0, help="equal GLOBAL batch (SURVEY config 3): each rank takes global/N images "
+                    "per step in micro-batches of --micro-batch, gradients accumulated, one exchange per step; scaling = strong")
+    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--optimizer", default="none", choices=["none", "fused", "sharded"],
+                    help="include the AdamW step in the timed step: fused = all-reduce + replicated one-launch FusedAdamW; "
+                         "sharded = reduce-scatter -> AdamW on the shard -> all-gather, overlapped with backward (N > 1)")
+    ap.add_argument("--no-dp-check", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else written to file descriptor 1 during the run (NCCL's version banner,
     # library chatter) is sent to stderr, and the result line is written to the saved descriptor at the end
@@ -151,7 +259,7 @@ def main():
     def emit(obj):
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         return run_reference(args, emit)
 
     import torch
@@ -173,10 +281,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     W = max(3, args.warmup)
     B, S = args.batch, args.img
+    strong = args.global_batch > 0
+    if strong:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world                      # images per rank and step
+    MB = min(args.micro_batch, B) if strong else B          # images per forward / backward
+    if B % MB:
+        raise SystemExit(f"per-rank batch {B} is not a multiple of the micro-batch {MB}")
+    n_micro = B // MB
 
     torch.manual_seed(1234)
     arch = T96 if args.model == "T96" else dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32])
-    gflop_img = GFLOP_PER_IMG_FWD_BWD if args.model == "T96" else 1554.3
+    gflop_img = GFLOP_TABLE.get((args.model, S), GFLOP_PER_IMG_FWD_BWD * (S / 512.0) ** 2)
     model = MSUNetSys(img_size=S, drop_path_rate=args.drop_path, attn_drop_rate=args.attn_drop, **arch).set_precision(args.precision).to(dev).train()
     if world > 1:
         from semantic_segmentation_of_stylegan2_artifacts_b200.dp import DataParallelB200
@@ -186,14 +303,29 @@ def main():
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
     params = [p for p in model.parameters()]
+    import contextlib
+    opt = None                       # set after the first warm-up step (the sharded optimizer needs the learnt bucket layout)
 
-    def step(x, y):
+    fused = None                     # replicated one-launch AdamW after the exchange (--optimizer fused)
+
+    def step_core(x, y):             # the capturable part of a step
         for p in params:
             p.grad = None
-        loss = crit(model(x), y)
-        loss.backward()
-        if world > 1:
+        for i in range(n_micro):     # n_micro == 1 unless --global-batch: micro-batches accumulate, the last one exchanges
+            last = i == n_micro - 1
+            with (contextlib.nullcontext() if (last or world == 1) else model.no_sync()):
+                loss = crit(model(x[i * MB:(i + 1) * MB]), y[i * MB:(i + 1) * MB])
+                (loss if n_micro == 1 else loss / n_micro).backward()
+        if opt is not None:
+            opt.step()               # sharded: joins the per-bucket reduce-scatter / update / all-gather launched during backward
+        elif world > 1:
             model.finish_gradient_sync()
+        return loss
+
+    def step(x, y):
+        loss = step_core(x, y)
+        if fused is not None:
+            fused.step()
         return loss
 
     def barrier():
@@ -202,7 +334,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- warm-up (also builds weight shadows, workspaces, func attributes)
-    for _ in range(W):
+    step(x_d, y_d)
+    if args.optimizer != "none":
+        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+        nd = [p for k, p in named if p.ndim == 1 or k.endswith(".bias") or "norm" in k.lower()]      # trainer.py:133-140
+        dc = [p for k, p in named if not (p.ndim == 1 or k.endswith(".bias") or "norm" in k.lower())]
+        groups = [{"params": dc, "weight_decay": 1e-3}, {"params": nd, "weight_decay": 0.0}]
+        if args.optimizer == "sharded":
+            if world == 1:
+                raise SystemExit("--optimizer sharded needs N > 1")
+            from semantic_segmentation_of_stylegan2_artifacts_b200.dp import ShardedAdamW
+            opt = ShardedAdamW(model, groups, lr=1e-5, betas=(0.9, 0.999), eps=1e-8)
+        else:
+            from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW
+            fused = FusedAdamW(groups, lr=1e-5, betas=(0.9, 0.999), eps=1e-8)
+    for _ in range(W - 1):
         step(x_d, y_d)
     barrier()
 
@@ -211,10 +357,14 @@ def main():
     use_graph = not args.no_graph
     if use_graph:
         try:
+            if args.optimizer == "sharded":
+                opt.prepare_step()       # per-step coefficients are uploaded from the host OUTSIDE the graph, before each replay
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                g_loss = step(x_d, y_d)
+                g_loss = step_core(x_d, y_d)
             graph.replay()
+            if args.optimizer == "sharded":
+                opt.after_replay()
             torch.cuda.synchronize()
         except Exception as e:  # capture is an optimisation, never a requirement
             print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
@@ -223,7 +373,13 @@ def main():
 
     def run_step():
         if graph is not None:
+            if args.optimizer == "sharded":
+                opt.prepare_step()
             graph.replay()
+            if args.optimizer == "sharded":
+                opt.after_replay()
+            if fused is not None:
+                fused.step()             # eager, after the replayed fwd + bwd (+ exchange), as graphs.GraphedStep users do
             return g_loss
         return step(x_d, y_d)
 
@@ -272,8 +428,7 @@ def main():
         if graph is not None:
             x_d.copy_(xd, non_blocking=True)
             y_d.copy_(yd, non_blocking=True)
-            graph.replay()
-            lv = g_loss.item()
+            lv = run_step().item()
         else:
             lv = step(xd, yd).item()
     e1.record()
@@ -301,8 +456,7 @@ def main():
         if graph is not None:
             x_d.copy_(xd, non_blocking=True)
             y_d.copy_(yd, non_blocking=True)
-            graph.replay()
-            lv = g_loss.item()
+            lv = run_step().item()
         else:
             lv = step(xd, yd).item()
     u1.record()
@@ -319,14 +473,18 @@ def main():
     step(x_d, y_d)          # every rank runs it (the step contains collectives); only rank 0 records events
     barrier()
     if rank == 0:
-        agg = {}
+        agg, fam = {}, {}
         for tag, a, b, _nb, _fl in ops.PROF:
+            t_ms = a.elapsed_time(b)
+            f = fam.setdefault(tag[3], [0.0, 0, 0, 0])       # per kernel family: ms, launches, algorithmic bytes, flops
+            f[0] += t_ms; f[1] += 1; f[2] += _nb; f[3] += _fl
             if not (tag[3].endswith("_tc") or tag[3].endswith("_simt")):
-                continue          # GEMM-shaped launches only; tools/op_table.py prints the full table
+                continue          # GEMM-shaped launches only for the dominant kernel; tools/op_table.py prints the full table
             d = agg.setdefault(tag, [0.0, 0])
-            d[0] += a.elapsed_time(b)
+            d[0] += t_ms
             d[1] += 1
         ops.PROF = None
+        fam_total = sum(v[0] for v in fam.values())
         top = max(agg.items(), key=lambda kv: kv[1][0])
         (M, N, K, kind), (tot_ms, cnt) = top
         peaks = {}
@@ -336,47 +494,110 @@ def main():
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = 2.0 * M * N * K / (tot_ms / cnt * 1e-3) / 1e12
-        traffic = None
+        traffic = None         # DRAM bytes of ONE ncu --set full capture: only reported for the kernel + shape it was taken on
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            if tj.get("kind") == kind and [tj.get("M"), tj.get("N"), tj.get("K")] == [M, N, K]:
+                traffic = tj.get("bytes_per_launch")
         except Exception:
             pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6451.0)) if peaks else 6451.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic, "kernel": f"{kind} M={M} N={N} K={K}", "launches_per_step": cnt,
                 "share_of_step": tot_ms / ms_per_step if graph is None else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                 "gemm_ms_by_kind": {f"{k[3]}:{k[0]}x{k[1]}x{k[2]}": round(v[0], 3) for k, v in
-                                    sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}}
+                                    sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]},
+                # every kernel family of one eager step, bracketed by CUDA events on the launch stream: share of the summed op
+                # time, achieved TFLOP/s (contractions) and GB/s of algorithmic bytes (memory-bound families) against the peaks
+                "families": {k: {"ms": round(v[0], 3), "share": round(v[0] / fam_total, 4), "launches": v[1],
+                                 **({"tflops": round(v[3] / v[0] / 1e9, 1), "frac_tensor": round(v[3] / v[0] / 1e9 / peak, 3)} if v[3] else {}),
+                                 **({"gbps": round(v[2] / v[0] / 1e6, 0), "frac_hbm": round(v[2] / v[0] / 1e6 / hbm_peak, 3)} if v[2] else {})}
+                             for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
+                "families_note": "eager pass, per-launch CUDA events (no side-stream overlap); shares are of the summed op time"}
+
+    # ---------------- numerical check of the multi-GPU path (untimed): the exchanged gradients of named tensors and the loss
+    # against a single-process pass over the GLOBAL batch (every rank's shard replayed on this rank with the same
+    # stochastic-depth noise, gradients accumulated under no_sync)
+    dp_check = None
+    if world > 1 and not args.no_dp_check and args.optimizer == "none":
+        from oracle import msunet_oracle as O            # noise generator only (test infrastructure used as the checker)
+        core = model.module
+        ocfg = O.Cfg(img_size=S, embed_dim=arch["embed_dim"], depths=tuple(arch["depths"]), num_heads=tuple(arch["num_heads"]))
+        names = ["patch_embed.proj.weight", "layers.0.blocks.1.attn.qkv.weight", "layers.2.blocks.3.mlp.0.weight",
+                 "concat_back_dim.3.weight", "layers_up.3.blocks.1.attn.relative_position_bias_table", "up.refine2.weight", "output.weight"]
+        pd = dict(core.named_parameters())
+        shards = [synth_batch(B, S, 4321 + r) for r in range(world)]
+        noise = [O.draw_sd_noise(ocfg, MB, args.drop_path, seed=1000 + r) for r in range(world)]
+        # (1) the data-parallel step on this rank's shard
+        core.inject_drop_path_noise(noise[rank] if args.drop_path > 0 else None)
+        loss_dp = step(x_d, y_d).detach().float().clone()
+        dist.all_reduce(loss_dp, op=dist.ReduceOp.SUM)
+        got = {k: pd[k].grad.detach().clone() for k in names}
+        # (2) single process over the global batch: shard by shard, gradients summed, divided by N
+        for p_ in params:
+            p_.grad = None
+        loss_sp = torch.zeros((), device=dev)
+        with model.no_sync():
+            for r in range(world):
+                core.inject_drop_path_noise(noise[r] if args.drop_path > 0 else None)
+                xr, yr = shards[r][0].to(dev), shards[r][1].to(dev)
+                for i in range(n_micro):
+                    l_ = crit(core(xr[i * MB:(i + 1) * MB]), yr[i * MB:(i + 1) * MB])
+                    (l_ / (n_micro * world)).backward()
+                loss_sp += l_.detach().float() if n_micro == 1 else 0.0
+        core.inject_drop_path_noise(None)
+        ops.next_grad_pass()
+        worst = 0.0
+        for k in names:
+            ref_g = pd[k].grad
+            worst = max(worst, float((got[k] - ref_g).abs().max() / ref_g.abs().max().clamp_min(1e-30)))
+        for p_ in params:
+            p_.grad = None
+        w_t = torch.tensor([worst], device=dev)
+        dist.all_reduce(w_t, op=dist.ReduceOp.MAX)
+        dp_check = {"max_rel": float(w_t.item()), "tensors": names,
+                    "loss_rel": (abs(float(loss_dp.item()) - float(loss_sp.item())) / abs(float(loss_sp.item()))) if n_micro == 1 else None,
+                    "bucket_writes": dict(model.stats),
+                    "how": "rank-averaged gradients after the NCCL exchange vs one process replaying every rank's shard (same "
+                           "stochastic-depth noise), max |a-b| / max |b| over the listed tensors, max over ranks"}
+        barrier()
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cstep, cores = cpu_reference_step_factory(S, 1)
+        cstep, cores, ckind = cpu_reference_step_factory(S, 1)
         cstep()
         t0 = time.perf_counter()
         n = 2
         for _ in range(n):
             cstep()
         cdt = (time.perf_counter() - t0) / n
-        cpu = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"T96 {S}x{S} fwd+DynamicLoss+bwd on 1 image/step, {n} timed steps after 1 warm-up"}
+        cpu = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": ckind,
+               "sample": f"T96 {S}x{S} fwd+DynamicLoss+bwd on 1 image/step, {n} timed steps after 1 warm-up "
+                         f"({'the reference modules from baseline/_ref' if ckind == 'reference' else 'oracle port'}, fp32)"}
 
     if rank == 0:
         emit(({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": metric_name(S), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"MS-UNet {args.model} ({'embed 96, depths 2-2-6-2' if args.model == 'T96' else 'embed 128, depths 2-2-18-2'}, window 7) training step fwd+DynamicLoss+bwd, "
-                                   f"{S}x{S}, batch {B}/GPU (global {B * world}), drop_path {args.drop_path}, attn_drop {args.attn_drop}",
+                                   f"{S}x{S}, batch {B}/GPU (global {B * world})"
+                                   + (f" in {n_micro} micro-batches of {MB} with gradient accumulation" if n_micro > 1 else "")
+                                   + f", drop_path {args.drop_path}, attn_drop {args.attn_drop}",
                        "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                        "l2": "working set >> L2: ~10 GB of activations are written and re-read every step",
-                       "optimizer": "excluded (metric is fwd+bwd)"},
+                       "optimizer": {"none": "excluded (metric is fwd+bwd)",
+                                     "fused": "included: gradient all-reduce + replicated one-launch FusedAdamW",
+                                     "sharded": "included: reduce-scatter -> AdamW on the rank's shard -> all-gather per bucket, "
+                                                "overlapped with backward (dp.ShardedAdamW)"}[args.optimizer]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_uint8_staging": e2e_u8,
             "gpu_launches": int(launches),
             "model_tflops": value * gflop_img / 1e3 / world,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "dp_check": dp_check,
         }))
     if world > 1:
         # tear down without ever hanging the launcher: captured graphs hold NCCL work, so give the orderly

@@ -273,7 +273,7 @@ class SwinBlockFn(Function):
         x2 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(a), w_fwd(f2w, dt), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
         ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
-                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a)
+                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b)
         ctx.cfg = (B, H, W, nH, geo, nW)
         ctx.drop = (attn_p, drop_seed)
         return x2.view(B, H, W, Cd)
@@ -282,59 +282,53 @@ class SwinBlockFn(Function):
     @once_differentiable
     def backward(ctx, dx2):
         (x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
-         xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a) = ctx.saved_tensors
+         xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b) = ctx.saved_tensors
         B, H, W, nH, geo, nW = ctx.cfg
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T, HW, Tw, hid = B * H * W, H * W, B * nW * 49, f1w.shape[0]
         dx2 = _c(dx2).view(T, Cd)
         f32 = dict(dtype=torch.float32, device=dev)
-        wg = _WgradFork(dev)
-        wg.__enter__()
-        # ---- MLP half
-        # stochastic-depth scale of the incoming gradient rows: large maps never materialise sd2 * dx2 — the dgrad GEMM scales its
-        # output rows in the epilogue and the weight-gradient GEMM keeps every split-K slab inside one sample and scales whole
-        # partials in its reduce (MsuOperand.rowscale); small maps (few tokens per sample) gather the scaled rows once
-        fused_sd = dt == BF16 and sd2 is not None and HW >= 4096 and HW % 64 == 0
-        if fused_sd:
-            dy2, dy2t = operand(dx2), operand(dx2, orient=1, rowscale=sd2, rps=HW)
-        else:
-            dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
-        # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum)
-        db2 = torch.empty(Cd, **f32)
-        dW2 = torch.empty(Cd, hid, **f32)
-        wg.run(lambda: gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev))
-        dh = torch.empty(T, hid, dtype=dt, device=dev)
-        gemm(dy2, w_dgrad(f2w, dt),
-             epilogue(dh, H=h, ldh=hid, rowscale=sd2 if fused_sd else None, rps=HW if fused_sd else 0), T, hid, Cd, dev)
-        db1 = torch.empty(hid, **f32)
-        dW1 = torch.empty(hid, Cd, **f32)
-        wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))
-        dxn = torch.empty(T, Cd, dtype=dt, device=dev)
-        gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
-        # ---- attention half: gradient rows in window order (zero rows for the padding tokens).  bf16: the LayerNorm backward
-        # that produces dx1 writes the scaled window-ordered copy itself (persistent buffer, padding rows zeroed once)
-        if dt == BF16:
-            dyw = ops.window_rows_buffer(Tw, Cd, geo, x)
-            dx1, dn2w, dn2b = ops.ln_bwd_dual(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dx2, dyw, geo, sd1, HW)
-            dy1, dy1t = operand(dyw), operand(dyw, orient=1)
-        else:
-            dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
-            dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
-        dbp = torch.empty(Cd, **f32)
-        dWp = torch.empty(Cd, Cd, **f32)
-        wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))
-        do = torch.empty(Tw, Cd, dtype=dt, device=dev)
-        gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
-        dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo, *ctx.drop)
-        dbqkv = torch.empty(3 * Cd, **f32)
-        dWqkv = torch.empty(3 * Cd, Cd, **f32)
-        wg.run(lambda: gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv),
-                            3 * Cd, Cd, Tw, dev))
-        dxw = torch.empty(Tw, Cd, dtype=dt, device=dev)
-        gemm(operand(dqkv), w_dgrad(qkvw, dt), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
-        dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
-        wg.__exit__()
+        with _WgradFork(dev) as wg:
+            # ---- MLP half
+            # stochastic-depth scale of the incoming gradient rows: large maps never materialise sd2 * dx2 — the dgrad GEMM scales its
+            # output rows in the epilogue and the weight-gradient GEMM keeps every split-K slab inside one sample and scales whole
+            # partials in its reduce (MsuOperand.rowscale); small maps (few tokens per sample) gather the scaled rows once
+            fused_sd = dt == BF16 and sd2 is not None and HW >= 4096 and HW % 64 == 0
+            if fused_sd:
+                dy2, dy2t = operand(dx2), operand(dx2, orient=1, rowscale=sd2, rps=HW)
+            else:
+                dy2, dy2t = rows(dx2, T, Cd, dt, rowscale=sd2, rps=HW)
+            # bias gradients ride along with the weight-gradient GEMMs (MsuEpilogue.colsum)
+            db2, dW2 = ops.grad_out(f2b), ops.grad_out(f2w)
+            wg.run(lambda: gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev))
+            dh = torch.empty(T, hid, dtype=dt, device=dev)
+            gemm(dy2, w_dgrad(f2w, dt),
+                 epilogue(dh, H=h, ldh=hid, rowscale=sd2 if fused_sd else None, rps=HW if fused_sd else 0), T, hid, Cd, dev)
+            db1, dW1 = ops.grad_out(f1b), ops.grad_out(f1w)
+            wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))
+            dxn = torch.empty(T, Cd, dtype=dt, device=dev)
+            gemm(operand(dh), w_dgrad(f1w, dt), epilogue(dxn), T, Cd, hid, dev)
+            # ---- attention half: gradient rows in window order (zero rows for the padding tokens).  bf16: the LayerNorm backward
+            # that produces dx1 writes the scaled window-ordered copy itself (persistent buffer, padding rows zeroed once)
+            if dt == BF16:
+                dyw = ops.window_rows_buffer(Tw, Cd, geo, x)
+                dx1, dn2w, dn2b = ops.ln_bwd_dual(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dx2, dyw, geo, sd1, HW)
+                dy1, dy1t = operand(dyw), operand(dyw, orient=1)
+            else:
+                dx1, dn2w, dn2b, _ = ops.ln_bwd(dxn, x1, n2w, n2b, mean2, rstd2, T, Cd, dres=dx2)
+                dy1, dy1t = rows(dx1, Tw, Cd, dt, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW)
+            dbp, dWp = ops.grad_out(projb), ops.grad_out(projw)
+            wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))
+            do = torch.empty(Tw, Cd, dtype=dt, device=dev)
+            gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
+            dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo, *ctx.drop, table=table)
+            dbqkv, dWqkv = ops.grad_out(qkvb), ops.grad_out(qkvw)
+            wg.run(lambda: gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv),
+                                3 * Cd, Cd, Tw, dev))
+            dxw = torch.empty(Tw, Cd, dtype=dt, device=dev)
+            gemm(operand(dqkv), w_dgrad(qkvw, dt), epilogue(dxw), Tw, Cd, 3 * Cd, dev)
+            dx, dn1w, dn1b, _ = ops.ln_bwd(dxw, x, n1w, n1b, mean1, rstd1, T, Cd, dres=dx1, dy_map=MAP_WINDOW, geo=geo)
         return (dx.view(B, H, W, Cd), dn1w, dn1b, dWqkv, dbqkv, dWp, dbp, dtable, dn2w, dn2b, dW1, db1, dW2, db2,
                 None, None, None, None, None, None, None, None, None)
 
@@ -357,24 +351,25 @@ class PatchEmbedFn(Function):
         y = torch.empty(T, E, dtype=dtype, device=dev)
         gemm(operand(patches), operand(w64), epilogue(y, bias=pb), T, E, 64, dev)
         out, mean, rstd = ops.ln_fwd(y, nw, nb, T, E)
-        ctx.save_for_backward(patches, y, nw, nb, mean, rstd)
+        ctx.save_for_backward(patches, y, nw, nb, mean, rstd, pw, pb)
         ctx.E = E
         return out.view(B, (S // 4) ** 2, E)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        patches, y, nw, nb, mean, rstd = ctx.saved_tensors
+        patches, y, nw, nb, mean, rstd, pw, pb = ctx.saved_tensors
         E = ctx.E
         dev = y.device
         T = y.shape[0]
         dout = _c(dout).view(T, E)
         with _WgradFork(dev):
             dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, T, E)
-            dpb = torch.empty(E, dtype=torch.float32, device=dev)
+            dpb = ops.grad_out(pb)
             dW64 = torch.empty(E, 64, dtype=torch.float32, device=dev)
             gemm(operand(dy, orient=1), operand(patches, orient=1), epilogue(dW64, out_f32=True, colsum=dpb), E, 64, T, dev)
-        dpw = ops.prep_weight(6, dW64, E, 48, (E, 3, 4, 4), torch.float32)
+        dpw = ops.grad_out(pw, (E, 3, 4, 4))
+        ops.prep_weight_into(6, dW64, dpw, E, 48)
         return None, dpw, dpb, dnw, dnb, None
 
 
@@ -405,7 +400,7 @@ class PatchMergeFn(Function):
         Cd = x.shape[-1]
         Tm = B * (H // 2) * (W // 2)
         dy = _c(dy).view(Tm, 2 * Cd)
-        drw = torch.empty(2 * Cd, 4 * Cd, dtype=torch.float32, device=dev)
+        drw = ops.grad_out(rw)
         with _WgradFork(dev) as wg:
             wg.run(lambda: gemm(operand(dy, orient=1), operand(xm, orient=1), epilogue(drw, out_f32=True), 2 * Cd, 4 * Cd, Tm, dev))
             dxm = torch.empty(Tm, 4 * Cd, dtype=dt, device=dev)
@@ -447,7 +442,7 @@ class PatchExpandFn(Function):
         with _WgradFork(dev) as wg:
             dy, dnw, dnb, _ = ops.ln_bwd(dout, y, nw, nb, mean, rstd, 4 * T, c2, dx_map=MAP_UNSHUFFLE, geo=geo,
                                          dx_shape=(T, 2 * Cd))
-            dew = torch.empty(2 * Cd, Cd, dtype=torch.float32, device=dev)
+            dew = ops.grad_out(ew)
             wg.run(lambda: gemm(operand(dy, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 2 * Cd, Cd, T, dev))
             dx = torch.empty(T, Cd, dtype=dt, device=dev)
             gemm(operand(dy), w_dgrad(ew, dt), epilogue(dx), T, Cd, 2 * Cd, dev)
@@ -468,19 +463,18 @@ class ConcatLinearFn(Function):
         y = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(x.view(T, Cd), t2=skip.view(T, Cd), ld2=Cd, k_split=Cd), w_fwd(w, dt), epilogue(y, bias=b),
              T, Cd, 2 * Cd, dev)
-        ctx.save_for_backward(x, skip, w)
+        ctx.save_for_backward(x, skip, w, b)
         return y.view(x.shape[0], -1, Cd)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, skip, w = ctx.saved_tensors
+        x, skip, w, b = ctx.saved_tensors
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
         T = x.numel() // Cd
         dy = _c(dy).view(T, Cd)
-        db = torch.empty(Cd, dtype=torch.float32, device=dev)
-        dw = torch.empty(Cd, 2 * Cd, dtype=torch.float32, device=dev)
+        db, dw = ops.grad_out(b), ops.grad_out(w)
 
         def wgrads():
             gemm(operand(dy, orient=1), operand(x.view(T, Cd), orient=1), epilogue(dw, ldc=2 * Cd, out_f32=True, colsum=db),
@@ -551,14 +545,14 @@ class HeadFn(Function):
         gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
         owv = _al(_c(ow).view(E))
         logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
-        ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd)
+        ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd, c1b, c2b)
         ctx.cfg = (B, r, x.shape, ow.shape)
         return logits.view(B, 1, S, S)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dlogits):
-        x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd = ctx.saved_tensors
+        x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd, c1b, c2b = ctx.saved_tensors
         B, r, xshape, owshape = ctx.cfg
         dev, dt = x2d.device, x2d.dtype
         T, E = x2d.shape
@@ -569,42 +563,40 @@ class HeadFn(Function):
         f32 = dict(dtype=torch.float32, device=dev)
         wd = dt if dt == BF16 else torch.float32
         dl = _c(dlogits).view(Mp)
-        wg = _WgradFork(dev)
-        wg.__enter__()
-        dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
-        # conv2 (weight gradients on the side stream: they fill the tails of the dgrad convolutions)
-        dc2b = torch.empty(E, **f32)
-        dw2r = torch.empty(E, 9 * E, **f32)
-        dc2w = torch.empty(E, E, 3, 3, **f32)
+        with _WgradFork(dev) as wg:
+            dz2, dnw, dnb, dow = ops.ln_bwd(dl, z2, nw, nb, mean, rstd, Mp, E, dotw=owv)
+            # conv2 (weight gradients on the side stream: they fill the tails of the dgrad convolutions)
+            dc2b = ops.grad_out(c2b)
+            dw2r = torch.empty(E, 9 * E, **f32)
+            dc2w = ops.grad_out(c2w)
 
-        def wgrad2():
-            gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
-                 epilogue(dw2r, out_f32=True, colsum=dc2b), E, 9 * E, Mp, dev)
-            ops.prep_weight_into(4, dw2r, dc2w, E, E)
-        wg.run(wgrad2)
-        w2f = shadow(c2w, 3, E, E, (E, 9 * E), wd)
-        dz1 = torch.empty(Mp, E, dtype=dt, device=dev)
-        gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
-        # conv1
-        dc1b = torch.empty(E, **f32)
-        dw1r = torch.empty(E, 9 * E, **f32)
-        dc1w = torch.empty(E, E, 3, 3, **f32)
+            def wgrad2():
+                gemm(operand(dz2, orient=1), operand(a1, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+                     epilogue(dw2r, out_f32=True, colsum=dc2b), E, 9 * E, Mp, dev)
+                ops.prep_weight_into(4, dw2r, dc2w, E, E)
+            wg.run(wgrad2)
+            w2f = shadow(c2w, 3, E, E, (E, 9 * E), wd)
+            dz1 = torch.empty(Mp, E, dtype=dt, device=dev)
+            gemm(operand(dz2, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2f), epilogue(dz1, H=z1, ldh=E), Mp, E, 9 * E, dev)
+            # conv1
+            dc1b = ops.grad_out(c1b)
+            dw1r = torch.empty(E, 9 * E, **f32)
+            dc1w = ops.grad_out(c1w)
 
-        def wgrad1():
-            gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
-                 epilogue(dw1r, out_f32=True, colsum=dc1b), E, 9 * E, Mp, dev)
-            ops.prep_weight_into(4, dw1r, dc1w, E, E)
-        wg.run(wgrad1)
-        w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
-        # conv1 dgrad (x gelu'(h0)) written by the GEMM epilogue in the inverse depth-to-space layout [T, 16E]
-        dh0 = torch.empty(T, 16 * E, dtype=dt, device=dev)
-        gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f),
-             epilogue(dh0, ldc=16 * E, H=h0, ldh=E, map=MAP_UNSHUFFLE, geo=sgeo), Mp, E, 9 * E, dev)
-        dew = torch.empty(16 * E, E, **f32)
-        wg.run(lambda: gemm(operand(dh0, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev))
-        dx = torch.empty(T, E, dtype=dt, device=dev)
-        gemm(operand(dh0), w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
-        wg.__exit__()
+            def wgrad1():
+                gemm(operand(dz1, orient=1), operand(a0, ld=E, orient=1, map=MAP_CONV3, geo=cgeo),
+                     epilogue(dw1r, out_f32=True, colsum=dc1b), E, 9 * E, Mp, dev)
+                ops.prep_weight_into(4, dw1r, dc1w, E, E)
+            wg.run(wgrad1)
+            w1f = shadow(c1w, 3, E, E, (E, 9 * E), wd)
+            # conv1 dgrad (x gelu'(h0)) written by the GEMM epilogue in the inverse depth-to-space layout [T, 16E]
+            dh0 = torch.empty(T, 16 * E, dtype=dt, device=dev)
+            gemm(operand(dz1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1f),
+                 epilogue(dh0, ldc=16 * E, H=h0, ldh=E, map=MAP_UNSHUFFLE, geo=sgeo), Mp, E, 9 * E, dev)
+            dew = ops.grad_out(ew)
+            wg.run(lambda: gemm(operand(dh0, orient=1), operand(x2d, orient=1), epilogue(dew, out_f32=True), 16 * E, E, T, dev))
+            dx = torch.empty(T, E, dtype=dt, device=dev)
+            gemm(operand(dh0), w_dgrad(ew, dt), epilogue(dx), T, E, 16 * E, dev)
         return (dx.view(xshape), dew, dc1w, dc1b, dc2w, dc2b, dnw, dnb, dow.view(owshape), None, None)
 
 

@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import os
 import sys
-import warnings
 import weakref
 
 import torch
@@ -69,8 +68,9 @@ class SwinTransformerBlock(nn.Module):
                                  nn.Dropout(dropout))
         self.attn_p = float(attention_dropout)
         if dropout > 0:
-            warnings.warn("MLP / projection dropout (DROP_RATE, 0.0 in config.yaml) is not fused yet and runs with p=0 "
-                          "(attention dropout and stochastic depth are supported); see DESIGN.md", stacklevel=3)
+            raise NotImplementedError("MLP / projection dropout (MODEL.DROP_RATE > 0; config.yaml:22 uses 0.0) is not built into the "
+                                      "fc1 / fc2 / proj epilogues: refusing to train a different model silently "
+                                      "(attention dropout and stochastic depth are supported)")
 
     def forward(self, x):  # x [B, H, W, C]
         B, H, W, _ = x.shape
@@ -234,7 +234,10 @@ class MSUNetSys(nn.Module):
         self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
         pr = self.patch_embed.patches_resolution
         self.patches_resolution = pr
-        self.pos_drop = nn.Dropout(p=drop_rate)
+        if drop_rate > 0:
+            raise NotImplementedError("MODEL.DROP_RATE > 0 (pos_drop / MLP / projection dropout, network/model_parts.py:606, 779) is "
+                                      "not built: config.yaml:22 uses 0.0; attention dropout and stochastic depth are supported")
+        self.pos_drop = nn.Dropout(p=drop_rate)          # p == 0: the identity (kept for the module tree)
         dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
         common = dict(window_size=window_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
                       attn_drop=attn_drop_rate, norm_layer=norm_layer, use_checkpoint=use_checkpoint)

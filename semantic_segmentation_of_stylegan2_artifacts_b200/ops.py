@@ -108,6 +108,52 @@ def _off_path(fn, *keep):
         fn()
 
 
+# ----------------------------------------------------------------------------------------------
+# Gradient slots: where a parameter's gradient should be WRITTEN by the kernel that produces it.  dp.DataParallelB200 registers
+# one fp32 view of its flat all-reduce bucket per parameter (keyed by the parameter's data pointer); the backward Functions ask
+# `grad_out(param, shape)` instead of torch.empty, so the weight-gradient GEMM / reduce writes straight into the bucket and the
+# per-parameter copy into it disappears.  A slot is handed out at most once per backward pass and only while the parameter has no
+# accumulated .grad (shared weights and gradient accumulation get private tensors and autograd adds them up as usual).
+# ----------------------------------------------------------------------------------------------
+_grad_slots: dict = {}      # param.data_ptr() -> [view, weakref(param), generation last handed out]
+_grad_gen = [0]
+
+
+def register_grad_slots(slots: dict) -> None:
+    """slots: {parameter: fp32 tensor view with the parameter's numel}.  Replaces the registrations of those parameters."""
+    import weakref
+    mine = {id(prm) for prm in slots}
+    for key in [k for k, e in _grad_slots.items() if e[1]() is None or id(e[1]()) in mine]:
+        del _grad_slots[key]                    # parameters may have moved (data re-pointed at a flat buffer): re-key them
+    for prm, view in slots.items():
+        _grad_slots[prm.data_ptr()] = [view, weakref.ref(prm), -1]
+
+
+def clear_grad_slots(params=None) -> None:
+    if params is None:
+        _grad_slots.clear()
+    else:
+        for prm in params:
+            _grad_slots.pop(prm.data_ptr(), None)
+
+
+def next_grad_pass() -> None:
+    """Called once per optimisation step (after the gradients were consumed): slots may be handed out again."""
+    _grad_gen[0] += 1
+
+
+def grad_out(param: torch.Tensor, shape=None) -> torch.Tensor:
+    """fp32 output tensor for the gradient of `param` (shape defaults to the parameter's)."""
+    shape = tuple(param.shape) if shape is None else tuple(shape)
+    ent = _grad_slots.get(param.data_ptr())
+    if ent is not None and ent[2] != _grad_gen[0]:
+        prm = ent[1]()
+        if prm is not None and prm.grad is None and ent[0].numel() == param.numel() and ent[0].device == param.device:
+            ent[2] = _grad_gen[0]
+            return ent[0].view(shape)
+    return torch.empty(shape, dtype=torch.float32, device=param.device)
+
+
 PROF = None  # bench.py / tools set this to a list to collect (tag, start_event, end_event, bytes, flops) per launch
 
 
@@ -192,9 +238,8 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
                                mean.data_ptr(), rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), rows, Cdim, dy_map,
                                dx_map, None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), part.data_ptr(),
                                L.stream_ptr()), "msu_ln_bwd")
-    dg = torch.empty(Cdim, dtype=torch.float32, device=dev)
-    db = torch.empty(Cdim, dtype=torch.float32, device=dev)
-    dw = torch.empty(Cdim, dtype=torch.float32, device=dev) if dotw is not None else None
+    dg, db = grad_out(gamma), grad_out(beta)
+    dw = grad_out(dotw) if dotw is not None else None
     _off_path(lambda: L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), L.ptr(dw), 0,
                                                           L.stream_ptr()), "msu_ln_param_reduce"), part)
     _p1(e0, (rows, Cdim, 0, "ln_bwd" + ("_dot" if dotw is not None else "") + ("_res" if dres is not None else "")),
@@ -230,8 +275,7 @@ def ln_bwd_dual(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows
                                     rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), dxw.data_ptr(), rows, Cdim,
                                     C.cast(g, C.c_void_p), L.ptr(rowscale), int(rps), part.data_ptr(), L.stream_ptr()),
             "msu_ln_bwd_dual")
-    dg = torch.empty(Cdim, dtype=torch.float32, device=dev)
-    db = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    dg, db = grad_out(gamma), grad_out(beta)
     _off_path(lambda: L.check(L.lib().msu_ln_param_reduce(part.data_ptr(), P, Cdim, dg.data_ptr(), db.data_ptr(), None, 0,
                                                           L.stream_ptr()), "msu_ln_param_reduce"), part)
     _p1(e0, (rows, Cdim, 0, "ln_bwd_dual"), (dy.numel() + 4 * rows * Cdim) * x.element_size())
@@ -257,8 +301,8 @@ def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, 
     return o
 
 
-def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 0.0, seed=None):
-    """Returns (dqkv, dtable[169, nH])."""
+def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 0.0, seed=None, table=None):
+    """Returns (dqkv, dtable[169, nH]).  `table`: the bias-table parameter (its gradient slot is used when one is registered)."""
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
     gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
@@ -268,7 +312,7 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
                                     dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p), float(p_drop),
                                     L.ptr(seed), L.stream_ptr()), "msu_winattn_bwd")
-    dtable = torch.empty(169, nH, dtype=torch.float32, device=dev)
+    dtable = grad_out(table, (169, nH)) if table is not None else torch.empty(169, nH, dtype=torch.float32, device=dev)
     _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
                               "msu_relbias_reduce"), part)
     _p1(e0, (n_windows, nH, 0, "winattn_bwd"), (2 * qkv.numel() + 2 * o.numel()) * qkv.element_size(),

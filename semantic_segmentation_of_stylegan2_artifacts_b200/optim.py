@@ -38,6 +38,10 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False))
         self._layout = None      # cached table / block maps for the current set of parameters with gradients
         self._chunk = None
+        # torch.amp.GradScaler protocol (trainer.py:182, 314-316): the scaler hands its scale and the inf flag over as
+        # `self.grad_scale` / `self.found_inf` instead of unscaling every gradient in a separate pass; the kernel multiplies
+        # by 1/scale while it reads the gradient
+        self._step_supports_amp_scaling = True
 
     # ------------------------------------------------------------------
     def _build(self):
@@ -111,6 +115,10 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        grad_scale, found_inf = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
+        if found_inf is not None and float(found_inf.item()) != 0.0:
+            return loss          # overflow: skip the step and its step count, as GradScaler._maybe_opt_step does for stock optimizers
+        inv_scale = None if grad_scale is None else (1.0 / grad_scale.detach().double()).float().reshape(1)
         lay = self._layout
         live = [p for group in self.param_groups for p in group["params"] if p.grad is not None]
         if lay is None or len(live) != len(lay["ids"]) or any(id(p) != i for p, i in zip(live, lay["ids"])):
@@ -156,7 +164,7 @@ class FusedAdamW(torch.optim.Optimizer):
         ev.record()
         lay["ev"][k] = ev
         L.check(L.lib().msu_adamw_step(lay["devt"][k].data_ptr(), lay["bt"].data_ptr(), lay["bc"].data_ptr(),
-                                       int(lay["bt"].numel()), None, None, L.stream_ptr()), "msu_adamw_step")
+                                       int(lay["bt"].numel()), L.ptr(inv_scale), None, L.stream_ptr()), "msu_adamw_step")
         # the kernel wrote through raw pointers: bump the autograd version counters so that everything keyed on them
         # (the bf16 weight shadows of functional.shadow, saved-tensor checks) sees the update
         torch.autograd.graph.increment_version(plist)

@@ -74,6 +74,63 @@ def test_signatures_match_reference(built):
     assert list(inspect.signature(VF.atrifact_prediction).parameters) == ["model", "testloader", "device", "img_size"]
 
 
+def _reference_dir():
+    for d in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(d, "network", "MSUNet.py")):
+            return d
+    return None
+
+
+@pytest.mark.skipif(_reference_dir() is None, reason="no reference checkout (/root/reference or baseline/_ref)")
+def test_signatures_match_the_reference_sources(built):
+    """Where the reference is present its own sources are the authority: names, order and defaults of every public callable of
+    the boundary are read from network/MSUNet.py, loss/DynamicLoss.py and scripts/validation_functions.py with `ast`
+    (importing validation_functions needs medpy) and compared with this package's."""
+    import ast
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.MSUNet import MSUNet
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    from semantic_segmentation_of_stylegan2_artifacts_b200.scripts import validation_functions as VF
+    ref = _reference_dir()
+
+    def ref_sig(rel, qual):
+        tree = ast.parse(open(os.path.join(ref, rel)).read())
+        scope = tree.body
+        for part in qual.split("."):
+            node = next(n for n in scope if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name == part)
+            scope = getattr(node, "body", [])
+        a = node.args
+        names = [x.arg for x in a.args]
+        defaults = [None] * (len(names) - len(a.defaults)) + [ast.literal_eval(d) if not isinstance(d, (ast.Attribute, ast.Name)) else "<expr>"
+                                                                for d in a.defaults]
+        return list(zip(names, defaults))
+
+    def my_sig(fn):
+        out = []
+        for k, v in inspect.signature(fn).parameters.items():
+            if v.kind in (v.VAR_KEYWORD, v.VAR_POSITIONAL):
+                continue
+            out.append((k, None if v.default is inspect._empty else v.default))
+        return out
+
+    def same(mine, theirs, extra_ok=()):
+        mine = [m for m in mine if m[0] not in extra_ok]
+        assert [m[0] for m in mine] == [t[0] for t in theirs], (mine, theirs)
+        for (k, dm), (_, dt) in zip(mine, theirs):
+            if dt != "<expr>":
+                assert dm == dt or (dm is None and dt is None), (k, dm, dt)
+
+    same(my_sig(MSUNet.__init__), ref_sig("network/MSUNet.py", "MSUNet.__init__"))
+    same(my_sig(MSUNet.forward), ref_sig("network/MSUNet.py", "MSUNet.forward"))
+    for meth in ("freeze_encoder", "unfreeze_encoder", "load_segface_weight", "load_IMAGENET1K_weight"):
+        same(my_sig(getattr(MSUNet, meth)), ref_sig("network/MSUNet.py", "MSUNet." + meth))
+    same(my_sig(MSUNetSys.__init__), ref_sig("network/model_parts.py", "MSUNetSys.__init__"), extra_ok=("run_dead_branches",))
+    same(my_sig(DynamicLoss.__init__), ref_sig("loss/DynamicLoss.py", "DynamicLoss.__init__"))
+    same(my_sig(DynamicLoss.forward), ref_sig("loss/DynamicLoss.py", "DynamicLoss.forward"))
+    for fn in ("validation_loss", "calculate_metrics", "calculate_metrics_real", "calculate_metrics_fake", "atrifact_prediction"):
+        same(my_sig(getattr(VF, fn)), ref_sig("scripts/validation_functions.py", fn))
+
+
 def test_errors_and_no_cpu_fallback(built):
     from types import SimpleNamespace as NS
     from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
@@ -245,7 +302,9 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1, out.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference's own modules when baseline/_ref holds them (tools/install_reference.py), else the oracle port
+    want_kind = "reference" if os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "network", "model_parts.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     ours = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
     assert (d["metric"], d["unit"]) == (ours["metric"], ours["unit"])

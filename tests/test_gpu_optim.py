@@ -202,3 +202,31 @@ def test_graphed_step_matches_eager_training():
         step(batches[0][0][:1], batches[0][1][:1])
     with pytest.raises(RuntimeError):
         GraphedStep(ma, crit, batches[0][0].cpu(), batches[0][1].cpu())
+
+
+def test_fused_adamw_under_grad_scaler_matches_torch():
+    """trainer.py:182, 314-316: `scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()`.  FusedAdamW takes the
+    scale through the GradScaler protocol (`grad_scale` / `found_inf`: 1/scale is applied inside the kernel, an overflow step is
+    skipped together with its step count) and must track stock torch.optim.AdamW driven by its own scaler, overflow included."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200.optim import FusedAdamW
+    pa, _ = _params(3)
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedAdamW(pa, lr=2e-3, weight_decay=0.01)
+    ob = torch.optim.AdamW(pb, lr=2e-3, weight_decay=0.01, foreach=False, fused=False)
+    sa, sb = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for step in range(5):
+        torch.manual_seed(7 + step)
+        ws = [torch.randn_like(p) for p in pa]
+        for ps, opt, sc in ((pa, oa, sa), (pb, ob, sb)):
+            opt.zero_grad(set_to_none=True)
+            loss = sum((p * w).sum() + (p * p).sum() for p, w in zip(ps, ws))
+            sc.scale(loss).backward()
+            if step == 2:
+                ps[0].grad[0, 0] = float("inf")          # overflow: both must skip this step and halve the scale
+            sc.step(opt)
+            sc.update()
+    torch.cuda.synchronize()
+    assert sa.get_scale() == sb.get_scale() == 512.0
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=3e-6, atol=1e-7), float((a - b).abs().max())
+    assert all(float(s["step"]) == 4.0 for s in oa.state_dict()["state"].values())
