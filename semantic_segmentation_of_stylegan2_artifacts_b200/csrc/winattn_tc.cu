@@ -75,7 +75,8 @@ constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 102
 //   MMA 2:  O_w[128 x 32] = P[:, own keys] V_w for w = a, b into TMEM columns [32 w, 32 w + 32): rows of the other
 //           window hold unused values; V is read MN-major straight from its TMA tile (no transpose)
 __global__ void __launch_bounds__(128, 3)
-winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
+winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm4,
+                      const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
                       int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -117,6 +118,15 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     auto issue_loads = [&](int64_t pair, int buf) {
         uint8_t* q = sOps + buf * AT_OPS_BYTES;
         mbar_arrive_expect_tx(&bar_load[buf], 6 * 4096);
+        if (pair + 1 < n_pairs) {
+            // ONE box for the unit: [32 channels] x [64 rows] x [2 windows, 49 rows apart] x [q, k, v, C channels apart] lands as
+            // Q_a Q_b K_a K_b V_a V_b (4 KB each).  An SM's TMA unit serves a box in a fixed ~222 clk up to ~12 KB (then ~57 B/clk):
+            // six 4 KB boxes cost 1330 clk per unit, one 24 KB box ~430.  Rows 49..63 of a window's tile are the next window's
+            // first rows (finite values that meet exact zeros in P); only the LAST pair would read past the tensor, so it keeps
+            // the bounds-checked 2-D boxes below.
+            tma_load_4d(q, &tm4, &bar_load[buf], h * HD, 0, (int)(pair * 2), 0);
+            return;
+        }
         const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
         tma_load_2d(q, &tm, &bar_load[buf], h * HD, r0);
         tma_load_2d(q + 4096, &tm, &bar_load[buf], h * HD, r1);
@@ -228,8 +238,10 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         }
         // O row -> staging box of its window ([49 x 32] bf16, 64B swizzle) in the P tile (MMA 2 has consumed it); the
         // two boxes leave as TMA stores: per-thread 64 B row stores were 32 separate lines per instruction
-        {
-            uint8_t* orow = sP + half * 4096 + i * 64;
+        if (i < WT) {
+            // staging box [2 windows][49 rows][32] (64 B rows, 64B swizzle on the box-row index): the pair leaves as ONE TMA store
+            const int R = half * WT + i;
+            uint8_t* orow = sP + R * 64;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 uint4 v;
@@ -237,15 +249,14 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
                 v.y = pk2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
                 v.z = pk2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
                 v.w = pk2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-                *reinterpret_cast<uint4*>(orow + ((c ^ ((i >> 1) & 3)) << 4)) = v;
+                *reinterpret_cast<uint4*>(orow + ((c ^ ((R >> 1) & 3)) << 4)) = v;
             }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();   // TMEM columns are free for the next unit; the staged rows are complete
         if (tid == 0) {
-            for (int w = 0; w < 2; w++)
-                if (pair * 2 + w < n_windows) tma_store_2d(sP + w * 4096, &tmO, h * HD, (int)((pair * 2 + w) * WT));
+            tma_store_3d(sP, &tmO, h * HD, 0, (int)(pair * 2));      // a window index past the end (odd count) is clipped by TMA
             tma_store_commit();
         }
     }
@@ -256,22 +267,31 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     }
 }
 
+// Window-pair tensor map over a window-ordered [n_windows * 49, parts * C] bf16 matrix:
+//   dims  (channel, row in window, window, part)   sizes (C, box_rows, n_windows, parts)
+//   strides        (row pitch, 49 rows, C channels) box   (32, box_rows, 2, parts)
+// box_rows = 64: operand loads (the 15 extra rows of a window's tile are the next window's first rows — the caller must not
+// use this map for the LAST pair, which would run past the allocation; out-of-range window indices are zero-filled);
+// box_rows = 49: stores of exactly the windows' rows (out-of-range windows are clipped).  parts = 1 drops the last dimension.
+static bool make_pair_map(CUtensorMap* tm, const void* ptr, int64_t n_windows, int C, int parts, int box_rows) {
+    const cuuint64_t pitch = (cuuint64_t)parts * C * 2;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)box_rows, (cuuint64_t)n_windows, (cuuint64_t)parts};
+    cuuint64_t gstr[3] = {pitch, (cuuint64_t)WT * pitch, (cuuint64_t)C * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 2, (cuuint32_t)parts};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return tc_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, parts > 1 ? 4 : 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // returns 0 launched, 1 unsupported
 int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15)) return 1;
     const int64_t rows = n_windows * WT;
-    CUtensorMap tm, tmO;
-    {   // output [rows, C], box = one window's [49 x 32] head slice
-        cuuint64_t od[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-        cuuint64_t os[1] = {(cuuint64_t)C * 2};
-        cuuint32_t ob[2] = {32, (cuuint32_t)WT};
-        cuuint32_t oe[2] = {1, 1};
-        if (tc_get_encode()(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, O, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return 1;
-    }
+    CUtensorMap tm, tm4, tmO;
+    if (!make_pair_map(&tmO, O, n_windows, C, 1, WT) || !make_pair_map(&tm4, qkv, n_windows, C, 3, 64)) return 1;
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
     cuuint32_t box[2] = {32, 64};
@@ -290,7 +310,7 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     // whole waves: 3 CTAs per SM are resident; a few CTAs more would start late and double the tail
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3) / nH));
     dim3 grid(gx, nH);
-    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tmO, bias, n_windows, nH, g, ad);
+    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tm4, tmO, bias, n_windows, nH, g, ad);
     count_launch();
     return check_launch("winattn_fwd_tc");
 }
@@ -318,6 +338,7 @@ constexpr int AB_SMEM = 2 * AB_X + 2 * AB_OPS + AT_BIAS_BYTES + 64 + 1024;
 // so every thread drains its own key row of dV, dK and its query row of dQ — a balanced epilogue.
 __global__ void __launch_bounds__(128, 2)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmQKV4, const __grid_constant__ CUtensorMap tmDO3,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
                       int64_t n_windows, int nH, WinGeo g, AttnDrop ad, long long* trace) {
 #define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
@@ -364,6 +385,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     auto issue_loads = [&](int64_t pair, int buf) {
         uint8_t* q = sOps + buf * AB_OPS;
         mbar_arrive_expect_tx(&bar_load[buf], 8 * 4096);
+        if (pair + 1 < n_pairs) {   // two boxes per unit instead of eight (see the forward kernel); the last pair stays bounds-checked
+            tma_load_4d(q, &tmQKV4, &bar_load[buf], h * HD, 0, (int)(pair * 2), 0);
+            tma_load_3d(q + 3 * AB_TILE, &tmDO3, &bar_load[buf], h * HD, 0, (int)(pair * 2));
+            return;
+        }
         const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
         tma_load_2d(q, &tmQKV, &bar_load[buf], h * HD, r0);
         tma_load_2d(q + 4096, &tmQKV, &bar_load[buf], h * HD, r1);
@@ -518,20 +544,21 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             tc_ld32_nowait(lane_base + 64 + half * 32, reinterpret_cast<uint32_t*>(dkk));
             tc_ld32_nowait(lane_base + half * 32, reinterpret_cast<uint32_t*>(dvv));
             tc_ld_wait();
-            // rows -> staging boxes [window][dq | dk | dv][49 x 32] (64B swizzle) in the P / dS tiles (consumed by the
-            // MMAs above); they leave as six TMA stores instead of 32-line scattered stores per instruction
-            uint8_t* row = sXP + half * 3 * 4096 + i * 64;
+            // rows -> ONE staging box [dq | dk | dv][2 windows][49 rows][32] (64 B rows, 64B swizzle on the box-row index) in the
+            // P / dS tiles (consumed by the MMAs above): the unit's 18.4 KB of gradients leave as one TMA store
+            if (i < WT) {
+            const int R0 = half * WT + i, R1 = R0 + 2 * WT, R2 = R0 + 4 * WT;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const int sw = (c ^ ((i >> 1) & 3)) << 4;
-                *reinterpret_cast<uint4*>(row + sw) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
+                *reinterpret_cast<uint4*>(sXP + R0 * 64 + ((c ^ ((R0 >> 1) & 3)) << 4)) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
                     pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
                     pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
-                *reinterpret_cast<uint4*>(row + 4096 + sw) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
+                *reinterpret_cast<uint4*>(sXP + R1 * 64 + ((c ^ ((R1 >> 1) & 3)) << 4)) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
                     pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
                     pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
-                *reinterpret_cast<uint4*>(row + 8192 + sw) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
+                *reinterpret_cast<uint4*>(sXP + R2 * 64 + ((c ^ ((R2 >> 1) & 3)) << 4)) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
                     pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
+            }
             }
         }
         AT_TRACE(6);
@@ -539,10 +566,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
-            for (int w = 0; w < 2; w++)
-                if (pair * 2 + w < n_windows)
-                    for (int part = 0; part < 3; part++)
-                        tma_store_2d(sXP + (w * 3 + part) * 4096, &tmOut, part * C + h * HD, (int)((pair * 2 + w) * WT));
+            tma_store_4d(sXP, &tmOut, h * HD, 0, (int)(pair * 2), 0);     // a window index past the end (odd count) is clipped by TMA
             tma_store_commit();
         }
         AT_TRACE(7);
@@ -581,9 +605,10 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15)) return 1;
-    CUtensorMap tmQKV, tmDO, tmOut;
+    CUtensorMap tmQKV, tmDO, tmQKV4, tmDO3, tmOut;
     if (!make_attn_map(&tmQKV, qkv, n_windows * WT, 3 * C) || !make_attn_map(&tmDO, dO, n_windows * WT, C) ||
-        !make_attn_map(&tmOut, dqkv, n_windows * WT, 3 * C, WT))
+        !make_pair_map(&tmQKV4, qkv, n_windows, C, 3, 64) || !make_pair_map(&tmDO3, dO, n_windows, C, 1, 64) ||
+        !make_pair_map(&tmOut, dqkv, n_windows, C, 3, WT))
         return 1;
     static PerDeviceOnce attr;
     if (attr.need()) {
@@ -600,7 +625,7 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         cudaMalloc(&trace_buf, trace_n * sizeof(long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
     }
-    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
+    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmQKV4, tmDO3, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
                                                     trace_on ? trace_buf : nullptr);
     if (trace_on) {   // debug only: synchronous dump of the per-unit phase timeline of two CTAs
         long long* host = (long long*)malloc(trace_n * sizeof(long long));

@@ -376,13 +376,21 @@ class ShardedAdamW:
             if b.flat.is_cuda and torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("ShardedAdamW.prepare_step() must be called before capturing / replaying a step")
             self.prepare_step()
+        lo, S = sh["lo"], sh["S"]
         if dp._backend == "nccl":
             dist.reduce_scatter_tensor(sh["gshard"], b.flat, op=dist.ReduceOp.AVG, group=dp.pg)
+            self._apply(b)
+            dist.all_gather_into_tensor(sh["pflat"], sh["pflat"][lo:lo + S], group=dp.pg)
         else:
-            dist.reduce_scatter_tensor(sh["gshard"], b.flat, op=dist.ReduceOp.SUM, group=dp.pg)
-            sh["gshard"].div_(self.world)
-        self._apply(b)
-        dist.all_gather_into_tensor(sh["pflat"], sh["pflat"][sh["lo"]:sh["lo"] + sh["S"]], group=dp.pg)
+            # portable path (gloo, used by the host-logic tests on CPU and by the single-GPU two-process test): the same data
+            # movement expressed with all-reduce only, the one collective every backend implements for every device
+            dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=dp.pg)
+            torch.div(b.flat[lo:lo + S], self.world, out=sh["gshard"])
+            self._apply(b)
+            tmp = torch.zeros_like(sh["pflat"])
+            tmp[lo:lo + S].copy_(sh["pflat"][lo:lo + S])
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=dp.pg)
+            sh["pflat"].copy_(tmp)
 
     def _apply(self, b: _Bucket):
         """One `msu_adamw_step` launch over this bucket's shard segments (CUDA only: there is no CPU fallback)."""
@@ -427,8 +435,12 @@ class ShardedAdamW:
             sh = b.shard
             full = {}
             for key in ("m", "v"):
-                out = torch.empty(b.numel, dtype=torch.float32, device=b.flat.device)
-                dist.all_gather_into_tensor(out, sh[key], group=self.dp.pg)
+                out = torch.zeros(b.numel, dtype=torch.float32, device=b.flat.device)
+                if self.dp._backend == "nccl":
+                    dist.all_gather_into_tensor(out, sh[key], group=self.dp.pg)
+                else:
+                    out[sh["lo"]:sh["lo"] + sh["S"]].copy_(sh[key])
+                    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.dp.pg)
                 full[key] = out
             for p, off in zip(b.params, b.offsets):
                 if p in index:

@@ -1,0 +1,62 @@
+"""The multi-rank CUDA path on ONE GPU: two processes on cuda:0 over gloo (tests/_dp_gpu_worker.py).  Checks on hardware what
+tests/test_dp_gloo.py checks on the CPU with a toy module: the exchanged gradients of the real MS-UNet equal the single-process
+gradient of the global batch (stochastic depth on, injected noise), gradients are produced IN the bucket slices by the kernels
+(no per-parameter copies), and reduce-scatter -> msu_adamw_step on the shard -> all-gather equals the replicated fused AdamW."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import msunet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_ranks_on_one_gpu(tmp_path):
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    from semantic_segmentation_of_stylegan2_artifacts_b200.network.model_parts import MSUNetSys
+    out = str(tmp_path / "res.pt")
+    port = str(_free_port())
+    worker = os.path.join(ROOT, "tests", "_dp_gpu_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", port, out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=900) == 0
+    res = torch.load(out, weights_only=False)
+    dev = torch.device("cuda:0")
+    cfg = O.Cfg(img_size=64, **O.T32)
+    X, Y = O.make_inputs(cfg, 4, real_last=False)
+    noise = O.draw_sd_noise(cfg, 4, 0.2, seed=11)
+    for prec in ("fp32", "bf16"):
+        m = MSUNetSys(img_size=64, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], drop_path_rate=0.2)
+        m.load_state_dict(O.make_weights(cfg), strict=True)
+        m.set_precision(prec).to(dev).train()
+        m.inject_drop_path_noise(noise)
+        DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)(m(X.to(dev)), Y.to(dev)).backward()
+        r = res[prec]
+        live = {k: p.grad.cpu() for k, p in m.named_parameters() if p.grad is not None}
+        assert set(live) == set(r["grads"])
+        tol = 2e-4 if prec == "fp32" else 3e-2        # bf16: the two shards round their activations independently of the full batch
+        for k, g in live.items():
+            e = float((r["grads"][k] - g).abs().max() / g.abs().max().clamp_min(1e-20))
+            assert e < tol, (prec, k, e)
+        st = r["stats"]
+        assert len(r["buckets"]) >= 2
+        # the kernels wrote (almost) every gradient straight into its bucket slice: only the shared concat_back_dim weights,
+        # which autograd sums from several uses, are copied
+        assert st["direct"] > 10 * st["copied"] and st["copied"] <= 2 * 2 * 4, st
+        # sharded == replicated optimizer, parameter for parameter
+        for k, v in r["replicated"].items():
+            assert torch.allclose(r["sharded"][k].float(), v.float(), rtol=2e-5, atol=2e-6), (prec, k)
+        assert torch.allclose(r["shard_state"], r["repl_state"], rtol=2e-5, atol=1e-8)
