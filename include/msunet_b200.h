@@ -94,21 +94,22 @@ int msu_colsum(const MsuOperand* X, int64_t M, int64_t N, float* out, int accumu
  * in_map: NONE | MERGE (gathers 2x2 neighbours, C = 4*Cin);  out_map: NONE | WINDOW (rows are window-order
  * indices; absent rows are written as zeros — the unmasked zero padding of TV:...:152-156).
  * mean/rstd are indexed by LayerNorm row (source pixel for WINDOW).  If `dotw` != NULL the kernel writes
- * logits[row] = dot(LN(x), dotw) instead of Y (head LN + 1x1 conv, network/model_parts.py:475, 846).
+ * logits[row] = dot(LN(x), dotw) instead of Y (head LN + 1x1 conv, network/model_parts.py:475, 846) and
+ * dot_m2[row] = mean_c(gamma_c dotw_c x-hat_c), the one row reduction msu_ln_bwd then needs (C <= 768 bf16 / 384 fp32).
  * Replaces nn.LayerNorm at TV:...:453-454, network/model_parts.py:94, 224, 404, 475, 813, 827. */
 int msu_ln_fwd(int dtype, const void* X, const float* gamma, const float* beta, void* Y, float* mean,
                float* rstd, int64_t rows, int32_t C, int32_t in_map, int32_t out_map, const int32_t* geo,
-               const float* dotw, void* stream);
+               const float* dotw, float* dot_m2, void* stream);
 
 /* LayerNorm backward.  dY is read through `dy_map` (NONE, or WINDOW: gradient rows live in window order),
  * dX written through `dx_map` (NONE, MERGE scatter, or UNSHUFFLE: inverse depth-to-space).  dX = LN'(dY) + dRes (dRes optional).
  * partial: fp32 workspace [msu_ln_bwd_partial_rows(dtype,rows,C), 3, C] for deterministic dgamma/dbeta/(ddotw) reduction, finished by
- * msu_ln_param_reduce.  If dotw != NULL, dY is a per-row scalar (d logits) times dotw. */
+ * msu_ln_param_reduce.  If dotw != NULL, dY is a per-row scalar (d logits) times dotw and dot_m2 is the forward's output. */
 int msu_ln_bwd_partial_rows(int dtype, int64_t rows, int32_t C);
 int msu_ln_bwd(int dtype, const void* dY, const void* X, const float* gamma, const float* beta,
                const float* mean, const float* rstd, const void* dRes, void* dX, int64_t rows, int32_t C,
-               int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,
-               void* stream);
+               int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, const float* dot_m2,
+               float* partial, void* stream);
 /* As msu_ln_bwd (no row maps) and additionally dXw[pix_to_win(row)] = rowscale[row / rows_per_sample] * dX[row]: the gradient rows
  * of the attention projection in window order (backward of TV:models/swin_transformer.py:219-227 + stochastic depth) come out of
  * the LayerNorm backward that produces them.  Padding rows of dXw are never written: the caller zeroes them once. */

@@ -54,9 +54,9 @@ _SIGS = {
     "msu_gemm": [C.POINTER(MsuOperand), C.POINTER(MsuOperand), C.POINTER(MsuEpilogue), _I64, _I64, _I64, _P, _I64,
                  C.c_int, _P],
     "msu_colsum": [C.POINTER(MsuOperand), _I64, _I64, _P, C.c_int, _P, _I64, _P],
-    "msu_ln_fwd": [C.c_int, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
+    "msu_ln_fwd": [C.c_int, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
     "msu_ln_bwd_partial_rows": [C.c_int, _I64, _I32],
-    "msu_ln_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
+    "msu_ln_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "msu_ln_bwd_dual": [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P],
     "msu_ln_param_reduce": [_P, _I32, _I32, _P, _P, _P, C.c_int, _P],
     "msu_winattn_fwd": [C.c_int, _P, _P, _P, _I64, _I32, _P, C.c_float, _P, _P],

@@ -93,9 +93,205 @@ __device__ __forceinline__ float group_sum_u(float v, int lpr) {   // branch-fre
     return v;
 }
 
+// Forward: persistent warps.  Warp w walks super-groups w, w + P, ... of LN_RG row groups (rpw rows each); the 16 B loads of
+// the NEXT super-group are issued before the current one is reduced (register double buffer), so every warp keeps
+// LN_RG * NV * 512 B of loads in flight all the time instead of only during the first third of a short-lived block's life
+// (the one-shot version: 4.4 TB/s plain, 2.6 TB/s for the head's dot variant).  gamma / beta live in registers for
+// narrow rows.  DOT (head LayerNorm + 1x1 conv, network/model_parts.py:842-846) never forms y:
+//   logit = sum_c ((x_c - mu) rs gamma_c + beta_c) w_c = rs (sum_c x_c gw_c - mu G) + Bw,   gw = gamma w, G = sum gw, Bw = sum beta w
+// i.e. 3 FMAs per element on top of the statistics.
+constexpr int LN_RG = 2;
+template <typename T, int NV>
+struct LnGroup {
+    int64_t r[LN_RG], lr[LN_RG];
+    bool live[LN_RG];
+    uint4 xr[LN_RG][NV];
+};
+// window row -> pixel row with 32-bit arithmetic (row counts are far below 2^31; the 64-bit divisions of win_to_pix cost
+// ~100 instructions per row)
+__device__ __forceinline__ int64_t win_to_pix32(const WinGeo& g, uint32_t wr) {
+    const uint32_t per_img = (uint32_t)(g.nwin() * WT);
+    const uint32_t b = wr / per_img, r = wr - b * per_img;
+    const uint32_t w = r / WT, i = r - w * WT;
+    const uint32_t nwx = (uint32_t)g.nwx();
+    const uint32_t wy = w / nwx, wx = w - wy * nwx, iy = i / WS, ix = i - iy * WS;
+    int py = (int)(wy * WS + iy) + g.sh; if (py >= g.Ph) py -= g.Ph;
+    int px = (int)(wx * WS + ix) + g.sw; if (px >= g.Pw) px -= g.Pw;
+    if (py >= g.H || px >= g.W) return -1;
+    return (int64_t)b * (g.H * g.W) + py * g.W + px;
+}
+__device__ __forceinline__ int64_t pix_to_win32(const WinGeo& g, uint32_t pr) {
+    const uint32_t hw = (uint32_t)(g.H * g.W);
+    const uint32_t b = pr / hw, r = pr - b * hw;
+    const uint32_t y = r / (uint32_t)g.W, x = r - y * (uint32_t)g.W;
+    int ry = (int)y - g.sh; if (ry < 0) ry += g.Ph;
+    int rx = (int)x - g.sw; if (rx < 0) rx += g.Pw;
+    const int wy = ry / WS, wx = rx / WS;
+    return (int64_t)b * (g.nwin() * WT) + (wy * g.nwx() + wx) * WT + (ry - wy * WS) * WS + (rx - wx * WS);
+}
+
+template <typename T, int NV, int MODE>
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_fwd_persist_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, T* __restrict__ Y,
+                                                              float* __restrict__ mean, float* __restrict__ rstd,
+                                                              int64_t rows, int C, float invC, int lpr,
+                                                              WinGeo wg, MergeGeo mg, const float* __restrict__ dotw,
+                                                              float* __restrict__ dot_m2) {
+    constexpr bool DOT = MODE == LNM_DOT;
+    constexpr bool PREG = DOT && NV <= 3;   // DOT: gamma * w in registers; other modes read gamma / beta from shared memory
+    constexpr int VW = VecW<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
+    const int Cin = C / 4;
+    const int64_t P = (int64_t)gridDim.x * LN_WARPS;
+    const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    const int64_t nsuper = (rows + (int64_t)rpw * LN_RG - 1) / ((int64_t)rpw * LN_RG);
+    bool vld[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) vld[j] = (l + lpr * j) * VW < C;
+    float pg[PREG ? NV : 1][VW], pb[(PREG && !DOT) ? NV : 1][VW];
+    float Gsum = 0.f, Bsum = 0.f;
+    extern __shared__ float ln_sp[];        // [gamma | beta] (non-DOT)
+    if (!DOT) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { ln_sp[c] = gamma[c]; ln_sp[C + c] = beta[c]; }
+        __syncthreads();
+    }
+    if (PREG) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c = (l + lpr * j) * VW;
+#pragma unroll
+            for (int e = 0; e < VW; e++) { pg[PREG ? j : 0][e] = 0.f; if (!DOT) pb[(PREG && !DOT) ? j : 0][e] = 0.f; }
+            if (vld[j]) {
+                ldf(gamma + c, pg[PREG ? j : 0], VW);
+                if (DOT) {
+                    float wl[VW], bt[VW];
+                    ldf(dotw + c, wl, VW);
+                    ldf(beta + c, bt, VW);
+#pragma unroll
+                    for (int e = 0; e < VW; e++) {
+                        pg[PREG ? j : 0][e] *= wl[e];
+                        Gsum += pg[PREG ? j : 0][e];
+                        Bsum = fmaf(bt[e], wl[e], Bsum);
+                    }
+                } else {
+                    ldf(beta + c, pb[(PREG && !DOT) ? j : 0], VW);
+                }
+            }
+        }
+        if (DOT) { Gsum = group_sum_u(Gsum, lpr); Bsum = group_sum_u(Bsum, lpr); }
+    }
+
+    auto load = [&](int64_t sg, LnGroup<T, NV>& G) {
+#pragma unroll
+        for (int g = 0; g < LN_RG; g++) {
+            G.r[g] = (sg * LN_RG + g) * rpw + sub;
+            G.lr[g] = G.r[g];       // LayerNorm row (statistics index)
+            G.live[g] = G.r[g] < rows;
+            if (MODE == LNM_WINDOW && G.live[g]) {
+                G.lr[g] = win_to_pix32(wg, (uint32_t)G.r[g]);
+                G.live[g] = G.lr[g] >= 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
+            }
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const int c = (l + lpr * j) * VW;
+                G.xr[g][j] = make_uint4(0, 0, 0, 0);
+                if (G.live[g] && vld[j]) {
+                    const T* p = (MODE == LNM_MERGE) ? X + merge_off(mg, G.lr[g], c, Cin) : X + G.lr[g] * C + c;
+                    G.xr[g][j] = *reinterpret_cast<const uint4*>(p);
+                }
+            }
+        }
+    };
+
+    LnGroup<T, NV> cur;
+    if (wid < nsuper) load(wid, cur);
+    for (int64_t sg = wid; sg < nsuper; sg += P) {
+        LnGroup<T, NV> nxt;
+        if (sg + P < nsuper) load(sg + P, nxt);
+#pragma unroll
+        for (int g = 0; g < LN_RG; g++) {
+            float x[NV][VW];
+            float s = 0.f, d = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                cvt_raw<T>(cur.xr[g][j], x[j]);
+#pragma unroll
+                for (int e = 0; e < VW; e++) {
+                    s += x[j][e];
+                    if (DOT && PREG) d = fmaf(x[j][e], pg[PREG ? j : 0][e], d);
+                }
+            }
+            const float mu = group_sum_u(s, lpr) * invC;
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                if (vld[j]) {
+#pragma unroll
+                    for (int e = 0; e < VW; e++) { const float a = x[j][e] - mu; v = fmaf(a, a, v); }
+                }
+            }
+            const float rs = rsqrtf(group_sum_u(v, lpr) * invC + LN_EPS);
+            const float nmr = -mu * rs;
+            if (cur.live[g] && l == 0) {
+                mean[cur.lr[g]] = mu;
+                rstd[cur.lr[g]] = rs;
+            }
+            const bool in_range = cur.r[g] < rows;
+            if (DOT && PREG) {
+                d = group_sum_u(d, lpr);
+                if (in_range && l == 0) {
+                    const float dc = fmaf(-mu, Gsum, d) * rs;           // sum_c gw_c x-hat_c
+                    Y[cur.r[g]] = from_f<T>(dc + Bsum);
+                    dot_m2[cur.r[g]] = dc * invC;                         // the backward's row mean of g * x-hat, per unit d(logit)
+                }
+                continue;
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const int c = (l + lpr * j) * VW;
+                if (in_range && vld[j]) {
+                    float y[VW];
+                    if (cur.live[g]) {
+                        float gl[VW], bl[VW];
+                        if (PREG) {
+#pragma unroll
+                            for (int e = 0; e < VW; e++) { gl[e] = pg[PREG ? j : 0][e]; bl[e] = pb[(PREG && !DOT) ? j : 0][e]; }
+                        } else if (DOT) {
+                            ldf(gamma + c, gl, VW);
+                            ldf(beta + c, bl, VW);
+                        } else {
+                            ldf(ln_sp + c, gl, VW);
+                            ldf(ln_sp + C + c, bl, VW);
+                        }
+#pragma unroll
+                        for (int e = 0; e < VW; e++) y[e] = fmaf(fmaf(x[j][e], rs, nmr), gl[e], bl[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VW; e++) y[e] = 0.f;
+                    }
+                    if (DOT) {
+                        float wl[VW];
+                        ldf(dotw + c, wl, VW);
+#pragma unroll
+                        for (int e = 0; e < VW; e++) dot = fmaf(y[e], wl[e], dot);
+                    } else {
+                        VecW<T>::st(Y + cur.r[g] * C + c, y);
+                    }
+                }
+            }
+            if (DOT) {
+                dot = group_sum_u(dot, lpr);
+                if (in_range && l == 0) Y[cur.r[g]] = from_f<T>(dot);
+            }
+        }
+        cur = nxt;
+    }
+}
+
 // Forward: every warp owns LN_RG row groups (rpw rows each) whose 16 B loads are all issued before the first
 // reduction, so ~2x the bytes are in flight per warp (the one-group version topped out at 3.4 TB/s).
-constexpr int LN_RG = 2;
 template <typename T, int NV, int MODE>
 __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ Y,
@@ -119,7 +315,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(
         lr[g] = r[g];       // LayerNorm row (statistics index)
         live[g] = r[g] < rows;
         if (MODE == LNM_WINDOW && live[g]) {
-            lr[g] = win_to_pix(wg, r[g]);
+            lr[g] = win_to_pix32(wg, (uint32_t)r[g]);
             live[g] = lr[g] >= 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
         }
 #pragma unroll
@@ -193,9 +389,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 1) ln_fwd_kernel(
 
 // Backward: warp w walks row groups  w, w + P, ...  (P = number of warps) and keeps the per-column parameter-gradient
 // partial sums in registers; partial[w][3][C] is reduced afterwards in a fixed order (deterministic).
-// Operands stay packed (16 B) in registers between the two passes over a row and the residual gradient is requested
-// together with x and dy, so a row group costs ONE memory round trip and the kernel fits 2 blocks (16 warps) per SM:
-// ~75 KB of loads in flight per SM instead of 24 KB (the first version ran at 8 warps/SM and ~1.4 TB/s).
+// The operands of a row group (x, dy, residual gradient: 16 B vectors) travel global -> shared memory with cp.async, each lane
+// into its own slots of a two-stage per-warp ring, so the NEXT group's loads are in flight while the current one is
+// reduced and no register is spent on data in flight (the accumulators already take 2 * NV * VW of them).  A lane only ever
+// reads back what it copied itself: cp.async.wait_group is all the synchronisation there is.  2 blocks (16 warps) per SM
+// keep >= 74 KB of loads in flight continuously (the register-staged version had them in flight a third of the time).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;           // 0: nothing is read, the slot is zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NV> __host__ __device__ constexpr int ln_bwd_stages() { return NV <= 6 ? 2 : 1; }
+
 template <typename T, int NV, int MODE, bool RES>
 __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ X,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -206,12 +414,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                                                               MsuOperand ug, T* __restrict__ dXw, const float* __restrict__ wscale,
                                                               int rows_per_sample) {
     constexpr bool DOT = MODE == LNM_DOT;
+    constexpr int NOPS = (DOT ? 1 : 2) + (RES ? 1 : 0);      // x, dy, dres
+    constexpr int OP_DY = 1, OP_RES = DOT ? 1 : 2;
+    constexpr int STAGES = ln_bwd_stages<NV>();
+    extern __shared__ __align__(16) uint4 ln_ring[];          // [warp][stage][op][j][lane]
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
     const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int64_t P = (int64_t)gridDim.x * LN_WARPS;
     constexpr int VW = VecW<T>::N;
     const int Cin = C / 4;
+    uint4* ring = ln_ring + (size_t)(threadIdx.x >> 5) * (STAGES * NOPS * NV * 32) + lane;
     bool vld[NV];
 #pragma unroll
     for (int j = 0; j < NV; j++) vld[j] = (l + lpr * j) * VW < C;
@@ -227,29 +440,47 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
     }
     if (DOT) ab[0][0] = 0.f;
 
-    for (int64_t g0 = wid * rpw; g0 < rows; g0 += P * rpw) {
-        const int64_t lr = g0 + sub;
-        const bool live = lr < rows;
-        const float mu = live ? mean[lr] : 0.f, rs = live ? rstd[lr] : 0.f;
-        const float nmr = -mu * rs;
-        const int64_t dyr = (MODE == LNM_WINDOW && live) ? pix_to_win(wg, lr) : lr;
+    struct RowInfo { int64_t lr, wrow; bool live; float mu, rs, dl, wsc; };
+    auto issue = [&](int64_t g0, int stage, RowInfo& ri) {
+        ri.lr = g0 + sub;
+        ri.live = ri.lr < rows;
+        ri.mu = ri.live ? mean[ri.lr] : 0.f;
+        ri.rs = ri.live ? rstd[ri.lr] : 0.f;
+        const int64_t dyr = (MODE == LNM_WINDOW && ri.live) ? pix_to_win32(wg, (uint32_t)ri.lr) : ri.lr;
         // DUAL: the same gradient row, scaled per sample, also goes to its window-order row (the padding rows of that
         // buffer are zeroed once by the caller and never written)
-        const int64_t wrow = (MODE == LNM_DUAL && live) ? pix_to_win(wg, lr) : 0;
-        const float wsc = (MODE == LNM_DUAL && live && wscale != nullptr) ? wscale[lr / rows_per_sample] : 1.0f;
-        const float dl = (DOT && live) ? to_f<T>(dY[lr]) : 0.f;
-        const int64_t rowoff = lr * C;
-        uint4 xr[NV], yr[DOT ? 1 : NV], rr[RES ? NV : 1];
+        ri.wrow = (MODE == LNM_DUAL && ri.live) ? pix_to_win32(wg, (uint32_t)ri.lr) : 0;
+        ri.wsc = (MODE == LNM_DUAL && ri.live && wscale != nullptr) ? wscale[ri.lr / rows_per_sample] : 1.0f;
+        ri.dl = (DOT && ri.live) ? to_f<T>(dY[ri.lr]) : 0.f;
+        uint4* st = ring + (size_t)stage * (NOPS * NV * 32);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const int c = (l + lpr * j) * VW;
-            if (live && vld[j]) {
-                const int64_t xo = (MODE == LNM_MERGE) ? merge_off(mg, lr, c, Cin) : rowoff + c;
-                xr[j] = *reinterpret_cast<const uint4*>(X + xo);
-                if (!DOT) yr[DOT ? 0 : j] = *reinterpret_cast<const uint4*>(dY + dyr * C + c);
-                if (RES) rr[RES ? j : 0] = *reinterpret_cast<const uint4*>(dRes + xo);
-            }
+            const bool on = ri.live && vld[j];
+            const int64_t xo = !on ? 0 : ((MODE == LNM_MERGE) ? merge_off(mg, ri.lr, c, Cin) : ri.lr * C + c);
+            cp_async16(st + (0 * NV + j) * 32, X + xo, on);
+            if (!DOT) cp_async16(st + (OP_DY * NV + j) * 32, dY + (on ? dyr * C + c : 0), on);
+            if (RES) cp_async16(st + (OP_RES * NV + j) * 32, dRes + xo, on);
         }
+        cp_async_commit();
+    };
+
+    RowInfo cur, nxt;
+    int stage = 0;
+    if (wid * rpw < rows) issue(wid * rpw, 0, cur);
+    for (int64_t g0 = wid * rpw; g0 < rows; g0 += P * rpw) {
+        const bool more = g0 + P * rpw < rows;
+        if (STAGES == 2) {
+            if (more) issue(g0 + P * rpw, stage ^ 1, nxt);
+            if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        } else {
+            cp_async_wait<0>();
+        }
+        const uint4* st = ring + (size_t)stage * (NOPS * NV * 32);
+        const int64_t lr = cur.lr;
+        const bool live = cur.live;
+        const float rs = cur.rs, nmr = -cur.mu * cur.rs, dl = cur.dl;
+        const int64_t rowoff = lr * C;
         // pass 1: row sums of g = dy * gamma and g * x-hat
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -257,14 +488,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
             if (live && vld[j]) {
                 const int c = (l + lpr * j) * VW;
                 float x[VW], dy[VW], gl[VW];
-                cvt_raw<T>(xr[j], x);
+                cvt_raw<T>(st[(0 * NV + j) * 32], x);
                 ldf(gamma + c, gl, VW);
                 if (DOT) {
                     ldf(dotw + c, dy, VW);
 #pragma unroll
                     for (int e = 0; e < VW; e++) dy[e] *= dl;
                 } else {
-                    cvt_raw<T>(yr[DOT ? 0 : j], dy);
+                    cvt_raw<T>(st[(OP_DY * NV + j) * 32], dy);
                 }
 #pragma unroll
                 for (int e = 0; e < VW; e++) {
@@ -284,16 +515,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
             const int c = (l + lpr * j) * VW;
             if (live && vld[j]) {
                 float x[VW], dy[VW], gl[VW], dx[VW];
-                cvt_raw<T>(xr[j], x);
+                cvt_raw<T>(st[(0 * NV + j) * 32], x);
                 ldf(gamma + c, gl, VW);
                 if (DOT) {
                     ldf(dotw + c, dy, VW);
 #pragma unroll
                     for (int e = 0; e < VW; e++) dy[e] *= dl;
                 } else {
-                    cvt_raw<T>(yr[DOT ? 0 : j], dy);
+                    cvt_raw<T>(st[(OP_DY * NV + j) * 32], dy);
                 }
-                if (RES) cvt_raw<T>(rr[RES ? j : 0], dx);
+                if (RES) cvt_raw<T>(st[(OP_RES * NV + j) * 32], dx);
                 else {
 #pragma unroll
                     for (int e = 0; e < VW; e++) dx[e] = 0.f;
@@ -313,11 +544,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
                 VecW<T>::st(dX + wo, dx);
                 if (MODE == LNM_DUAL) {
 #pragma unroll
-                    for (int e = 0; e < VW; e++) dx[e] *= wsc;
-                    VecW<T>::st(dXw + wrow * C + c, dx);
+                    for (int e = 0; e < VW; e++) dx[e] *= cur.wsc;
+                    VecW<T>::st(dXw + cur.wrow * C + c, dx);
                 }
             }
         }
+        if (STAGES == 2) { cur = nxt; stage ^= 1; }
+        else if (more) issue(g0 + P * rpw, 0, cur);
     }
     // fold the row groups of this warp (lanes l, l+lpr, ...) in a fixed order, then one partial row per warp
     float* pg = partial + wid * 3 * (int64_t)C;
@@ -360,6 +593,140 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_bwd_kernel(
     }
 }
 
+// Head backward (LayerNorm + 1x1 conv as a dot product, network/model_parts.py:842-846): with dy_c = dl w_c the two row
+// reductions of the generic backward are known in closed form from what the forward saved,
+//   mean_c(dy_c gamma_c) = dl G / C,   mean_c(dy_c gamma_c x-hat_c) = dl m2      (gw = gamma w, G = sum gw, m2 from the forward)
+//   dx_c = rs dl (gw_c - G/C) - rs^2 dl m2 (x_c - mu)
+// so a row needs no shuffle at all: 2 FMAs + 1 FMUL per element for dx and one FMA for the parameter sums
+// S1_c = sum_rows dl x-hat_c, S0 = sum_rows dl  (d gamma = w S1, d beta = w S0, d w = gamma S1 + beta S0).
+// The generic kernel spent ~14 instructions per element here and was issue-bound at 3.8 TB/s.
+template <typename T, int NV, bool RES>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_dot_kernel(const T* __restrict__ dL, const T* __restrict__ X,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      const float* __restrict__ m2, const T* __restrict__ dRes,
+                                                                      T* __restrict__ dX, int64_t rows, int C, float invC, int lpr,
+                                                                      const float* __restrict__ dotw, float* __restrict__ partial) {
+    constexpr int VW = VecW<T>::N;
+    constexpr int RG = 2;
+    const int lane = threadIdx.x & 31;
+    const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
+    const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    const int64_t P = (int64_t)gridDim.x * LN_WARPS;
+    bool vld[NV];
+    float gwc[NV][VW], ag[NV][VW];
+    float G = 0.f, s0 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int c = (l + lpr * j) * VW;
+        vld[j] = c < C;
+#pragma unroll
+        for (int e = 0; e < VW; e++) { gwc[j][e] = 0.f; ag[j][e] = 0.f; }
+        if (vld[j]) {
+            float wl[VW];
+            ldf(gamma + c, gwc[j], VW);
+            ldf(dotw + c, wl, VW);
+#pragma unroll
+            for (int e = 0; e < VW; e++) { gwc[j][e] *= wl[e]; G += gwc[j][e]; }
+        }
+    }
+    G = group_sum_u(G, lpr) * invC;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+#pragma unroll
+        for (int e = 0; e < VW; e++) gwc[j][e] -= G;
+    }
+    // x (and the residual gradient) of RG row groups per stage go through a two-stage per-warp cp.async ring (see ln_bwd_kernel)
+    constexpr int NOPS = RES ? 2 : 1;
+    extern __shared__ __align__(16) uint4 ln_ring[];          // [warp][stage][group][op][j][lane]
+    uint4* ring = ln_ring + (size_t)(threadIdx.x >> 5) * (2 * RG * NOPS * NV * 32) + lane;
+    struct Grp { int lr[RG]; float mu[RG], a[RG], b[RG]; };   // rows < 2^31
+    auto issue = [&](int64_t g0, int stage, Grp& Gp) {
+        uint4* st = ring + (size_t)stage * (RG * NOPS * NV * 32);
+#pragma unroll
+        for (int g = 0; g < RG; g++) {
+            const int64_t lr = g0 + (int64_t)g * rpw + sub;
+            const bool live = lr < rows;
+            Gp.lr[g] = live ? (int)lr : -1;
+            float mu = 0.f, rs = 0.f, mm = 0.f, dl = 0.f;
+            if (live) { mu = mean[lr]; rs = rstd[lr]; mm = m2[lr]; dl = to_f<T>(dL[lr]); }
+            s0 += dl;
+            Gp.mu[g] = mu;
+            Gp.a[g] = rs * dl;
+            Gp.b[g] = -rs * dl * mm * rs;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const int c = (l + lpr * j) * VW;
+                const bool on = live && vld[j];
+                const int64_t xo = on ? lr * C + c : 0;
+                cp_async16(st + ((g * NOPS + 0) * NV + j) * 32, X + xo, on);
+                if (RES) cp_async16(st + ((g * NOPS + 1) * NV + j) * 32, dRes + xo, on);
+            }
+        }
+        cp_async_commit();
+    };
+    Grp cur, nxt;
+    int stage = 0;
+    const int64_t step = P * rpw * RG;
+    if (wid * rpw * RG < rows) issue(wid * rpw * RG, 0, cur);
+    for (int64_t g0 = wid * rpw * RG; g0 < rows; g0 += step) {
+        const bool more = g0 + step < rows;
+        if (more) issue(g0 + step, stage ^ 1, nxt);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        const uint4* st = ring + (size_t)stage * (RG * NOPS * NV * 32);
+#pragma unroll
+        for (int g = 0; g < RG; g++) {
+            const float mu = cur.mu[g], a = cur.a[g], b = cur.b[g];
+            const bool live = cur.lr[g] >= 0;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                if (live && vld[j]) {
+                    float x[VW], dx[VW];
+                    cvt_raw<T>(st[((g * NOPS + 0) * NV + j) * 32], x);
+                    if (RES) cvt_raw<T>(st[((g * NOPS + (RES ? 1 : 0)) * NV + j) * 32], dx);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < VW; e++) dx[e] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < VW; e++) {
+                        const float xm = x[e] - mu;
+                        dx[e] += fmaf(b, xm, a * gwc[j][e]);
+                        ag[j][e] = fmaf(a, xm, ag[j][e]);
+                    }
+                    VecW<T>::st(dX + (int64_t)cur.lr[g] * C + (l + lpr * j) * VW, dx);
+                }
+            }
+        }
+        cur = nxt;
+        stage ^= 1;
+    }
+    // fold the rows of this warp (lanes l, l + lpr, ...) in a fixed order, then one partial row per warp
+    float* pg = partial + wid * 3 * (int64_t)C;
+    for (int o = lpr; o < 32; o <<= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int e = 0; e < VW; e++) ag[j][e] += __shfl_xor_sync(0xffffffffu, ag[j][e], o);
+        }
+        const int c = (l + lpr * j) * VW;
+        if (sub == 0 && c < C) {
+            float w[VW], gl[VW], bt[VW];
+            ldf(dotw + c, w, VW);
+            ldf(gamma + c, gl, VW);
+            ldf(beta + c, bt, VW);
+#pragma unroll
+            for (int e = 0; e < VW; e += 4) {
+                *reinterpret_cast<float4*>(pg + c + e) = make_float4(w[e] * ag[j][e], w[e + 1] * ag[j][e + 1], w[e + 2] * ag[j][e + 2], w[e + 3] * ag[j][e + 3]);
+                *reinterpret_cast<float4*>(pg + C + c + e) = make_float4(w[e] * s0, w[e + 1] * s0, w[e + 2] * s0, w[e + 3] * s0);
+                *reinterpret_cast<float4*>(pg + 2 * C + c + e) = make_float4(fmaf(gl[e], ag[j][e], bt[e] * s0), fmaf(gl[e + 1], ag[j][e + 1], bt[e + 1] * s0),
+                                                                             fmaf(gl[e + 2], ag[j][e + 2], bt[e + 2] * s0), fmaf(gl[e + 3], ag[j][e + 3], bt[e + 3] * s0));
+            }
+        }
+    }
+}
+
 // out[a][c] = sum_p partial[p][a][c]; block = 32 columns x 32 row-lanes, fixed-order tree => deterministic.
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ partial, int P, int C,
                                                                float* dgamma, float* dbeta, float* ddotw, int accumulate) {
@@ -381,31 +748,36 @@ __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __re
     }
 }
 
-// lanes per row: power of two in [4, 32] giving about 3-4 vectors (of 4 elements) per lane
+// lanes per row: power of two in [4, 32] giving at most 3 vectors (16 B) per lane while the row fits 32 lanes x 3
 static int pick_lpr(int C, int vw) {
     const int nvec = (C + vw - 1) / vw;
     int lpr = 4;
-    while (lpr < 32 && lpr * 4 < nvec) lpr <<= 1;
+    while (lpr < 32 && lpr * 3 < nvec) lpr <<= 1;
     return lpr;
 }
 
 template <typename T, int NV>
 static int launch_fwd(const void* X, const float* gamma, const float* beta, void* Y, float* mean, float* rstd,
                       int64_t rows, int C, int lpr, int in_map, int out_map, const int32_t* geo, const float* dotw,
-                      cudaStream_t st) {
+                      float* dot_m2, cudaStream_t st) {
     WinGeo wg{0, 0, 0, 0, 0, 0};
     MergeGeo mg{0, 0};
     if (out_map == MSU_MAP_WINDOW) wg = make_wingeo(geo);
     if (in_map == MSU_MAP_MERGE) { mg.H = geo[0]; mg.W = geo[1]; }
     const int rpb = LN_WARPS * (32 / lpr) * LN_RG;
-    const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
+    const int64_t want = (rows + rpb - 1) / rpb;
+    const unsigned grid = (unsigned)want;
     const float invC = 1.0f / (float)C;
 #define LN_FWD_LAUNCH(MODE)                                                                                               \
     ln_fwd_kernel<T, NV, MODE><<<grid, LN_WARPS * 32, 0, st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd, rows, C, invC, lpr, \
                                                               wg, mg, dotw)
     if (dotw != nullptr) {
         if (in_map != MSU_MAP_NONE || out_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: dotw with a row map is not supported"); return -1; }
-        LN_FWD_LAUNCH(LNM_DOT);
+        if (NV > 3 || dot_m2 == nullptr) { set_error("msu_ln_fwd: dotw needs C <= %d and a dot_m2 output", 96 * VecW<T>::N); return -1; }
+        // persistent variant (register-prefetched, y never formed): the resident block count, 2 per SM for narrow rows
+        const unsigned pgrid = (unsigned)imax(1, imin(want, (int64_t)num_sms() * (NV <= 3 ? 2 : 1)));
+        ln_fwd_persist_kernel<T, NV, LNM_DOT><<<pgrid, LN_WARPS * 32, 2 * C * sizeof(float), st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd,
+                                                                                                  rows, C, invC, lpr, wg, mg, dotw, dot_m2);
     } else if (out_map == MSU_MAP_WINDOW) {
         if (in_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: in_map and out_map together are not supported"); return -1; }
         LN_FWD_LAUNCH(LNM_WINDOW);
@@ -423,7 +795,7 @@ template <typename T, int NV>
 static int launch_bwd(const void* dY, const void* X, const float* gamma, const float* beta, const float* mean,
                       const float* rstd, const void* dRes, void* dX, int64_t rows, int C, int lpr, int dy_map, int dx_map,
                       const int32_t* geo, const float* dotw, float* partial, int grid, cudaStream_t st, void* dXw = nullptr,
-                      const float* wscale = nullptr, int rows_per_sample = 1) {
+                      const float* wscale = nullptr, int rows_per_sample = 1, const float* dot_m2 = nullptr) {
     WinGeo wg{0, 0, 0, 0, 0, 0};
     MergeGeo mg{0, 0};
     if (dy_map == MSU_MAP_WINDOW || dXw != nullptr) wg = make_wingeo(geo);
@@ -432,16 +804,41 @@ static int launch_bwd(const void* dY, const void* X, const float* gamma, const f
     if (dx_map == MSU_MAP_UNSHUFFLE) for (int k = 0; k < 4; k++) ug.geo[k] = geo[k];
     const float invC = 1.0f / (float)C;
 #define LN_BWD_LAUNCH(MODE, RES)                                                                                           \
-    ln_bwd_kernel<T, NV, MODE, RES><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd,     \
+    do {                                                                                                                   \
+        constexpr int nops_ = ((MODE) == LNM_DOT ? 1 : 2) + ((RES) ? 1 : 0);                                               \
+        constexpr int smem_ = LN_WARPS * ln_bwd_stages<NV>() * nops_ * NV * 32 * 16;                                        \
+        static PerDeviceOnce attr_;                                                                                        \
+        if (smem_ > 48 * 1024 && attr_.need()) {                                                                           \
+            cudaFuncSetAttribute(ln_bwd_kernel<T, NV, MODE, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_);     \
+            attr_.set();                                                                                                   \
+        }                                                                                                                  \
+        ln_bwd_kernel<T, NV, MODE, RES><<<grid, LN_WARPS * 32, smem_, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd, \
                                                                    (const T*)dRes, (T*)dX, rows, C, invC, lpr, wg, mg, dotw, partial, ug, \
-                                                                   (T*)dXw, wscale, rows_per_sample)
+                                                                   (T*)dXw, wscale, rows_per_sample);                      \
+    } while (0)
     const int nmaps = (dy_map != MSU_MAP_NONE) + (dx_map != MSU_MAP_NONE) + (dotw != nullptr);
     if (nmaps > 1) { set_error("msu_ln_bwd: at most one of dy_map / dx_map / dotw"); return -1; }
     if (dXw != nullptr) {
         if (nmaps != 0) { set_error("msu_ln_bwd_dual: no other row map allowed"); return -1; }
         if (dRes) LN_BWD_LAUNCH(LNM_DUAL, true); else LN_BWD_LAUNCH(LNM_DUAL, false);
     } else if (dotw != nullptr) {
-        if (dRes) LN_BWD_LAUNCH(LNM_DOT, true); else LN_BWD_LAUNCH(LNM_DOT, false);
+        if constexpr (NV <= 3) {
+            if (dot_m2 == nullptr) { set_error("msu_ln_bwd: dotw needs the forward's dot_m2"); return -1; }
+            constexpr int sm1 = LN_WARPS * 2 * 2 * NV * 32 * 16;          // [warps][stages][RG][op][NV][lane] x 16 B
+            static PerDeviceOnce attr_;
+            if (attr_.need()) {
+                cudaFuncSetAttribute(ln_bwd_dot_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sm1);
+                cudaFuncSetAttribute(ln_bwd_dot_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
+                attr_.set();
+            }
+            if (dRes) ln_bwd_dot_kernel<T, NV, true><<<grid, LN_WARPS * 32, 2 * sm1, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd, dot_m2,
+                                                                                         (const T*)dRes, (T*)dX, rows, C, invC, lpr, dotw, partial);
+            else ln_bwd_dot_kernel<T, NV, false><<<grid, LN_WARPS * 32, sm1, st>>>((const T*)dY, (const T*)X, gamma, beta, mean, rstd, dot_m2,
+                                                                                   (const T*)dRes, (T*)dX, rows, C, invC, lpr, dotw, partial);
+        } else {
+            set_error("msu_ln_bwd: dotw needs C <= %d", 96 * VecW<T>::N);
+            return -1;
+        }
     } else if (dy_map == MSU_MAP_WINDOW) {
         if (dRes) LN_BWD_LAUNCH(LNM_WINDOW, true); else LN_BWD_LAUNCH(LNM_WINDOW, false);
     } else if (dx_map == MSU_MAP_MERGE) {
@@ -478,7 +875,7 @@ using namespace msu;
 
 extern "C" int msu_ln_fwd(int dtype, const void* X, const float* gamma, const float* beta, void* Y, float* mean,
                           float* rstd, int64_t rows, int32_t C, int32_t in_map, int32_t out_map, const int32_t* geo,
-                          const float* dotw, void* stream) {
+                          const float* dotw, float* dot_m2, void* stream) {
     MSU_REQUIRE(X && gamma && beta && Y && mean && rstd, "msu_ln_fwd: null pointer");
     MSU_REQUIRE(C > 0 && C % (dtype == MSU_F32 ? 4 : 8) == 0, "msu_ln_fwd: C=%d must be a positive multiple of the 16-byte vector width", C);
     MSU_REQUIRE(in_map == MSU_MAP_NONE || in_map == MSU_MAP_MERGE, "msu_ln_fwd: bad in_map %d", in_map);
@@ -486,8 +883,8 @@ extern "C" int msu_ln_fwd(int dtype, const void* X, const float* gamma, const fl
     MSU_REQUIRE((in_map == 0 && out_map == 0) || geo != nullptr, "msu_ln_fwd: geo required for mapped rows");
     if (rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_fwd, float, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, st);
-    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_fwd, __nv_bfloat16, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, st);
+    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_fwd, float, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, dot_m2, st);
+    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_fwd, __nv_bfloat16, X, gamma, beta, Y, mean, rstd, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), in_map, out_map, geo, dotw, dot_m2, st);
     MSU_REQUIRE(false, "msu_ln_fwd: unsupported dtype %d", dtype);
 }
 
@@ -503,8 +900,8 @@ extern "C" int msu_ln_bwd_partial_rows(int dtype, int64_t rows, int32_t C) {
 
 extern "C" int msu_ln_bwd(int dtype, const void* dY, const void* X, const float* gamma, const float* beta,
                           const float* mean, const float* rstd, const void* dRes, void* dX, int64_t rows, int32_t C,
-                          int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, float* partial,
-                          void* stream) {
+                          int32_t dy_map, int32_t dx_map, const int32_t* geo, const float* dotw, const float* dot_m2,
+                          float* partial, void* stream) {
     MSU_REQUIRE(dY && X && gamma && beta && mean && rstd && dX && partial, "msu_ln_bwd: null pointer");
     MSU_REQUIRE(C > 0 && C % (dtype == MSU_F32 ? 4 : 8) == 0, "msu_ln_bwd: C=%d must be a positive multiple of the 16-byte vector width", C);
     MSU_REQUIRE(dy_map == MSU_MAP_NONE || dy_map == MSU_MAP_WINDOW, "msu_ln_bwd: bad dy_map %d", dy_map);
@@ -512,8 +909,8 @@ extern "C" int msu_ln_bwd(int dtype, const void* dY, const void* X, const float*
     MSU_REQUIRE(dx_map != MSU_MAP_UNSHUFFLE || (geo != nullptr && geo[3] % (dtype == MSU_F32 ? 4 : 8) == 0), "msu_ln_bwd: UNSHUFFLE needs geo with a vector-aligned chunk width");
     const int grid = msu_ln_bwd_partial_rows(dtype, rows, C) / LN_WARPS;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_bwd, float, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st);
-    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_bwd, __nv_bfloat16, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st);
+    if (dtype == MSU_F32) LN_DISPATCH_NV(launch_bwd, float, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st, nullptr, nullptr, 1, dot_m2);
+    if (dtype == MSU_BF16) LN_DISPATCH_NV(launch_bwd, __nv_bfloat16, dY, X, gamma, beta, mean, rstd, dRes, dX, rows, C, pick_lpr(C, dtype == MSU_F32 ? 4 : 8), dy_map, dx_map, geo, dotw, partial, grid, st, nullptr, nullptr, 1, dot_m2);
     MSU_REQUIRE(false, "msu_ln_bwd: unsupported dtype %d", dtype);
 }
 

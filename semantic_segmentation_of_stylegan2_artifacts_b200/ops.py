@@ -209,17 +209,19 @@ def _geo_arr(geo):
 
 def ln_fwd(x: torch.Tensor, gamma, beta, rows: int, Cdim: int, *, in_map=MAP_NONE, out_map=MAP_NONE, geo=None,
            n_stat_rows: Optional[int] = None, dotw: Optional[torch.Tensor] = None):
-    """Returns (y, mean, rstd).  y is [rows, C] (or [rows] logits when dotw is given)."""
+    """Returns (y, mean, rstd).  y is [rows, C] (or [rows] logits when dotw is given; rstd is then [2, rows]: the second row
+    holds the per-row dot statistic the backward needs, see msu_ln_fwd)."""
     _need_cuda(x, "x")
     y = torch.empty((rows,) if dotw is not None else (rows, Cdim), dtype=x.dtype, device=x.device)
     ns = rows if n_stat_rows is None else n_stat_rows
     mean = torch.empty(ns, dtype=torch.float32, device=x.device)
-    rstd = torch.empty(ns, dtype=torch.float32, device=x.device)
+    rstd = torch.empty((2, ns) if dotw is not None else (ns,), dtype=torch.float32, device=x.device)
     g = _geo_arr(geo)
     e0 = _p0()
     L.check(L.lib().msu_ln_fwd(L.dt(x), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
                                mean.data_ptr(), rstd.data_ptr(), rows, Cdim, in_map, out_map,
-                               None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), L.stream_ptr()), "msu_ln_fwd")
+                               None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw),
+                               rstd[1].data_ptr() if dotw is not None else None, L.stream_ptr()), "msu_ln_fwd")
     _p1(e0, (rows, Cdim, 0, "ln_fwd" + ("_dot" if dotw is not None else "")),
         (ns * Cdim + y.numel()) * x.element_size())
     return y, mean, rstd
@@ -236,7 +238,8 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma, beta, mean, rstd, rows: int
     e0 = _p0()
     L.check(L.lib().msu_ln_bwd(L.dt(x), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                mean.data_ptr(), rstd.data_ptr(), L.ptr(dres), dx.data_ptr(), rows, Cdim, dy_map,
-                               dx_map, None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw), part.data_ptr(),
+                               dx_map, None if g is None else C.cast(g, C.c_void_p), L.ptr(dotw),
+                               rstd[1].data_ptr() if dotw is not None else None, part.data_ptr(),
                                L.stream_ptr()), "msu_ln_bwd")
     dg, db = grad_out(gamma), grad_out(beta)
     dw = grad_out(dotw) if dotw is not None else None
