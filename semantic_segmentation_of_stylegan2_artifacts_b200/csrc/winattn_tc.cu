@@ -41,15 +41,52 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw64(uint32_t saddr, uint3
 struct MaskInfoTc { int any, ty, tx; };
 __device__ __forceinline__ MaskInfoTc mask_info_tc(const WinGeo& g, int w) {
     MaskInfoTc m;
-    const int wy = w / g.nwx(), wx = w % g.nwx();
-    m.ty = (g.sh > 0 && wy == g.Ph / WS - 1) ? WS - g.sh : WS;
-    m.tx = (g.sw > 0 && wx == g.Pw / WS - 1) ? WS - g.sw : WS;
+    const uint32_t nwx = (uint32_t)g.nwx();
+    const uint32_t wy = (uint32_t)w / nwx, wx = (uint32_t)w - wy * nwx;
+    m.ty = (g.sh > 0 && (int)wy == g.Ph / WS - 1) ? WS - g.sh : WS;
+    m.tx = (g.sw > 0 && (int)wx == g.Pw / WS - 1) ? WS - g.sw : WS;
     m.any = (m.ty < WS) || (m.tx < WS);
     return m;
 }
-__device__ __forceinline__ int region_tc(const MaskInfoTc& m, int t) {
-    const int a = t / WS, b = t - a * WS;
-    return (a >= m.ty ? 2 : 0) + (b >= m.tx ? 1 : 0);
+// Shift mask of query token t as a bitmask over the 49 keys (bit j set = same region = attends normally; clear = -100,
+// TV:models/swin_transformer.py:186-209).  Only the windows of the last window row / column of a shifted block have one, so the
+// per-key work sits behind a warp-uniform branch (a warp's 32 rows belong to one window): the branch-free per-element
+// region compares were 45 % of the kernel's instructions, paid by every window.
+__device__ __forceinline__ uint64_t mask_allowed_tc(const MaskInfoTc& m, int t) {
+    const uint32_t a = (uint32_t)t / WS, b = (uint32_t)t - a * WS;
+    uint32_t cols = (1u << m.tx) - 1u;                 // keys left of the column split
+    if ((int)b >= m.tx) cols = ~cols & 0x7fu;
+    uint32_t rows = (1u << m.ty) - 1u;                 // key rows above the row split
+    if ((int)a >= m.ty) rows = ~rows & 0x7fu;
+    uint64_t allowed = 0;
+#pragma unroll
+    for (int r = 0; r < WS; r++)
+        if ((rows >> r) & 1u) allowed |= (uint64_t)cols << (WS * r);
+    return allowed;
+}
+
+// this head's [49, 49] relative-position bias, pre-multiplied by log2(e), rows padded to 50 floats (8 B aligned: the softmax
+// reads it with 25 LDS.64 per row, conflict free for 16 consecutive rows).  All loads are issued before the first store: the
+// rolled loop was 19 dependent global round trips, 12 % of the forward kernel's time.
+constexpr int AT_BROW = 50;
+__device__ __forceinline__ void stage_bias_tc(float* sBias, const float* __restrict__ bias, int h, int tid) {
+    constexpr int N = WT * WT, PER = (N + 127) / 128;
+    float v[PER];
+    const float* src = bias + (int64_t)h * N;
+#pragma unroll
+    for (int m = 0; m < PER; m++) {
+        const int k = tid + 128 * m;
+        v[m] = k < N ? src[k] : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < PER; m++) {
+        const int k = tid + 128 * m;
+        if (k < N) {
+            const int r = k / WT;
+            sBias[r * AT_BROW + (k - r * WT)] = v[m] * LOG2E;
+        }
+    }
+    if (tid < WT) sBias[tid * AT_BROW + WT] = 0.f;
 }
 
 __device__ __forceinline__ uint32_t pk2(float a, float b) {
@@ -64,7 +101,7 @@ __device__ __forceinline__ float ex2_fast(float x) {
 
 constexpr int AT_P_BYTES = 16 * 1024;   // compact P tile: row = query (128), 64 own-window keys (128 B rows, 128B swizzle)
 constexpr int AT_OPS_BYTES = 24 * 1024;  // one stage of Q, K, V tiles (8 KB each: two [64 rows x 32] boxes)
-constexpr int AT_BIAS_BYTES = 2404 * 4;  // this head's [49,49] bias, pre-multiplied by log2(e)
+constexpr int AT_BIAS_BYTES = 49 * 50 * 4 + 8;  // this head's [49,49] bias (rows padded to 50), pre-multiplied by log2(e)
 constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 1024;
 
 // Forward.  Unit = two windows x one head.  The operand tiles are double buffered: the TMA loads of unit n+1 are issued
@@ -89,7 +126,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5;
     const int C = nH * HD;
     const int h = blockIdx.y;
-    for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
+    stage_bias_tc(sBias, bias, h, tid);
 
     if (tid == 0) {
         mbar_init(&bar_load[0], 1);
@@ -157,9 +194,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         }
         // ---- softmax on this thread's row
         const bool row_ok = (i < WT) && (win < n_windows);
-        const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
-        const int ri = region_tc(mi, i);
-        const float* brow = sBias + i * WT;
+        const MaskInfoTc mi = mask_info_tc(g, (int)((uint32_t)win % (uint32_t)nwin_img));
+        const float2* brow = reinterpret_cast<const float2*>(sBias + i * AT_BROW);
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
@@ -174,26 +210,33 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         float inv = 0.f;
         uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) pk[j] = 0u;
+        for (int j = 24; j < 32; j++) pk[j] = 0u;
         if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 25; j++) {                       // log2-domain logits (column 49 of the padded bias row is 0)
+                const float2 b2 = brow[j];
+                s[2 * j] = fmaf(s[2 * j], ATT_SCALE * LOG2E, b2.x);
+                s[2 * j + 1] = fmaf(s[2 * j + 1], ATT_SCALE * LOG2E, b2.y);
+            }
+            if (mi.any) {                                        // warp-uniform: windows on the shifted block's last row / column
+                const uint64_t allowed = mask_allowed_tc(mi, i);
+#pragma unroll
+                for (int j = 0; j < WT; j++)
+                    if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
+            }
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < WT; j++) {
-                s[j] = fmaf(s[j], ATT_SCALE * LOG2E, brow[j]);    // log2-domain logits
-                if (mi.any && region_tc(mi, j) != ri) s[j] += -100.0f * LOG2E;
-                mx = fmaxf(mx, s[j]);
-            }
+            for (int j = 0; j < WT; j++) mx = fmaxf(mx, s[j]);
+            // the row sum is the fp32 one (the reference normalises in fp32 and rounds P afterwards, TV:...:210-214)
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < WT; j += 2) {
                 const float p0 = ex2_fast(s[j] - mx);
                 const float p1 = (j + 1 < WT) ? ex2_fast(s[j + 1] - mx) : 0.f;
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
-                const float2 back = __bfloat1622float2(b2);      // normalise by what the tensor core will actually sum
-                sum += back.x + back.y;
+                sum += p0 + p1;
+                pk[j >> 1] = pk2(p0, p1);
             }
-            inv = ad.inv_keep / sum;
+            inv = __fdividef(ad.inv_keep, sum);
             if (ad.thr) {   // attention dropout: dropped probabilities leave the P tile (the row sum above is the undropped one)
                 const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
 #pragma unroll
@@ -203,6 +246,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
                     if ((hs >> 16) < ad.thr) pk[jp] &= 0x0000ffffu;
                 }
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 25; j++) pk[j] = 0u;
         }
         // P row -> compact tile: row tid, 8 x 16 B chunks, 128B swizzle (chunk ^ (row & 7)); padding rows are zero
         {
@@ -341,7 +387,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                       const __grid_constant__ CUtensorMap tmQKV4, const __grid_constant__ CUtensorMap tmDO3,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
                       int64_t n_windows, int nH, WinGeo g, AttnDrop ad, long long* trace) {
+#ifdef MSU_ATT_TRACE_BUILD   // phase timeline (debug builds only: even a predicated-off clock read costs issue slots in this kernel)
 #define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define AT_TRACE(ev) do { } while (0)
+#endif
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sXP = smem;                        // P rows
@@ -354,7 +404,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const int tid = threadIdx.x, warp = tid >> 5;
     const int C = nH * HD;
     const int h = blockIdx.y;
-    for (int k = tid; k < WT * WT; k += 128) sBias[k] = bias[(int64_t)h * WT * WT + k] * LOG2E;
+    stage_bias_tc(sBias, bias, h, tid);
     if (tid == 0) {
         mbar_init(&bar_load[0], 1);
         mbar_init(&bar_load[1], 1);
@@ -427,9 +477,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
         }
         const bool row_ok = (i < WT) && (win < n_windows);
-        const MaskInfoTc mi = mask_info_tc(g, (int)(win % nwin_img));
-        const int ri = region_tc(mi, i);
-        const float* brow = sBias + i * WT;
+        const MaskInfoTc mi = mask_info_tc(g, (int)((uint32_t)win % (uint32_t)nwin_img));
+        const float2* brow = reinterpret_cast<const float2*>(sBias + i * AT_BROW);
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
@@ -450,17 +499,25 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 tc_ld_wait();
             }
             if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 25; j++) {                   // log2-domain logits (column 49 of the padded bias row is 0)
+                    const float2 b2 = brow[j];
+                    s[2 * j] = fmaf(s[2 * j], ATT_SCALE * LOG2E, b2.x);
+                    s[2 * j + 1] = fmaf(s[2 * j + 1], ATT_SCALE * LOG2E, b2.y);
+                }
+                if (mi.any) {                                    // warp-uniform (see the forward kernel)
+                    const uint64_t allowed = mask_allowed_tc(mi, i);
+#pragma unroll
+                    for (int j = 0; j < WT; j++)
+                        if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
+                }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < WT; j++) {
-                    s[j] = fmaf(s[j], ATT_SCALE * LOG2E, brow[j]);
-                    if (mi.any && region_tc(mi, j) != ri) s[j] += -100.0f * LOG2E;
-                    mx = fmaxf(mx, s[j]);
-                }
+                for (int j = 0; j < WT; j++) mx = fmaxf(mx, s[j]);
                 float sum = 0.f;
 #pragma unroll
                 for (int j = 0; j < WT; j++) { s[j] = ex2_fast(s[j] - mx); sum += s[j]; }
-                const float inv = 1.0f / sum;
+                const float inv = __fdividef(1.0f, sum);
                 if (ad.thr) {   // attention dropout: dP = m * dP~ with the forward's mask m in {0, 1/keep}
                     const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
 #pragma unroll
