@@ -183,11 +183,13 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         uint8_t* sV = sQ + 16384;
         if (tid == 0) {
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
-            tma_store_wait_read0();      // the previous unit's output boxes (staged in the P tile) have left shared memory
             tc_fence_after();
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
             tc_mma_bf16(tmem, qd, kd, idesc1, 0);
             tc_mma_bf16(tmem, qd + 2, kd + 2, idesc1, 1);   // +32 B: second K=16 slice of the 64 B rows
+            // the previous unit's output box (staged in the P tile) must have left shared memory before any thread rewrites the
+            // tile: waited for while the MMAs run, and before the commit that releases the softmax threads
+            tma_store_wait_read0();
             tc_commit(bar_mma);
             // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
             if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
@@ -224,18 +226,22 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
                 for (int j = 0; j < WT; j++)
                     if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
             }
-            float mx = -INFINITY;
+            // four independent chains per reduction: with one warp per scheduler and CTA, a 49-long dependent chain of
+            // FMNMX / FADD costs its full latency (~4 clk per link)
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < WT; j++) mx = fmaxf(mx, s[j]);
+            for (int j = 0; j < WT; j++) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             // the row sum is the fp32 one (the reference normalises in fp32 and rounds P afterwards, TV:...:210-214)
-            float sum = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < WT; j += 2) {
                 const float p0 = ex2_fast(s[j] - mx);
                 const float p1 = (j + 1 < WT) ? ex2_fast(s[j + 1] - mx) : 0.f;
-                sum += p0 + p1;
+                s4[(j >> 1) & 3] += p0 + p1;
                 pk[j >> 1] = pk2(p0, p1);
             }
+            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             inv = __fdividef(ad.inv_keep, sum);
             if (ad.thr) {   // attention dropout: dropped probabilities leave the P tile (the row sum above is the undropped one)
                 const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
@@ -376,43 +382,207 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
 constexpr int AB_TILE = 8 * 1024;          // one [128 x 32] bf16 operand tile (two 64-row boxes)
 constexpr int AB_X = 16 * 1024;            // one [128 x 64] bf16 P / dS tile
 constexpr int AB_OPS = 4 * AB_TILE;        // one stage of Q, K, V, dO
-constexpr int AB_SMEM = 2 * AB_X + 2 * AB_OPS + AT_BIAS_BYTES + 64 + 1024;
+constexpr int AB_XCH = 3 * 2 * 128 * 4;    // row-pair exchange slots: [max | sum | dot][part][row]
+constexpr int AB_STAGES = 3;               // operand stages
+constexpr int AB_SMEM = 2 * 2 * AB_X + AB_STAGES * AB_OPS + AT_BIAS_BYTES + AB_XCH + 256 + 1024;
+constexpr int AB_THREADS = 13 * 32;
+constexpr int AB_KSPLIT = 24;              // part 0 owns keys [0, 24), part 1 keys [24, 49)
 
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void pair_sync(int wq) {   // the two warps that share TMEM lane quadrant wq
+    switch (wq) {           // immediate ids: a register id makes ptxas reserve all 16 named barriers
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+
+// Backward kernel.  256 threads: TWO threads per query row (the tensor memory caps a CTA at 256 columns = 2 CTAs per SM, and
+// with one thread per row that was 2 warps per scheduler, each a ~1100-instruction serial stream per unit: issue slots 35 %
+// used).  Warps w and w + 4 read the same TMEM lane quadrant; part 0 (warps 0-3) owns keys [0, 24) of the row, part 1 keys
+// [24, 49): three 16 B chunks of the P / dS tile rows each (+ the zero tail), 24 / 25 d(bias) accumulators, and half of the
+// dq / dk / dv epilogue columns.  Row maximum, row sum and sum_j e_j dP_j are exchanged through shared memory with a 64-thread
+// named barrier per warp pair (two exchanges per unit).
 // Operand tiles are double buffered (the loads of unit n+1 are issued before unit n is touched).  dV / dK of window w
 // use ONE MN-major A descriptor over the compact tile with the two 64-key chunks 8 KB apart (= the two windows' row
 // blocks): the products of window w's rows land in TMEM lanes 64 w .. 64 w + 63 (the other half holds unused values),
-// so every thread drains its own key row of dV, dK and its query row of dQ — a balanced epilogue.
-__global__ void __launch_bounds__(128, 2)
+// so every row's dq, dk and dv come from its own lane — a balanced epilogue.
+template <int PART>
+__device__ __forceinline__ void winattn_bwd_rows(uint32_t trow, const float* __restrict__ brow_base, bool row_ok, const MaskInfoTc& mi,
+                                                 int i, int row, int wq, float* xch, const AttnDrop& ad, uint32_t rowkey,
+                                                 uint32_t ds0, uint32_t ds1, float (&acc)[25], uint8_t* prow, uint8_t* srow,
+                                                 uint64_t* tile_free, uint32_t tile_parity, bool tile_wait) {
+    constexpr int KB = PART == 0 ? 0 : AB_KSPLIT;           // first key of this part
+    constexpr int NK = PART == 0 ? AB_KSPLIT : WT - AB_KSPLIT;   // 24 / 25 keys
+    float s[32], dp[32];
+    {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        uint32_t* dr = reinterpret_cast<uint32_t*>(dp);
+        if (PART == 0) {
+            tc_ld16_nowait(trow, sr);
+            tc_ld8_nowait(trow + 16, sr + 16);
+            tc_ld16_nowait(trow + 128, dr);
+            tc_ld8_nowait(trow + 128 + 16, dr + 16);
+        } else {
+            tc_ld8_nowait(trow + 24, sr);
+            tc_ld16_nowait(trow + 32, sr + 8);
+            tc_ld8_nowait(trow + 48, sr + 24);
+            tc_ld8_nowait(trow + 128 + 24, dr);
+            tc_ld16_nowait(trow + 128 + 32, dr + 8);
+            tc_ld8_nowait(trow + 128 + 48, dr + 24);
+        }
+        tc_ld_wait();
+    }
+    float* x_max = xch, *x_sum = xch + 256, *x_dot = xch + 512;
+    float mpart = -INFINITY;
+    if (row_ok) {
+        const float2* brow = reinterpret_cast<const float2*>(brow_base + KB);
+#pragma unroll
+        for (int j = 0; j < (NK + 1) / 2; j++) {            // log2-domain logits (column 49 of the padded bias row is 0)
+            const float2 b2 = brow[j];
+            s[2 * j] = fmaf(s[2 * j], ATT_SCALE * LOG2E, b2.x);
+            s[2 * j + 1] = fmaf(s[2 * j + 1], ATT_SCALE * LOG2E, b2.y);
+        }
+        if (mi.any) {                                        // warp-uniform (see the forward kernel)
+            const uint64_t allowed = mask_allowed_tc(mi, i) >> KB;
+#pragma unroll
+            for (int j = 0; j < NK; j++)
+                if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < NK; j++) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+        mpart = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    }
+    x_max[PART * 128 + row] = mpart;
+    pair_sync(wq);
+    const float mx = fmaxf(mpart, x_max[(PART ^ 1) * 128 + row]);
+    float spart = 0.f, dpart = 0.f;
+    if (row_ok) {
+        if (ad.thr) {   // attention dropout: dP = m * dP~ with the forward's mask m in {0, 1/keep}
+#pragma unroll
+            for (int jp = 0; jp < (NK + 1) / 2; jp++) {
+                const uint32_t hs = attn_drop_hash(rowkey, KB / 2 + jp, ds0, ds1);
+                dp[2 * jp] *= ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
+                if (2 * jp + 1 < NK) dp[2 * jp + 1] *= ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
+            }
+        }
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NK; j++) {
+            s[j] = ex2_fast(s[j] - mx);
+            s4[j & 3] += s[j];
+            d4[j & 3] = fmaf(s[j], dp[j], d4[j & 3]);
+        }
+        spart = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        dpart = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+    }
+    x_sum[PART * 128 + row] = spart;
+    x_dot[PART * 128 + row] = dpart;
+    pair_sync(wq);
+    uint32_t pk[16], dk_[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) { pk[j] = 0u; dk_[j] = 0u; }
+    if (row_ok) {
+        // both threads of the row add the two partial sums in the same order: identical inv / delta
+        const float sum = x_sum[row] + x_sum[128 + row];
+        const float inv = __fdividef(1.0f, sum);
+        const float delta = (x_dot[row] + x_dot[128 + row]) * inv;
+#pragma unroll
+        for (int j = 0; j < NK; j++) s[j] *= inv;                      // P
+        if (!ad.thr) {
+#pragma unroll
+            for (int j = 0; j < NK; j += 2) pk[j >> 1] = pk2(s[j], (j + 1 < NK) ? s[j + 1] : 0.f);
+        } else {        // with dropout the dV operand is P~ = m * P (the kept entries scaled by 1/keep)
+#pragma unroll
+            for (int jp = 0; jp < (NK + 1) / 2; jp++) {
+                const uint32_t hs = attn_drop_hash(rowkey, KB / 2 + jp, ds0, ds1);
+                const float m0 = ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
+                const float m1 = ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
+                pk[jp] = pk2(s[2 * jp] * m0, (2 * jp + 1 < NK) ? s[2 * jp + 1] * m1 : 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NK; j++) {
+            dp[j] = s[j] * (dp[j] - delta);   // dS
+            acc[j] += dp[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NK; j += 2) dk_[j >> 1] = pk2(dp[j], (j + 1 < NK) ? dp[j + 1] : 0.f);
+    }
+    // own 16 B chunks of row `row` of both compact tiles (128 B rows, 128B swizzle); zeros for padding rows and for the
+    // key tail 49..63 (they are contracted over in dV / dK).  The tile buffer was the staging box of the unit two back:
+    // its TMA store must have drained.
+    if (tile_wait) mbar_wait(tile_free, tile_parity);
+    constexpr int C0 = PART == 0 ? 0 : 3, NC = PART == 0 ? 3 : 5;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const int sw = ((C0 + c) ^ (row & 7)) << 4;
+        const uint4 pv = c < 4 ? make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]) : make_uint4(0, 0, 0, 0);
+        const uint4 sv = c < 4 ? make_uint4(dk_[4 * c], dk_[4 * c + 1], dk_[4 * c + 2], dk_[4 * c + 3]) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(prow + sw) = pv;
+        *reinterpret_cast<uint4*>(srow + sw) = sv;
+    }
+}
+
+// Persistent, warp-specialised: ONE CTA per SM with all 512 TMEM columns = two S / dP buffers, so that two units are in
+// flight per CTA and the softmax group never waits for its own unit's MMAs:
+//   warps 0-7   softmax group (two threads per row, see winattn_bwd_rows): unit n in TMEM buffer n & 1, P / dS tiles n & 1
+//   warps 8-11  epilogue group (one thread per row): dq / dk / dv of unit n from buffer n & 1 -> staging box -> TMA store;
+//               warp 8 lane 0 also issues the TMA loads (unit n + 3 into the operand stage unit n has just released)
+//   warp  12    MMA issuer (one thread): dV / dK / dQ of unit n when its tiles are written, S / dP of unit n + 2 as soon as
+//               the epilogue group has drained buffer n & 1.  It has a warp of its own: the twelve dV / dK / dQ MMAs execute in
+//               ~1300 clk (MN-major operands: shared-memory-read bound) and the issuing thread blocks behind them.
+// (Register files are allocated to warps in groups of four: 13 warps count as 16, 128 registers per thread.)
+// Per TMEM buffer the cycle is S / dP MMAs -> softmax -> dV / dK / dQ MMAs -> drain; with two buffers a unit costs
+// max(softmax, half that cycle).  The one-unit-at-a-time version (2 CTAs per SM) spent a third of every warp's time waiting
+// for its own unit's MMAs (~850 clk for S / dP, ~1150 clk for the twelve shared-memory-read-bound dV / dK / dQ MMAs).
+__global__ void __launch_bounds__(AB_THREADS, 1)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmQKV4, const __grid_constant__ CUtensorMap tmDO3,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
                       int64_t n_windows, int nH, WinGeo g, AttnDrop ad, long long* trace) {
-#ifdef MSU_ATT_TRACE_BUILD   // phase timeline (debug builds only: even a predicated-off clock read costs issue slots in this kernel)
-#define AT_TRACE(ev) do { if (trace != nullptr && tid == 0 && blockIdx.y == 0 && it < 8) trace[((size_t)blockIdx.x * 8 + it) * 8 + (ev)] = clock64(); } while (0)
+#ifdef MSU_ATT_TRACE_BUILD   // phase timeline (debug builds only), first 8 units of CTAs with blockIdx.y == 0: [cta][unit][16 events]
+#define AB_TRACE(ev) do { if (trace != nullptr && lane == 0 && blockIdx.y == 0 && n < 8) trace[((size_t)blockIdx.x * 8 + n) * 16 + (ev)] = clock64(); } while (0)
 #else
-#define AT_TRACE(ev) do { } while (0)
+#define AB_TRACE(ev) do { } while (0)
 #endif
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sXP = smem;                        // P rows
-    uint8_t* sXS = sXP + AB_X;                  // dS rows
-    uint8_t* sOps = sXS + AB_X;                 // [2][Q | K | V | dO]
-    float* sBias = reinterpret_cast<float*>(sOps + 2 * AB_OPS);
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);   // [2]
-    uint64_t* bar_mma = bar_load + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* sTiles = smem;                             // [2][P 16 KB | dS 16 KB]
+    uint8_t* sOps = sTiles + 2 * 2 * AB_X;              // [AB_STAGES][Q | K | V | dO]
+    float* sBias = reinterpret_cast<float*>(sOps + AB_STAGES * AB_OPS);
+    float* sXch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBias) + AT_BIAS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sXch) + AB_XCH);
+    uint64_t* full = bars;                              // [AB_STAGES] operands landed
+    uint64_t* s_ready = full + AB_STAGES;               // [2] S / dP in TMEM
+    uint64_t* tiles_ready = s_ready + 2;                // [2] P / dS tiles written (8 softmax warps)
+    uint64_t* out_ready = tiles_ready + 2;              // [2] dV / dK / dQ in TMEM (their MMAs retired: tiles and operand stage free)
+    uint64_t* buf_free = out_ready + 2;                 // [2] the epilogue group has drained the TMEM buffer (4 warps)
+    uint64_t* tile_free = buf_free + 2;                 // [2] the staging box has left the tile buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = nH * HD;
     const int h = blockIdx.y;
-    stage_bias_tc(sBias, bias, h, tid);
+    if (tid < 128) stage_bias_tc(sBias, bias, h, tid);
     if (tid == 0) {
-        mbar_init(&bar_load[0], 1);
-        mbar_init(&bar_load[1], 1);
-        mbar_init(bar_mma, 1);
+        for (int k = 0; k < AB_STAGES; k++) mbar_init(&full[k], 1);
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&s_ready[k], 1);
+            mbar_init(&tiles_ready[k], 8);
+            mbar_init(&out_ready[k], 1);
+            mbar_init(&buf_free[k], 4);
+            mbar_init(&tile_free[k], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -421,157 +591,157 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const uint32_t tmem = *tmem_slot;
 
     const int64_t n_pairs = (n_windows + 1) / 2;
+    const int n_units = (int)((n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x);    // pairs blockIdx.x, + gridDim.x, ...
     const int nwin_img = g.nwin();
-    const int half = tid >> 6, i = tid & 63;
-    const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
-    const uint32_t id_kv = make_idesc_bf16(128, 64, 1, 1);     // dV, dK: A MN-major, B MN-major (both windows' columns)
-    const uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
-    uint32_t ph_mma = 0;
-    const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
-    float acc[WT];
-#pragma unroll
-    for (int j = 0; j < WT; j++) acc[j] = 0.f;
 
-    auto issue_loads = [&](int64_t pair, int buf) {
-        uint8_t* q = sOps + buf * AB_OPS;
-        mbar_arrive_expect_tx(&bar_load[buf], 8 * 4096);
-        if (pair + 1 < n_pairs) {   // two boxes per unit instead of eight (see the forward kernel); the last pair stays bounds-checked
-            tma_load_4d(q, &tmQKV4, &bar_load[buf], h * HD, 0, (int)(pair * 2), 0);
-            tma_load_3d(q + 3 * AB_TILE, &tmDO3, &bar_load[buf], h * HD, 0, (int)(pair * 2));
-            return;
-        }
-        const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
-        tma_load_2d(q, &tmQKV, &bar_load[buf], h * HD, r0);
-        tma_load_2d(q + 4096, &tmQKV, &bar_load[buf], h * HD, r1);
-        tma_load_2d(q + AB_TILE, &tmQKV, &bar_load[buf], C + h * HD, r0);
-        tma_load_2d(q + AB_TILE + 4096, &tmQKV, &bar_load[buf], C + h * HD, r1);
-        tma_load_2d(q + 2 * AB_TILE, &tmQKV, &bar_load[buf], 2 * C + h * HD, r0);
-        tma_load_2d(q + 2 * AB_TILE + 4096, &tmQKV, &bar_load[buf], 2 * C + h * HD, r1);
-        tma_load_2d(q + 3 * AB_TILE, &tmDO, &bar_load[buf], h * HD, r0);
-        tma_load_2d(q + 3 * AB_TILE + 4096, &tmDO, &bar_load[buf], h * HD, r1);
-    };
-    if (tid == 0 && (int64_t)blockIdx.x < n_pairs) issue_loads(blockIdx.x, 0);
-
-    int it = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, it++) {
-        const int buf = it & 1;
-        const int64_t win = pair * 2 + half;
-        uint8_t* sQ = sOps + buf * AB_OPS;
-        uint8_t* sK = sQ + AB_TILE;
-        uint8_t* sV = sK + AB_TILE;
-        uint8_t* sD = sV + AB_TILE;                 // dO
-        AT_TRACE(0);
-        if (tid == 0) {
-            mbar_wait(&bar_load[buf], (it >> 1) & 1);
-            tma_store_wait_read0();      // the previous unit's output boxes (staged in the P / dS tiles) have left shared memory
+    if (warp < 8) {
+        // ===================== softmax group =====================
+        const int wq = warp & 3, part = warp >> 2;
+        const int row = wq * 32 + lane;             // query row of the unit's 128 (TMEM lane)
+        const int half = row >> 6, i = row & 63;
+        const uint32_t ds0 = ad.thr ? ad.seed[0] : 0u, ds1 = ad.thr ? ad.seed[1] : 0u;
+        float acc[25];
+#pragma unroll
+        for (int j = 0; j < 25; j++) acc[j] = 0.f;
+        const float* brow = sBias + i * AT_BROW;
+        for (int n = 0; n < n_units; n++) {
+            const int b = n & 1;
+            const uint32_t par = (uint32_t)(n >> 1) & 1u;
+            const int64_t pair = blockIdx.x + (int64_t)n * gridDim.x;
+            const int64_t win = pair * 2 + half;
+            const bool row_ok = (i < WT) && (win < n_windows);
+            const MaskInfoTc mi = mask_info_tc(g, (int)((uint32_t)win % (uint32_t)nwin_img));
+            const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
+            uint8_t* sXP = sTiles + b * 2 * AB_X;
+            uint8_t* sXS = sXP + AB_X;
+            if (warp == 0) AB_TRACE(0);
+            mbar_wait(&s_ready[b], par);
             tc_fence_after();
-            AT_TRACE(1);
-            const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
-            const uint64_t vd = make_desc_kmajor_sw64(smem_u32(sV)), dd = make_desc_kmajor_sw64(smem_u32(sD));
-            tc_mma_bf16(tmem, qd, kd, id_s, 0);
-            tc_mma_bf16(tmem, qd + 2, kd + 2, id_s, 1);
-            tc_mma_bf16(tmem + 128, dd, vd, id_s, 0);
-            tc_mma_bf16(tmem + 128, dd + 2, vd + 2, id_s, 1);
-            tc_commit(bar_mma);
-            // the other stage was last read by the MMAs of unit it-1, which completed before that unit's epilogue
-            if (pair + gridDim.x < n_pairs) issue_loads(pair + gridDim.x, buf ^ 1);
+            if (warp == 0) AB_TRACE(1);
+            const uint32_t trow = tmem + b * 256 + ((uint32_t)(wq * 32) << 16) + half * 64;
+            if (part == 0) winattn_bwd_rows<0>(trow, brow, row_ok, mi, i, row, wq, sXch, ad, rowkey, ds0, ds1, acc, sXP + row * 128, sXS + row * 128,
+                                               &tile_free[b], par ^ 1u, n >= 2);
+            else winattn_bwd_rows<1>(trow, brow, row_ok, mi, i, row, wq, sXch, ad, rowkey, ds0, ds1, acc, sXP + row * 128, sXS + row * 128,
+                                     &tile_free[b], par ^ 1u, n >= 2);
+            fence_proxy_async_smem();               // tile rows (generic proxy) -> visible to the MMAs (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tiles_ready[b]);
+            if (warp == 0) AB_TRACE(2);
         }
-        const bool row_ok = (i < WT) && (win < n_windows);
-        const MaskInfoTc mi = mask_info_tc(g, (int)((uint32_t)win % (uint32_t)nwin_img));
-        const float2* brow = reinterpret_cast<const float2*>(sBias + i * AT_BROW);
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
-        AT_TRACE(2);
-        uint32_t pk[32], dk_[32];
+        // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i, this part's keys
+        if (i < WT) {
+            float* out = dbias_partial + (((int64_t)blockIdx.x * 2 + half) * nH + h) * (WT * WT) + i * WT + (part ? AB_KSPLIT : 0);
+            const int nk = part ? WT - AB_KSPLIT : AB_KSPLIT;
 #pragma unroll
-        for (int j = 0; j < 32; j++) { pk[j] = 0u; dk_[j] = 0u; }
-        {
-            float s[64], dp[64];
-            {
-                uint32_t* sr = reinterpret_cast<uint32_t*>(s);
-                uint32_t* dr = reinterpret_cast<uint32_t*>(dp);
-                const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + half * 64;
-                tc_ld32_nowait(trow, sr);
-                tc_ld32_nowait(trow + 32, sr + 32);
-                tc_ld32_nowait(trow + 128, dr);
-                tc_ld32_nowait(trow + 160, dr + 32);
-                tc_ld_wait();
-            }
-            if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 25; j++) {                   // log2-domain logits (column 49 of the padded bias row is 0)
-                    const float2 b2 = brow[j];
-                    s[2 * j] = fmaf(s[2 * j], ATT_SCALE * LOG2E, b2.x);
-                    s[2 * j + 1] = fmaf(s[2 * j + 1], ATT_SCALE * LOG2E, b2.y);
-                }
-                if (mi.any) {                                    // warp-uniform (see the forward kernel)
-                    const uint64_t allowed = mask_allowed_tc(mi, i);
-#pragma unroll
-                    for (int j = 0; j < WT; j++)
-                        if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
-                }
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < WT; j++) mx = fmaxf(mx, s[j]);
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < WT; j++) { s[j] = ex2_fast(s[j] - mx); sum += s[j]; }
-                const float inv = __fdividef(1.0f, sum);
-                if (ad.thr) {   // attention dropout: dP = m * dP~ with the forward's mask m in {0, 1/keep}
-                    const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
-#pragma unroll
-                    for (int jp = 0; jp < 25; jp++) {
-                        const uint32_t hs = attn_drop_hash(rowkey, jp, ds0, ds1);
-                        dp[2 * jp] *= ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
-                        if (2 * jp + 1 < WT) dp[2 * jp + 1] *= ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
-                    }
-                }
-                float delta = 0.f;
-#pragma unroll
-                for (int j = 0; j < WT; j++) { s[j] *= inv; delta = fmaf(s[j], dp[j], delta); }
-#pragma unroll
-                for (int j = 0; j < WT; j += 2)   // P tile for dV: without dropout the probabilities themselves
-                    pk[j >> 1] = pk2(s[j], (j + 1 < WT) ? s[j + 1] : 0.f);
-                if (ad.thr) {   // with dropout: P~ = m * P (the kept entries scaled by 1/keep)
-                    const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
-#pragma unroll
-                    for (int jp = 0; jp < 25; jp++) {
-                        const uint32_t hs = attn_drop_hash(rowkey, jp, ds0, ds1);
-                        const float m0 = ((hs & 0xffffu) >= ad.thr) ? ad.inv_keep : 0.f;
-                        const float m1 = ((hs >> 16) >= ad.thr) ? ad.inv_keep : 0.f;
-                        pk[jp] = pk2(s[2 * jp] * m0, (2 * jp + 1 < WT) ? s[2 * jp + 1] * m1 : 0.f);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < WT; j++) {
-                    dp[j] = s[j] * (dp[j] - delta);   // dS
-                    acc[j] += dp[j];
-                }
-#pragma unroll
-                for (int j = 0; j < WT; j += 2)
-                    dk_[j >> 1] = pk2(dp[j], (j + 1 < WT) ? dp[j + 1] : 0.f);
-            }
+            for (int j = 0; j < 25; j++)
+                if (j < nk) out[j] = acc[j];
         }
-        AT_TRACE(3);
-        {   // row tid of both compact tiles (zeros for padding rows: they are contracted over in dV / dK)
-            uint8_t* prow = sXP + tid * 128;
-            uint8_t* srow = sXS + tid * 128;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int sw = (c ^ (tid & 7)) << 4;
-                *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                *reinterpret_cast<uint4*>(srow + sw) = make_uint4(dk_[4 * c], dk_[4 * c + 1], dk_[4 * c + 2], dk_[4 * c + 3]);
+    } else if (warp < 12) {
+        // ===================== epilogue group (warp 8 lane 0 also issues the TMA loads and the TMA store) =====================
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int half = row >> 6, i = row & 63;
+        const bool is_tma = (warp == 8 && lane == 0);
+        auto issue_loads = [&](int n) {                  // unit n -> stage n % AB_STAGES (the caller knows the stage is free)
+            const int st = n % AB_STAGES;
+            const int64_t pair = blockIdx.x + (int64_t)n * gridDim.x;
+            uint8_t* q = sOps + st * AB_OPS;
+            mbar_arrive_expect_tx(&full[st], 8 * 4096);
+            if (pair + 1 < n_pairs) {   // two boxes per unit instead of eight (see the forward kernel); the last pair stays bounds-checked
+                tma_load_4d(q, &tmQKV4, &full[st], h * HD, 0, (int)(pair * 2), 0);
+                tma_load_3d(q + 3 * AB_TILE, &tmDO3, &full[st], h * HD, 0, (int)(pair * 2));
+                return;
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        __syncthreads();
-        AT_TRACE(4);
-        if (tid == 0) {
+            const int r0 = (int)(pair * 2 * WT), r1 = r0 + WT;
+            tma_load_2d(q, &tmQKV, &full[st], h * HD, r0);
+            tma_load_2d(q + 4096, &tmQKV, &full[st], h * HD, r1);
+            tma_load_2d(q + AB_TILE, &tmQKV, &full[st], C + h * HD, r0);
+            tma_load_2d(q + AB_TILE + 4096, &tmQKV, &full[st], C + h * HD, r1);
+            tma_load_2d(q + 2 * AB_TILE, &tmQKV, &full[st], 2 * C + h * HD, r0);
+            tma_load_2d(q + 2 * AB_TILE + 4096, &tmQKV, &full[st], 2 * C + h * HD, r1);
+            tma_load_2d(q + 3 * AB_TILE, &tmDO, &full[st], h * HD, r0);
+            tma_load_2d(q + 3 * AB_TILE + 4096, &tmDO, &full[st], h * HD, r1);
+        };
+        if (is_tma)
+            for (int n = 0; n < AB_STAGES && n < n_units; n++) issue_loads(n);
+        for (int n = 0; n < n_units; n++) {
+            const int b = n & 1;
+            const uint32_t par = (uint32_t)(n >> 1) & 1u;
+            const int64_t pair = blockIdx.x + (int64_t)n * gridDim.x;
+            uint8_t* sStage = sTiles + b * 2 * AB_X;     // the unit's own tile buffer, once its MMAs have retired
+            mbar_wait(&out_ready[b], par);
             tc_fence_after();
-            const uint32_t xp = smem_u32(sXP), xs = smem_u32(sXS);
-            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sD);
+            if (warp == 8) AB_TRACE(8);
+            if (is_tma && n + AB_STAGES < n_units) issue_loads(n + AB_STAGES);   // the unit's operand stage is free
+            // own query row of dQ and own key row of dK, dV (lanes 64..127 hold window b)
+            float dq[32], dkk[32], dvv[32];
+            const uint32_t lane_base = tmem + b * 256 + ((uint32_t)(wq * 32) << 16) + half * 32;
+            tc_ld32_nowait(lane_base + 128, reinterpret_cast<uint32_t*>(dq));
+            tc_ld32_nowait(lane_base + 64, reinterpret_cast<uint32_t*>(dkk));
+            tc_ld32_nowait(lane_base, reinterpret_cast<uint32_t*>(dvv));
+            tc_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&buf_free[b]);    // S / dP of unit n + 2 may overwrite the buffer
+            // rows -> ONE staging box [dq | dk | dv][2 windows][49 rows][32] (64 B rows, 64B swizzle on the box-row index):
+            // the unit's 18.4 KB of gradients leave as one TMA store
+            if (i < WT) {
+                const int R0 = half * WT + i, R1 = R0 + 2 * WT, R2 = R0 + 4 * WT;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    *reinterpret_cast<uint4*>(sStage + R0 * 64 + ((c ^ ((R0 >> 1) & 3)) << 4)) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
+                        pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
+                        pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
+                    *reinterpret_cast<uint4*>(sStage + R1 * 64 + ((c ^ ((R1 >> 1) & 3)) << 4)) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
+                        pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
+                        pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
+                    *reinterpret_cast<uint4*>(sStage + R2 * 64 + ((c ^ ((R2 >> 1) & 3)) << 4)) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
+                        pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
+                }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 5, 128;" ::: "memory");          // the four epilogue warps
+            if (is_tma) {
+                tma_store_4d(sStage, &tmOut, h * HD, 0, (int)(pair * 2), 0);     // a window index past the end (odd count) is clipped by TMA
+                tma_store_commit();
+                tma_store_wait_read0();                  // the box has left shared memory: the softmax group may reuse the tiles
+                mbar_arrive(&tile_free[b]);
+                AB_TRACE(9);
+            }
+        }
+        if (is_tma) tma_store_wait_all();
+    } else if (lane == 0) {
+        // ===================== MMA issuer (one thread) =====================
+        const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
+        const uint32_t id_kv = make_idesc_bf16(128, 64, 1, 1);     // dV, dK: A MN-major, B MN-major (both windows' columns)
+        const uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
+        auto mma1 = [&](int n) {                         // S and dP of unit n into TMEM buffer n & 1 (the caller knows it is free)
+            const int st = n % AB_STAGES;
+            mbar_wait(&full[st], (uint32_t)(n / AB_STAGES) & 1u);
+            tc_fence_after();
+            const uint8_t* q = sOps + st * AB_OPS;
+            const uint64_t qd = make_desc_kmajor_sw64(smem_u32(q)), kd = make_desc_kmajor_sw64(smem_u32(q + AB_TILE));
+            const uint64_t vd = make_desc_kmajor_sw64(smem_u32(q + 2 * AB_TILE)), dd = make_desc_kmajor_sw64(smem_u32(q + 3 * AB_TILE));
+            const uint32_t t = tmem + (n & 1) * 256;
+            tc_mma_bf16(t, qd, kd, id_s, 0);
+            tc_mma_bf16(t, qd + 2, kd + 2, id_s, 1);
+            tc_mma_bf16(t + 128, dd, vd, id_s, 0);
+            tc_mma_bf16(t + 128, dd + 2, vd + 2, id_s, 1);
+            tc_commit(&s_ready[n & 1]);
+        };
+        for (int n = 0; n < 2 && n < n_units; n++) mma1(n);
+        for (int n = 0; n < n_units; n++) {
+            const int b = n & 1, st = n % AB_STAGES;
+            const uint32_t par = (uint32_t)(n >> 1) & 1u;
+            AB_TRACE(4);
+            mbar_wait(&tiles_ready[b], par);
+            tc_fence_after();
+            AB_TRACE(5);
+            const uint8_t* q = sOps + st * AB_OPS;
+            const uint32_t xp = smem_u32(sTiles + b * 2 * AB_X), xs = xp + AB_X;
+            const uint32_t qa = smem_u32(q), ka = qa + AB_TILE, da = qa + 3 * AB_TILE;
+            const uint32_t t = tmem + b * 256;
 #pragma unroll
             for (int k = 0; k < 4; k++) {   // contraction over 16 rows of both windows per step (2 KB of X, 1 KB of B per window)
                 // A: M chunk 0 = keys of window a (rows [16k, 16k+16) of block a), chunk 1 = 8 KB further = block b.
@@ -579,65 +749,28 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 // [64 w, 64 w + 64) hold window w's result in columns [32 w, 32 w + 32), the rest is unused
                 const uint64_t ap = make_desc_mnmajor_sw128(xp + k * 2048, 8192);
                 const uint64_t as = make_desc_mnmajor_sw128(xs + k * 2048, 8192);
-                tc_mma_bf16(tmem, ap, make_desc_mnmajor_sw64(da + k * 1024, 4096), id_kv, k != 0);        // dV
-                tc_mma_bf16(tmem + 64, as, make_desc_mnmajor_sw64(qa + k * 1024, 4096), id_kv, k != 0);   // dK
+                tc_mma_bf16(t, ap, make_desc_mnmajor_sw64(da + k * 1024, 4096), id_kv, k != 0);        // dV
+                tc_mma_bf16(t + 64, as, make_desc_mnmajor_sw64(qa + k * 1024, 4096), id_kv, k != 0);   // dK
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {   // contraction over the 64 own keys: +32 B per step inside the 128 B rows
                 const uint64_t as = make_desc_kmajor_sw128(xs + k * 32);
-                tc_mma_bf16(tmem + 128, as, make_desc_mnmajor_sw64(ka + k * 1024, 4096), id_q, k != 0);   // dQ
+                tc_mma_bf16(t + 128, as, make_desc_mnmajor_sw64(ka + k * 1024, 4096), id_q, k != 0);   // dQ
             }
-            tc_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
-        AT_TRACE(5);
-        {
-            // own query row of dQ and own key row of dK, dV (lanes 64..127 hold window b): three 64 B stores per thread
-            float dq[32], dkk[32], dvv[32];
-            const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-            tc_ld32_nowait(lane_base + 128 + half * 32, reinterpret_cast<uint32_t*>(dq));
-            tc_ld32_nowait(lane_base + 64 + half * 32, reinterpret_cast<uint32_t*>(dkk));
-            tc_ld32_nowait(lane_base + half * 32, reinterpret_cast<uint32_t*>(dvv));
-            tc_ld_wait();
-            // rows -> ONE staging box [dq | dk | dv][2 windows][49 rows][32] (64 B rows, 64B swizzle on the box-row index) in the
-            // P / dS tiles (consumed by the MMAs above): the unit's 18.4 KB of gradients leave as one TMA store
-            if (i < WT) {
-            const int R0 = half * WT + i, R1 = R0 + 2 * WT, R2 = R0 + 4 * WT;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                *reinterpret_cast<uint4*>(sXP + R0 * 64 + ((c ^ ((R0 >> 1) & 3)) << 4)) = make_uint4(pk2(dq[8 * c] * ATT_SCALE, dq[8 * c + 1] * ATT_SCALE),
-                    pk2(dq[8 * c + 2] * ATT_SCALE, dq[8 * c + 3] * ATT_SCALE), pk2(dq[8 * c + 4] * ATT_SCALE, dq[8 * c + 5] * ATT_SCALE),
-                    pk2(dq[8 * c + 6] * ATT_SCALE, dq[8 * c + 7] * ATT_SCALE));
-                *reinterpret_cast<uint4*>(sXP + R1 * 64 + ((c ^ ((R1 >> 1) & 3)) << 4)) = make_uint4(pk2(dkk[8 * c] * ATT_SCALE, dkk[8 * c + 1] * ATT_SCALE),
-                    pk2(dkk[8 * c + 2] * ATT_SCALE, dkk[8 * c + 3] * ATT_SCALE), pk2(dkk[8 * c + 4] * ATT_SCALE, dkk[8 * c + 5] * ATT_SCALE),
-                    pk2(dkk[8 * c + 6] * ATT_SCALE, dkk[8 * c + 7] * ATT_SCALE));
-                *reinterpret_cast<uint4*>(sXP + R2 * 64 + ((c ^ ((R2 >> 1) & 3)) << 4)) = make_uint4(pk2(dvv[8 * c], dvv[8 * c + 1]), pk2(dvv[8 * c + 2], dvv[8 * c + 3]),
-                    pk2(dvv[8 * c + 4], dvv[8 * c + 5]), pk2(dvv[8 * c + 6], dvv[8 * c + 7]));
-            }
+            tc_commit(&out_ready[b]);
+            AB_TRACE(6);
+            if (n + 2 < n_units) {                       // S / dP of unit n + 2 as soon as the epilogue group has drained the buffer
+                mbar_wait(&buf_free[b], par);
+                mma1(n + 2);
+                AB_TRACE(7);
             }
         }
-        AT_TRACE(6);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_4d(sXP, &tmOut, h * HD, 0, (int)(pair * 2), 0);     // a window index past the end (odd count) is clipped by TMA
-            tma_store_commit();
-        }
-        AT_TRACE(7);
     }
-    if (tid == 0) tma_store_wait_all();
-    // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i
-    if (i < WT) {
-        float* out = dbias_partial + (((int64_t)blockIdx.x * 2 + half) * nH + h) * (WT * WT) + i * WT;
-#pragma unroll
-        for (int j = 0; j < WT; j++) out[j] = acc[j];
-    }
-    if (warp == 0) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
 }
 
@@ -653,7 +786,7 @@ static bool make_attn_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_
 
 int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
     const int64_t pairs = (n_windows + 1) / 2;
-    return (int)imax(1, imin(pairs, ((int64_t)num_sms() * 2) / nH));   // whole waves of the 2 resident CTAs per SM
+    return (int)imax(1, imin(pairs, (int64_t)num_sms() / nH));         // persistent: one CTA per SM
 }
 
 // returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
@@ -674,32 +807,38 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         attr.set();
     }
     dim3 grid(winattn_bwd_tc_grid(n_windows, nH), nH);
+    long long* trace_buf = nullptr;
+#ifdef MSU_ATT_TRACE_BUILD
     static const int trace_on = getenv("MSU_ATT_TRACE") ? atoi(getenv("MSU_ATT_TRACE")) : 0;
-    static long long* trace_buf = nullptr;
-    const size_t trace_n = (size_t)grid.x * 8 * 8;
+    const size_t trace_n = (size_t)grid.x * 8 * 16;
     if (trace_on) {
-        if (trace_buf != nullptr) cudaFree(trace_buf);
         cudaMalloc(&trace_buf, trace_n * sizeof(long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
     }
-    winattn_bwd_tc_kernel<<<grid, 128, AB_SMEM, st>>>(tmQKV, tmDO, tmQKV4, tmDO3, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
-                                                    trace_on ? trace_buf : nullptr);
-    if (trace_on) {   // debug only: synchronous dump of the per-unit phase timeline of two CTAs
+#endif
+    winattn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQKV, tmDO, tmQKV4, tmDO3, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
+                                                             trace_buf);
+#ifdef MSU_ATT_TRACE_BUILD
+    if (trace_on) {   // synchronous dump of the per-unit role timeline of two CTAs
         long long* host = (long long*)malloc(trace_n * sizeof(long long));
         cudaStreamSynchronize(st);
         cudaMemcpy(host, trace_buf, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
-        static const char* names[8] = {"start", "loaded", "S_dP_ready", "softmax_done", "tiles_synced", "mma2_done", "stored", "end"};
+        static const char* names[10] = {"sm_wait", "sm_S_ready", "sm_tiles_done", "-", "mma_wait_tiles", "mma_tiles_ready", "mma2_issued",
+                                        "mma1_next_issued", "epi_out_ready", "epi_stored"};
         for (int cta : {0, (int)grid.x / 2}) {
-            const long long t0 = host[(size_t)cta * 64];
+            const long long t0 = host[(size_t)cta * 128];
             fprintf(stderr, "[att trace] nwin=%lld nH=%d grid=%d cta %d\n", (long long)n_windows, nH, (int)grid.x, cta);
             for (int it = 0; it < 8; it++) {
                 fprintf(stderr, "  unit %d:", it);
-                for (int ev = 0; ev < 8; ev++) fprintf(stderr, " %s=%lld", names[ev], host[((size_t)cta * 8 + it) * 8 + ev] ? host[((size_t)cta * 8 + it) * 8 + ev] - t0 : -1);
+                for (int ev = 0; ev < 10; ev++)
+                    if (ev != 3) fprintf(stderr, " %s=%lld", names[ev], host[((size_t)cta * 8 + it) * 16 + ev] ? host[((size_t)cta * 8 + it) * 16 + ev] - t0 : -1);
                 fprintf(stderr, "\n");
             }
         }
         free(host);
+        cudaFree(trace_buf);
     }
+#endif
     count_launch();
     return check_launch("winattn_bwd_tc");
 }
