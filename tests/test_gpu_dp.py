@@ -50,7 +50,8 @@ def test_two_ranks_on_one_gpu(tmp_path):
         tol = 2e-4 if prec == "fp32" else 3e-2        # bf16: the two shards round their activations independently of the full batch
         for k, g in live.items():
             e = float((r["grads"][k] - g).abs().max() / g.abs().max().clamp_min(1e-20))
-            assert e < tol, (prec, k, e)
+            # the tiny 2-window bias tables of the deep stages sum few, independently rounded terms (DESIGN section 2 gives them the wider bound)
+            assert e < (2 * tol if (prec == "bf16" and "relative_position_bias_table" in k) else tol), (prec, k, e)
         st = r["stats"]
         assert len(r["buckets"]) >= 2
         # the kernels wrote (almost) every gradient straight into its bucket slice: only the shared concat_back_dim weights,
