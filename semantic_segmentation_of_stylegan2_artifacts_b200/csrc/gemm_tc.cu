@@ -27,6 +27,53 @@
 
 namespace msu {
 
+// ---- CTA pair (cta_group::2) helpers: two CTAs of a cluster (the two SMs of a TPC) run ONE M = 256 UMMA; each holds its own
+// 128 rows of A and HALF of B's rows, so the B bytes an SM stages and its tensor core reads are halved.  In the
+// shared::cluster window the CTA rank of a pair is bit 24 of a shared-memory address: clearing it addresses the same offset
+// in the even (leader) CTA.
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads whose completion bytes are counted by the LEADER CTA's mbarrier (issued by both CTAs, each into its own shared memory)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+        smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_PEER_MASK) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     int64_t M;
@@ -36,6 +83,7 @@ struct TcParams {
     int kb1, kb2, k_split;    // k-blocks (of 64) from source 1 / source 2; column where source 2 starts in B
     int C, H, W, bmw, bmh, cblocks, tiles_x, tiles_y;  // conv geometry
     int stages;               // operand pipeline depth
+    int pair;                 // mode 4: CTA pairs (cta_group::2, M = 256): each CTA stages half of every weight tile
     int box2;                 // mode 4, MSU_CONV_2BOX=1: the two halo rows arrive as one TMA box and the three weight tiles as one 3-D
                               // box (2 boxes per K block instead of 5).  Parity-tested, but measured the same 687 us: with the box
                               // rate out of the way the kernel sits on its shared-memory bandwidth bound, so it stays off
@@ -132,7 +180,7 @@ __device__ __forceinline__ int64_t tile_row0(const TcParams& p, int mt, int r) {
 // 16 B chunk g of row `row` inside a [32 rows x 64 B] SWIZZLE_64B slab (1 KB aligned): chunk ^= (row / 2) % 4
 __device__ __forceinline__ uint32_t slab_off(int row, int g) { return (uint32_t)(row * 64 + ((g ^ ((row >> 1) & 3)) << 4)); }
 
-template <bool EPI_TMA, int TC_EPI_WARPS>
+template <bool EPI_TMA, int TC_EPI_WARPS, bool PAIR = false>
 __global__ void __launch_bounds__(32 * (2 + TC_EPI_WARPS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -153,19 +201,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int KB = p.kb1 + p.kb2;
+    // PAIR (mode 4 only): the two CTAs of a cluster take adjacent tiles (same trip count: tile and grid counts are even); the even
+    // CTA issues the M = 256 MMAs for both, every barrier the MMA thread waits on lives in its shared memory
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         for (int a = 0; a < 2 * TC_EPI_WARPS; a++) mbar_init(&auxbar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -193,6 +250,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // two image rows per tile share the three weight tiles of (dy, 32-channel block): halo rows of
                         // 130 pixels x 32 channels (64B swizzle), K = 9C walked in exact 32-channel steps (no zero padding)
                         const int dyi = kb / p.cblocks, c0 = (kb % p.cblocks) * 32;
+                        if (PAIR) {
+                            // own two halo rows + own HALF of the three weight tiles (rows [BN/2 rank, +BN/2) of each); the bytes
+                            // of both CTAs are counted by the leader's barrier
+                            const int hb = (p.BN / 2) * 64;
+                            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (2 * 130 * 64 + 3 * hb));
+                            if (p.box2) {   // two boxes per K block: both halo rows, all three taps' half tiles
+                                tma_load_4d_pair(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
+                                tma_load_3d_pair(b_dst, &tmB, &full[stage], dyi * 3 * p.C + c0, nt * p.BN + (int)cta_rank * (p.BN / 2), 0);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
+                            tma_load_4d_pair(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
+                            tma_load_4d_pair(a_dst + TC_HALO32_BYTES, &tmA, &full[stage], c0, cx - 1, cy + dyi, cb);
+                            for (int dx = 0; dx < 3; dx++)
+                                tma_load_2d_pair(b_dst + dx * hb, &tmB, &full[stage], (dyi * 3 + dx) * p.C + c0, nt * p.BN + (int)cta_rank * (p.BN / 2));
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         const int bb = p.BN * 64;
                         mbar_arrive_expect_tx(&full[stage], 2 * 130 * 64 + 3 * bb);
                         if (p.box2) {
@@ -239,9 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN, 0, 0);
+        // ===================== MMA issuer (one thread; the leader CTA's in a pair) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int it = 0;
@@ -261,19 +336,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // close to the critical path at 12 MMAs per K block): pixel shift dx = +64 B = +4 (the swizzle
                         // follows the address bits), second image row = +TC_HALO32_BYTES, weight tile of tap dx = +BN*64 B
                         const uint64_t ad = make_desc_kmajor_sw64_g(a_addr), bd = make_desc_kmajor_sw64_g(b_addr);
-                        const uint32_t bstep = (uint32_t)(p.BN * 4);
+                        const uint32_t bstep = (uint32_t)((PAIR ? p.BN / 2 : p.BN) * 4);         // a CTA of a pair holds half of a weight tile's rows
                         const uint32_t rstep = p.box2 ? (130 * 64) >> 4 : TC_HALO32_BYTES >> 4;   // one box: the rows are contiguous
                         const uint32_t acc0 = kb != 0;
 #pragma unroll
                         for (int r = 0; r < 2; r++) {
                             const uint64_t ar = ad + (uint64_t)(r * rstep);
                             const uint32_t d = d_tmem + r * 128;
-                            tc_mma_bf16(d, ar, bd, idesc, acc0);
-                            tc_mma_bf16(d, ar + 2, bd + 2, idesc, 1);
-                            tc_mma_bf16(d, ar + 4, bd + bstep, idesc, 1);
-                            tc_mma_bf16(d, ar + 6, bd + bstep + 2, idesc, 1);
-                            tc_mma_bf16(d, ar + 8, bd + 2 * bstep, idesc, 1);
-                            tc_mma_bf16(d, ar + 10, bd + 2 * bstep + 2, idesc, 1);
+                            if (PAIR) {
+                                tc_mma_bf16_pair(d, ar, bd, idesc, acc0);
+                                tc_mma_bf16_pair(d, ar + 2, bd + 2, idesc, 1);
+                                tc_mma_bf16_pair(d, ar + 4, bd + bstep, idesc, 1);
+                                tc_mma_bf16_pair(d, ar + 6, bd + bstep + 2, idesc, 1);
+                                tc_mma_bf16_pair(d, ar + 8, bd + 2 * bstep, idesc, 1);
+                                tc_mma_bf16_pair(d, ar + 10, bd + 2 * bstep + 2, idesc, 1);
+                            } else {
+                                tc_mma_bf16(d, ar, bd, idesc, acc0);
+                                tc_mma_bf16(d, ar + 2, bd + 2, idesc, 1);
+                                tc_mma_bf16(d, ar + 4, bd + bstep, idesc, 1);
+                                tc_mma_bf16(d, ar + 6, bd + bstep + 2, idesc, 1);
+                                tc_mma_bf16(d, ar + 8, bd + 2 * bstep, idesc, 1);
+                                tc_mma_bf16(d, ar + 10, bd + 2 * bstep + 2, idesc, 1);
+                            }
                         }
                     } else if (p.mode == 3) {
                         for (int dx = 0; dx < 3; dx++) {
@@ -293,10 +377,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int k = 0; k < TC_BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle row
                             tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    tc_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
+                    if (PAIR) tc_commit_pair(&empty[stage]); else tc_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull[acc]);                  // accumulator ready for the epilogue
+                if (PAIR) tc_commit_pair(&tfull[acc]); else tc_commit(&tfull[acc]);           // accumulator ready for the epilogue
                 TC_TRACE(4);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -357,7 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (cc + NSUB >= nch_tot) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
                     released = true;
                 }
                 float v[TC_CW];
@@ -455,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!released) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
             }
             if (warp == 2) TC_TRACE(7);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -565,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (c + NSUB >= nchunks && racc == p.nacc - 1) {   // this warp's last read of the accumulators: hand TMEM back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
                     released = true;
                 }
                 // ---- own accumulator row -> bf16 -> scratch (row = lane)
@@ -630,17 +714,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!released) {                               // no chunk of the last accumulator fell to this warp
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
             }
             if (warp == 2) TC_TRACE(7);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
     }
 }
 
@@ -782,8 +867,14 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             p.kb1 = 3 * p.cblocks;
             cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bn};
             cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-            static const int box2_on = getenv("MSU_CONV_2BOX") ? atoi(getenv("MSU_CONV_2BOX")) : 0;
-            p.box2 = box2_on;
+            // CTA pairs: the kernel sits on two on-chip limits at once, shared-memory bandwidth (operand reads of the tensor core
+            // + TMA writes) and the TMA unit's box rate; a pair halves the weight-tile share of the first, two boxes per K block
+            // instead of five lift the second (either alone measured no gain).  Needs whole-row TMA-store tiles, one N tile, an
+            // even tile count and half tiles of whole 8-row swizzle groups (MSU_CONV_PAIR=0 / MSU_CONV_2BOX=0: off).
+            static const int pair_on = getenv("MSU_CONV_PAIR") ? atoi(getenv("MSU_CONV_PAIR")) : 1;
+            p.pair = (pair_on && epi_tma && p.num_n_tiles == 1 && p.BN % 16 == 0 && p.num_m_tiles % 2 == 0 && num_sms() >= 2) ? 1 : 0;
+            static const int box2_on = getenv("MSU_CONV_2BOX") ? atoi(getenv("MSU_CONV_2BOX")) : -1;
+            p.box2 = box2_on < 0 ? p.pair : box2_on;
             cuuint32_t box[4] = {32, 130, (cuuint32_t)(p.box2 ? 2 : 1), 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             if (get_encode()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(A->ptr), gdim, gstr, box, estr,
@@ -816,16 +907,16 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (p.mode == 4 && p.box2) {   // the three dx tiles of (dy, channel block) as one box: third dimension = tap, C columns apart
         cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
         cuuint64_t gstr[2] = {(cuuint64_t)B->ld * 2, (cuuint64_t)p.C * 2};
-        cuuint32_t box[3] = {32, (cuuint32_t)p.BN, 3};
+        cuuint32_t box[3] = {32, (cuuint32_t)(p.pair ? p.BN / 2 : p.BN), 3};
         cuuint32_t estr[3] = {1, 1, 1};
         if (get_encode()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(B->ptr), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 1;
-    } else if (p.mode == 4) {   // weight tiles [BN rows, 32 k] with the 64B swizzle of the halo rows
+    } else if (p.mode == 4) {   // weight tiles [BN rows, 32 k] with the 64B swizzle of the halo rows (a CTA of a pair: half the rows)
         cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
         cuuint64_t gstr[1] = {(cuuint64_t)B->ld * 2};
-        cuuint32_t box[2] = {32, (cuuint32_t)p.BN};
+        cuuint32_t box[2] = {32, (cuuint32_t)(p.pair ? p.BN / 2 : p.BN)};
         cuuint32_t estr[2] = {1, 1};
         if (get_encode()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(B->ptr), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -834,7 +925,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     } else if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
 
     p.a_stage = p.mode == 4 ? 2 * TC_HALO32_BYTES : (p.mode == 3 ? 17 * 1024 : TC_A_BYTES);
-    p.b_stage = p.mode == 4 ? 3 * p.BN * 64 : (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
+    p.b_stage = p.mode == 4 ? 3 * (p.pair ? p.BN / 2 : p.BN) * 64 : (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
     const int stage_bytes = p.a_stage + p.b_stage;
     // [operand stages][1 KB: barriers, TMEM slot][epilogue slabs] + 1 KB alignment slack
     const int TC_EPI_WARPS = epi_tma ? TC_EPW_TMA : TC_EPW_GEN;
@@ -897,6 +988,8 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPW_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         smem_set.set();
     }
@@ -909,7 +1002,19 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         cudaMemsetAsync(trace_buf, 0, 148 * 8 * 16 * sizeof(long long), st);
         p.trace = trace_buf;
     }
-    if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
+    if (p.pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);            // whole pairs
+        cfg.blockDim = dim3(32 * (2 + TC_EPW_TMA), 1, 1);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p);
+        if (e != cudaSuccess) { set_error("gemm_tc (CTA pairs): %s", cudaGetErrorString(e)); return (int)e; }
+    } else if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     else gemm_tc_kernel<false, TC_EPW_GEN><<<grid, 32 * (2 + TC_EPW_GEN), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     count_launch();
     if (trace_on) {   // debug only: synchronous dump of the per-tile role timeline of two CTAs
