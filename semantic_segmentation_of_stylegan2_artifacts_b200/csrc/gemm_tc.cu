@@ -180,6 +180,20 @@ __device__ __forceinline__ int64_t tile_row0(const TcParams& p, int mt, int r) {
 // 16 B chunk g of row `row` inside a [32 rows x 64 B] SWIZZLE_64B slab (1 KB aligned): chunk ^= (row / 2) % 4
 __device__ __forceinline__ uint32_t slab_off(int row, int g) { return (uint32_t)(row * 64 + ((g ^ ((row >> 1) & 3)) << 4)); }
 
+// tile -> (m tile, n tile).  CTA pairs of the plain / dual-source modes: the two CTAs of a cluster (consecutive tile numbers) take the
+// two 128-row halves of one 256-row M tile and the SAME n tile (they share its B rows); n tiles fastest among the pair tiles.
+template <bool PAIR>
+__device__ __forceinline__ void tile_mn(const TcParams& p, int tile, int& mt, int& nt) {
+    if (PAIR && p.mode < 2) {
+        const int q = tile >> 1;
+        nt = q % p.num_n_tiles;
+        mt = (q / p.num_n_tiles) * 2 + (tile & 1);
+    } else {
+        mt = tile / p.num_n_tiles;
+        nt = tile % p.num_n_tiles;
+    }
+}
+
 template <bool EPI_TMA, int TC_EPI_WARPS, bool PAIR = false>
 __global__ void __launch_bounds__(32 * (2 + TC_EPI_WARPS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -232,7 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-                const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+                int mt, nt;
+            tile_mn<PAIR>(p, tile, mt, nt);
                 int cb = 0, cy = 0, cx = 0;
                 TC_TRACE(0);
                 if (p.mode >= 2) {
@@ -291,6 +306,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_4d(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
                         for (int dx = 0; dx < 3; dx++)
                             tma_load_2d(b_dst + dx * B_BYTES, &tmB, &full[stage], (dyi * 3 + dx) * p.C + c0, nt * p.BN);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    if (PAIR) {     // plain / dual-source: own 128 rows of A, own half of the B tile's rows; bytes counted by the leader
+                        const int hb = (p.BN / 2) * TC_BK * 2;
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (TC_A_BYTES + hb));
+                        int bk;
+                        if (kb < p.kb1) {
+                            tma_load_2d_pair(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+                            bk = kb * TC_BK;
+                        } else {
+                            tma_load_2d_pair(a_dst, &tmA2, &full[stage], (kb - p.kb1) * TC_BK, mt * TC_BM);
+                            bk = p.k_split + (kb - p.kb1) * TC_BK;
+                        }
+                        tma_load_2d_pair(b_dst, &tmB, &full[stage], bk, nt * p.BN + (int)cta_rank * (p.BN / 2));
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -374,8 +404,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
                         const uint64_t bdesc = make_desc_kmajor_sw128(b_addr);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle row
-                            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < TC_BK / 16; k++) {   // +32 B per K=16 step inside the 128 B swizzle row
+                            if (PAIR) tc_mma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     if (PAIR) tc_commit_pair(&empty[stage]); else tc_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -404,7 +436,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0; uint32_t acc_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            int mt, nt;
+            tile_mn<PAIR>(p, tile, mt, nt);
             // chunk list of this warp: cc = r * nchunks + c over the tile's accumulators r (consecutive row segments)
             const int nch_tot = p.nacc * nchunks;
             const int c_first = (sub + it) % NSUB;
@@ -562,7 +595,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0; uint32_t acc_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            int mt, nt;
+            tile_mn<PAIR>(p, tile, mt, nt);
             bool released = false;
             bool first = true;
             for (int racc = 0; racc < p.nacc; racc++) {
@@ -903,6 +937,17 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             if (!make_map_2d(&tmA, A->ptr, M, K, A->ld, TC_BM)) return 1;
             tmA2 = tmA;
         }
+        // CTA pairs for the long-K shapes: a pair shares the B tile, (128 + BN) -> (128 + BN / 2) operand rows per CTA and K block.
+        // Measured (tools/gemm_case.py, pairs on / off): 8192 x 4096 x 4096 183 / 193 us (1504 TFLOP/s), 4096 x 3072 x 768 27.5 / 31.2,
+        // 65536 x 192 x 768 35.0 / 36.3, 16384 x 384 x 1536 27.2 / 27.9; at K = 384 the two-tile-per-CTA kernels are bound by their
+        // prologue and epilogue tail and pairs cost 3-6 %, hence the K threshold.  The M tile count is rounded up to whole pairs:
+        // a tile past M loads zeros and stores nothing (MSU_TC_PAIR=0: off, MSU_TC_PAIR_K: threshold).
+        static const int tpair_on = getenv("MSU_TC_PAIR") ? atoi(getenv("MSU_TC_PAIR")) : 1;
+        static const int tpair_k = getenv("MSU_TC_PAIR_K") ? atoi(getenv("MSU_TC_PAIR_K")) : 768;
+        if (tpair_on && K >= tpair_k && p.BN % 16 == 0 && p.num_m_tiles >= 2 && num_sms() >= 2) {
+            p.pair = 1;
+            p.num_m_tiles = (p.num_m_tiles + 1) & ~1;
+        }
     }
     if (p.mode == 4 && p.box2) {   // the three dx tiles of (dy, channel block) as one box: third dimension = tap, C columns apart
         cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
@@ -922,16 +967,16 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 1;
-    } else if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.BN)) return 1;
+    } else if (!make_map_2d(&tmB, B->ptr, N, K, B->ld, p.pair ? p.BN / 2 : p.BN)) return 1;
 
     p.a_stage = p.mode == 4 ? 2 * TC_HALO32_BYTES : (p.mode == 3 ? 17 * 1024 : TC_A_BYTES);
-    p.b_stage = p.mode == 4 ? 3 * (p.pair ? p.BN / 2 : p.BN) * 64 : (p.mode == 3 ? 3 : 1) * p.BN * TC_BK * 2;
+    p.b_stage = p.mode == 4 ? 3 * (p.pair ? p.BN / 2 : p.BN) * 64 : (p.mode == 3 ? 3 : 1) * (p.pair ? p.BN / 2 : p.BN) * TC_BK * 2;
     const int stage_bytes = p.a_stage + p.b_stage;
     // [operand stages][1 KB: barriers, TMEM slot][epilogue slabs] + 1 KB alignment slack
     const int TC_EPI_WARPS = epi_tma ? TC_EPW_TMA : TC_EPW_GEN;
     auto stages_for = [&](int sb) { int s_ = (227 * 1024 - 2048 - TC_EPI_WARPS * p.epi_bytes) / sb; return s_ > 8 ? 8 : s_; };
     p.stages = stages_for(stage_bytes);
-    if (p.mode < 3 && p.BN > 192 && p.stages < 4 && !env_bn) {
+    if (p.mode < 3 && p.BN > 192 && p.stages < 4 && !env_bn && !p.pair) {
         // operand bytes in flight bound the mainloop: a narrower N tile that buys the 4th stage wins
         const int bn2 = pick_bn(N, 192, epi_tma ? 32 : 16);
         const int sb2 = p.a_stage + bn2 * TC_BK * 2;
@@ -990,6 +1035,8 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             e = cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPW_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPW_GEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         smem_set.set();
     }
@@ -1005,14 +1052,15 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (p.pair) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);            // whole pairs
-        cfg.blockDim = dim3(32 * (2 + TC_EPW_TMA), 1, 1);
+        cfg.blockDim = dim3(32 * (2 + (epi_tma ? TC_EPW_TMA : TC_EPW_GEN)), 1, 1);
         cfg.dynamicSmemBytes = (size_t)smem;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p);
+        cudaError_t e = epi_tma ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p)
+                                : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPW_GEN, true>, tmA, tmA2, tmB, tmC, tmAux, p);
         if (e != cudaSuccess) { set_error("gemm_tc (CTA pairs): %s", cudaGetErrorString(e)); return (int)e; }
     } else if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     else gemm_tc_kernel<false, TC_EPW_GEN><<<grid, 32 * (2 + TC_EPW_GEN), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
