@@ -89,6 +89,10 @@ out["families_us"] = {k: {"us": round(v[0], 1), "n": v[1]} for k, v in sorted(fa
 lst = by_stream[main]
 big = sorted(((lst[i + 1][0] - lst[i][1], fam(lst[i][2]), fam(lst[i + 1][2])) for i in range(len(lst) - 1)), reverse=True)[:12]
 out["largest_main_gaps"] = [{"gap_us": round(g_, 1), "after": a, "before": b_} for g_, a, b_ in big]
+# the first kernels of the replay and the surroundings of the largest gap (start offset, duration, name)
+out["first_kernels"] = [{"t_us": round(b - t0, 1), "dur_us": round(e - b, 1), "name": fam(n_)} for b, e, n_, _ in ks[:24]]
+gi = max(range(len(ks) - 1), key=lambda i: ks[i + 1][0] - max(k[1] for k in ks[:i + 1]))
+out["around_largest_idle"] = [{"t_us": round(b - t0, 1), "dur_us": round(e - b, 1), "name": fam(n_)} for b, e, n_, _ in ks[max(0, gi - 6):gi + 6]]
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)
