@@ -76,6 +76,18 @@ typedef struct {
                                colsum[m] = sum_k A(m,k), the bias gradient of the same layer (autograd's   \
                                grad_output.sum(0)); fused into the tensor-core kernel as one extra N=16     \
                                MMA against a tile of ones where the tiling allows, else a column-sum pass */
+    /* Fused head LayerNorm + 1x1 conv (network/model_parts.py:475, 846 behind the second 3x3 conv, :471): when lnd_w != NULL the
+     * GEMM (N = the LayerNorm width, one N tile, no other fused operand) also normalises every output row (after bias, rounded
+     * to `dtype` as stored) and writes lnd_logits[m] = dot(LN(row), lnd_w) (`dtype`) with the statistics msu_ln_bwd(dotw) needs:
+     * lnd_mean / lnd_rstd / lnd_m2 [M] fp32.  C may then be NULL (inference: the row itself is not stored).
+     * Supported by the tcgen05 TMA-store path only: msu_gemm fails otherwise (no silent fallback). */
+    const float* lnd_gamma;
+    const float* lnd_beta;
+    const float* lnd_w;
+    void* lnd_logits;
+    float* lnd_mean;
+    float* lnd_rstd;
+    float* lnd_m2;
 } MsuEpilogue;
 
 /* C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ), fp32 accumulation.

@@ -39,7 +39,9 @@ class MsuEpilogue(C.Structure):
                 ("H", C.c_void_p), ("ldc", C.c_int64), ("ldr", C.c_int64), ("ldh", C.c_int64),
                 ("rowscale", C.c_void_p), ("rows_per_sample", C.c_int32), ("act", C.c_int32),
                 ("map", C.c_int32), ("dtype", C.c_int32), ("geo", C.c_int32 * 6), ("out_f32", C.c_int32),
-                ("accumulate", C.c_int32), ("colsum", C.c_void_p)]
+                ("accumulate", C.c_int32), ("colsum", C.c_void_p),
+                ("lnd_gamma", C.c_void_p), ("lnd_beta", C.c_void_p), ("lnd_w", C.c_void_p), ("lnd_logits", C.c_void_p),
+                ("lnd_mean", C.c_void_p), ("lnd_rstd", C.c_void_p), ("lnd_m2", C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None

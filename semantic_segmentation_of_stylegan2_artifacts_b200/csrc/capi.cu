@@ -41,7 +41,7 @@ using namespace msu;
 
 extern "C" int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t M, int64_t N, int64_t K,
                         float* splitk_ws, int64_t splitk_ws_elems, int backend, void* stream) {
-    MSU_REQUIRE(A && B && E && A->ptr && B->ptr && E->C, "msu_gemm: null pointer");
+    MSU_REQUIRE(A && B && E && A->ptr && B->ptr && (E->C || E->lnd_w), "msu_gemm: null pointer");
     MSU_REQUIRE(M >= 0 && N > 0 && K > 0, "msu_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -55,6 +55,8 @@ extern "C" int msu_gemm(const MsuOperand* A, const MsuOperand* B, const MsuEpilo
         if (rc == 0) g_last_backend = 1;
         else if (rc != 1) return rc;
     }
+    MSU_REQUIRE(!(rc == 1 && E->lnd_w != nullptr), "msu_gemm: the fused LayerNorm + dot epilogue needs the tcgen05 TMA-store path "
+                "(bf16, unmapped output, one N tile of a multiple of 32 columns, no other fused operand)");
     if (rc == 1) {
         rc = gemm_simt(A, B, E, M, N, K, splitk_ws, splitk_ws_elems, st);
         if (rc != 0) return rc;

@@ -194,7 +194,7 @@ __device__ __forceinline__ void tile_mn(const TcParams& p, int tile, int& mt, in
     }
 }
 
-template <bool EPI_TMA, int TC_EPI_WARPS, bool PAIR = false>
+template <bool EPI_TMA, int TC_EPI_WARPS, bool PAIR = false, bool LND = false>
 __global__ void __launch_bounds__(32 * (2 + TC_EPI_WARPS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -211,6 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     uint64_t* auxbar = reinterpret_cast<uint64_t*>(tmem_slot + 4);   // [TC_EPI_WARPS][2] aux-in slab landed (TMA path)
     uint8_t* sScratch = smem + (size_t)p.stages * (p.a_stage + p.b_stage) + 1024;   // [TC_EPI_WARPS][epi_bytes], 1 KB aligned
+    float* sGw = reinterpret_cast<float*>(sScratch + (size_t)TC_EPI_WARPS * p.epi_bytes);   // LND: gamma * w [N] (+ 1 KB of shared memory)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -225,6 +226,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         for (int a = 0; a < 2 * TC_EPI_WARPS; a++) mbar_init(&auxbar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (LND) {
+        for (int n = threadIdx.x; n < p.N; n += blockDim.x) sGw[n] = p.E.lnd_gamma[n] * p.E.lnd_w[n];
     }
     if (warp == 1) {
         if (PAIR) {
@@ -431,6 +435,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* slab_aux = slab_out + 2048;            // Cpre staging (out) or R/H operand (in, 2 slabs)
         uint64_t* abar = auxbar + 2 * (warp - 2);
         const bool aux_in = (E.R != nullptr || E.H != nullptr);
+        constexpr bool lnd = LND;            // fused head LayerNorm + dot: its own instantiation (registers of the common epilogues)
+        float lnd_g = 0.f, lnd_bw = 0.f;     // G = sum_c gamma_c w_c, Bw = sum_c beta_c w_c (the same in every lane)
+        if (lnd) {
+            for (int n = 0; n < p.N; n++) {
+                lnd_g += sGw[n];
+                lnd_bw = fmaf(E.lnd_beta[n], E.lnd_w[n], lnd_bw);
+            }
+        }
         uint32_t aux_phase[2] = {0, 0};
         int aux_buf = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -438,9 +450,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             int mt, nt;
             tile_mn<PAIR>(p, tile, mt, nt);
-            // chunk list of this warp: cc = r * nchunks + c over the tile's accumulators r (consecutive row segments)
+            // chunk list of this warp: cc = r * nchunks + c over the tile's accumulators r (consecutive row segments).
+            // Fused LayerNorm + dot (lnd): a warp owns ALL chunks of one 32-row block (its lanes carry the rows' statistics from
+            // chunk to chunk); the blocks of consecutive tiles rotate over the NSUB warps of the quadrant.
             const int nch_tot = p.nacc * nchunks;
-            const int c_first = (sub + it) % NSUB;
+            int c_first = (sub + it) % NSUB, c_end = nch_tot, c_step = NSUB;
+            if (lnd) {
+                const int r_mine = (sub - (it * p.nacc) % NSUB + NSUB) % NSUB;
+                c_first = r_mine < p.nacc ? r_mine * nchunks : nch_tot;
+                c_end = r_mine < p.nacc ? c_first + nchunks : nch_tot;
+                c_step = 1;
+            }
+            float st_c0 = 0.f, st_s = 0.f, st_q = 0.f, st_d = 0.f;
             auto row0_of = [&](int cc) { return (int)(tile_row0(p, mt, cc / nchunks) + quad * 32); };
             if (aux_in && c_first < nch_tot && lane == 0) {   // operand slab of the first chunk
                 mbar_arrive_expect_tx(&abar[aux_buf], 2048);
@@ -453,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
             bool released = false;
             bool first = true;
-            for (int cc = c_first; cc < nch_tot; cc += NSUB) {
+            for (int cc = c_first; cc < c_end; cc += c_step) {
                 const int r = cc / nchunks, c = cc - r * nchunks;
                 uint32_t raw[TC_CW];
                 tc_ld32_nowait(t_base + r * 128 + c * TC_CW, raw);
@@ -464,14 +485,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int64_t m_own = (int64_t)row0 + lane;
                     rs = m_own < p.M ? E.rowscale[m_own / E.rows_per_sample] : 0.0f;
                 }
-                if (aux_in && cc + NSUB < nch_tot && lane == 0) {   // next chunk's operand slab (its buffer was drained a chunk ago)
-                    const int cn = cc + NSUB;
+                if (aux_in && cc + c_step < c_end && lane == 0) {   // next chunk's operand slab (its buffer was drained a chunk ago)
+                    const int cn = cc + c_step;
                     mbar_arrive_expect_tx(&abar[aux_buf ^ 1], 2048);
                     tma_load_2d(slab_aux + (aux_buf ^ 1) * 2048, &tmAux, &abar[aux_buf ^ 1], nt * p.BN + (cn % nchunks) * TC_CW, row0_of(cn));
                 }
                 tc_ld_wait();
                 if (warp == 2 && first) TC_TRACE(10);
-                if (cc + NSUB >= nch_tot) {
+                if (cc + c_step >= c_end) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
@@ -536,6 +557,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < TC_CW; i++) v[i] *= rs;
                 }
+                if (lnd) {
+                    // head LayerNorm + 1x1 conv on the rows as they are stored (bf16-rounded): shifted one-pass statistics
+                    // (shift = the row's first value) and sum_c v_c gw_c with gw = gamma w from shared memory (broadcast reads)
+                    if (c == 0) { st_s = st_q = st_d = 0.f; }
+#pragma unroll
+                    for (int g4 = 0; g4 < TC_CW / 4; g4++) {
+                        const float4 gq = *reinterpret_cast<const float4*>(sGw + n0 + g4 * 4);
+                        const float gw[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i += 2) {
+                            const uint32_t u = pack_bf16x2(v[g4 * 4 + i], v[g4 * 4 + i + 1]);
+                            const float a0 = bf16lo_f(u), a1 = bf16hi_f(u);
+                            if (c == 0 && g4 == 0 && i == 0) st_c0 = a0;
+                            const float d0 = a0 - st_c0, d1 = a1 - st_c0;
+                            st_s += d0 + d1;
+                            st_q = fmaf(d0, d0, fmaf(d1, d1, st_q));
+                            st_d = fmaf(a0, gw[i], fmaf(a1, gw[i + 1], st_d));
+                        }
+                    }
+                    if (c == nchunks - 1) {
+                        const float invn = 1.0f / (float)p.N;
+                        const float ms = st_s * invn;
+                        const float mu = st_c0 + ms;
+                        const float rs = rsqrtf(fmaxf(fmaf(-ms, ms, st_q * invn), 0.f) + 1e-5f);
+                        const float dc = fmaf(-mu, lnd_g, st_d) * rs;                // sum_c gw_c x-hat_c
+                        const int64_t m_own = (int64_t)row0 + lane;
+                        if (m_own < p.M) {
+                            reinterpret_cast<__nv_bfloat16*>(E.lnd_logits)[m_own] = __float2bfloat16(dc + lnd_bw);
+                            E.lnd_mean[m_own] = mu;
+                            E.lnd_rstd[m_own] = rs;
+                            E.lnd_m2[m_own] = dc * invn;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int g = 0; g < 4; g++)
                     *reinterpret_cast<uint4*>(slab_out + slab_off(lane, g)) =
@@ -544,7 +599,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (warp == 2 && first) TC_TRACE(8);
-                if (lane == 0) {
+                if (lane == 0 && E.C != nullptr) {
                     if (E.map == MSU_MAP_NONE) {
                         tma_store_2d(slab_out, &tmC, n0, row0);
                         if (E.Cpre != nullptr) tma_store_2d(slab_aux, &tmAux, n0, row0);
@@ -845,6 +900,12 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     if (E->bias && !aligned16(E->bias)) return 1;
     if (M < 64) return 1;  // tiny problems: not worth a 128-row tile
     if (get_encode() == nullptr) return 1;
+    const bool lnd = E->lnd_w != nullptr;      // fused head LayerNorm + dot: only this path implements it (the caller fails on 1)
+    if (lnd && (!E->lnd_gamma || !E->lnd_beta || !E->lnd_logits || !E->lnd_mean || !E->lnd_rstd || !E->lnd_m2 || E->map != MSU_MAP_NONE ||
+                E->R || E->H || E->Cpre || E->act || E->rowscale || N % 32 != 0 || N > 256 || !aligned16(E->lnd_gamma) ||
+                !aligned16(E->lnd_beta) || !aligned16(E->lnd_w)))
+        return 1;
+    if (!lnd && E->C == nullptr) return 1;
 
     TcParams p{};
     p.M = M; p.N = (int)N; p.K = (int)K;
@@ -863,11 +924,13 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         (E->geo[1] * E->geo[2]) % 32 == 0 && N == E->geo[3] && E->ldc == (int64_t)E->geo[2] * E->geo[2] * E->geo[3])
         epi_tma = true;
     if (A->map == MSU_MAP_CONV3 && A->geo[1] % 128 != 0) epi_tma = false;
+    if (lnd && !epi_tma) return 1;
     const int naux = E->Cpre ? 1 : ((E->R || E->H) ? 2 : 0);
     p.epi_tma = epi_tma ? 1 : 0;
     p.epi_bytes = epi_tma ? 2048 * (1 + naux) : ((TC_SCRATCH_BYTES + 1023) / 1024) * 1024;
     p.BN = pick_bn(N, env_bn ? env_bn : 256, epi_tma ? 32 : 16);
     p.num_n_tiles = (int)((N + p.BN - 1) / p.BN);
+    if (lnd && p.num_n_tiles != 1) return 1;
     p.E = *E;
     CUtensorMap tmA, tmA2, tmB;
     if (A->map == MSU_MAP_CONV3) {
@@ -974,7 +1037,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     const int stage_bytes = p.a_stage + p.b_stage;
     // [operand stages][1 KB: barriers, TMEM slot][epilogue slabs] + 1 KB alignment slack
     const int TC_EPI_WARPS = epi_tma ? TC_EPW_TMA : TC_EPW_GEN;
-    auto stages_for = [&](int sb) { int s_ = (227 * 1024 - 2048 - TC_EPI_WARPS * p.epi_bytes) / sb; return s_ > 8 ? 8 : s_; };
+    auto stages_for = [&](int sb) { int s_ = (227 * 1024 - 2048 - TC_EPI_WARPS * p.epi_bytes - (lnd ? 1024 : 0)) / sb; return s_ > 8 ? 8 : s_; };
     p.stages = stages_for(stage_bytes);
     if (p.mode < 3 && p.BN > 192 && p.stages < 4 && !env_bn && !p.pair) {
         // operand bytes in flight bound the mainloop: a narrower N tile that buys the 4th stage wins
@@ -989,7 +1052,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         }
     }
     const int stage_bytes_final = p.a_stage + p.b_stage;
-    const int fixed_bytes = 2048 + TC_EPI_WARPS * p.epi_bytes;
+    const int fixed_bytes = 2048 + TC_EPI_WARPS * p.epi_bytes + (lnd ? 1024 : 0);
     if (env_stages && p.stages > env_stages) p.stages = env_stages;
     if (p.stages < 2) return 1;
     const int smem = p.stages * stage_bytes_final + fixed_bytes;
@@ -998,7 +1061,7 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         const void* aux = E->Cpre ? E->Cpre : (E->R ? E->R : E->H);
         const int64_t ldaux = E->Cpre ? E->ldc : (E->R ? E->ldr : E->ldh);
         if (E->map == MSU_MAP_NONE) {
-            if (!make_map_slab(&tmC, E->C, M, N, E->ldc)) return 1;
+            if (E->C != nullptr && !make_map_slab(&tmC, E->C, M, N, E->ldc)) return 1;
             if (aux != nullptr && !make_map_slab(&tmAux, aux, M, N, ldaux)) return 1;
         } else {
             // 5-D view (c, p2, w, p1, b*H + h) of the depth-to-space tensor: SHUFFLE memory is [(b, h p + p1, w p + p2), c],
@@ -1037,6 +1100,10 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
             e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPW_GEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPW_TMA, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         smem_set.set();
     }
@@ -1059,10 +1126,12 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = epi_tma ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p)
-                                : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPW_GEN, true>, tmA, tmA2, tmB, tmC, tmAux, p);
+        cudaError_t e = lnd ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true, true>, tmA, tmA2, tmB, tmC, tmAux, p)
+                            : (epi_tma ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p)
+                                       : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPW_GEN, true>, tmA, tmA2, tmB, tmC, tmAux, p));
         if (e != cudaSuccess) { set_error("gemm_tc (CTA pairs): %s", cudaGetErrorString(e)); return (int)e; }
-    } else if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
+    } else if (lnd) gemm_tc_kernel<true, TC_EPW_TMA, false, true><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
+    else if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     else gemm_tc_kernel<false, TC_EPW_GEN><<<grid, 32 * (2 + TC_EPW_GEN), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
     count_launch();
     if (trace_on) {   // debug only: synchronous dump of the per-tile role timeline of two CTAs

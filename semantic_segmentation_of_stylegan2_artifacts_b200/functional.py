@@ -57,6 +57,7 @@ def _al(*ts):
 import os as _os
 
 _WG_ON = _os.environ.get("MSUNET_B200_WGRAD_STREAM", "1") != "0"
+_FUSED_HEAD_LN = _os.environ.get("MSUNET_B200_FUSED_HEAD_LN", "1") != "0"   # head LayerNorm + 1x1 conv in the second conv's epilogue
 _wg_streams: dict = {}
 
 
@@ -541,10 +542,23 @@ class HeadFn(Function):
         a1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(a0, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1), epilogue(a1, Cpre=z1, bias=c1b, act=1),
              Mp, E, 9 * E, dev)
-        z2 = torch.empty(Mp, E, dtype=dt, device=dev)
-        gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
         owv = _al(_c(ow).view(E))
-        logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
+        if _FUSED_HEAD_LN and dt == BF16 and E % 32 == 0 and E <= 256 and S % 128 == 0:
+            # LayerNorm + 1x1 conv ride in the second conv's epilogue (per-row statistics in the epilogue registers): the
+            # [Mp, E] tensor is not read again, and not even written when no gradient is wanted (inference)
+            need_grad = any(ctx.needs_input_grad)
+            z2 = torch.empty(Mp, E, dtype=dt, device=dev) if need_grad else None
+            logits = torch.empty(Mp, dtype=dt, device=dev)
+            mean = torch.empty(Mp, dtype=torch.float32, device=dev)
+            rstd = torch.empty(2, Mp, dtype=torch.float32, device=dev)       # [rstd | dot statistic], see ops.ln_fwd
+            gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2),
+                 epilogue(z2, ldc=E, bias=c2b, lnd=(nw, nb, owv, logits, mean, rstd[0], rstd[1]), dtype=dt), Mp, E, 9 * E, dev)
+            if z2 is None:
+                z2 = logits          # placeholder: nothing of the head is needed without a backward
+        else:
+            z2 = torch.empty(Mp, E, dtype=dt, device=dev)
+            gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
+            logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
         ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd, c1b, c2b)
         ctx.cfg = (B, r, x.shape, ow.shape)
         return logits.view(B, 1, S, S)

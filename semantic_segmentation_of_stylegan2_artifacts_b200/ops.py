@@ -54,9 +54,29 @@ def operand(t: torch.Tensor, ld: Optional[int] = None, *, t2: Optional[torch.Ten
 
 def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=None, R=None, ldr: Optional[int] = None,
              H=None, ldh: int = 0, rowscale=None, rps: int = 0, act: int = 0, map: int = MAP_NONE, geo=None,
-             out_f32: bool = False, accumulate: bool = False, offset: int = 0, colsum=None) -> MsuEpilogue:
+             out_f32: bool = False, accumulate: bool = False, offset: int = 0, colsum=None, lnd=None,
+             dtype: Optional[torch.dtype] = None) -> MsuEpilogue:
+    """`lnd` = (gamma, beta, w, logits, mean, rstd, m2): fused head LayerNorm + 1x1 conv (see MsuEpilogue.lnd_*); `Cm` may then be
+    None (the rows are not stored; `ldc` and `dtype` must be given)."""
     e = MsuEpilogue()
-    e.C = Cm.data_ptr() + offset * Cm.element_size()
+    e.C = None if Cm is None else Cm.data_ptr() + offset * Cm.element_size()
+    if Cm is None:
+        if lnd is None or ldc is None or dtype is None:
+            raise ValueError("an output tensor is required (only the fused LayerNorm + dot epilogue may drop it)")
+        e.Cpre = e.bias = e.R = e.H = None
+        e.bias = L.ptr(bias)
+        e.ldc = e.ldr = ldc
+        e.ldh = 0
+        e.rowscale = None
+        e.rows_per_sample = 0
+        e.act = 0
+        e.map = MAP_NONE
+        e.dtype = L._DT[dtype]
+        e.geo = L.geo6(None)
+        e.out_f32 = e.accumulate = 0
+        e.colsum = None
+        (e.lnd_gamma, e.lnd_beta, e.lnd_w, e.lnd_logits, e.lnd_mean, e.lnd_rstd, e.lnd_m2) = (L.ptr(v) for v in lnd)
+        return e
     e.Cpre = L.ptr(Cpre)
     e.bias = L.ptr(bias)
     e.R = L.ptr(R)
@@ -73,6 +93,8 @@ def epilogue(Cm: torch.Tensor, ldc: Optional[int] = None, *, Cpre=None, bias=Non
     e.out_f32 = 1 if out_f32 else 0
     e.accumulate = 1 if accumulate else 0
     e.colsum = L.ptr(colsum)
+    if lnd is not None:
+        (e.lnd_gamma, e.lnd_beta, e.lnd_w, e.lnd_logits, e.lnd_mean, e.lnd_rstd, e.lnd_m2) = (L.ptr(v) for v in lnd)
     if colsum is not None and (colsum.dtype != torch.float32 or not out_f32):
         raise TypeError("colsum (bias gradient) needs an fp32 vector and an fp32 weight-gradient output")
     if out_f32 and Cm.dtype != torch.float32:
@@ -186,6 +208,8 @@ def gemm(A: MsuOperand, B: MsuOperand, E: MsuEpilogue, M: int, N: int, K: int, d
             nb = K * (M + (N // 9 if B.map == MAP_CONV3 else N)) * es + M * N * 4
         else:
             kind = "conv3x3" if A.map == MAP_CONV3 else "gemm"
+            if E.lnd_w is not None:
+                kind += "_lnd"             # its own template instantiation: LayerNorm + dot statistics in the epilogue
             a_cols = K // 9 if A.map == MAP_CONV3 else K
             outs = 1 + (E.Cpre is not None) + (E.R is not None) + (E.H is not None)
             nb = (M * a_cols + N * K + outs * M * N) * es

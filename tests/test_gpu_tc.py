@@ -504,3 +504,48 @@ def test_conv3x3_two_row_tiles_fused_epilogues(ops, geom):
 
     tc, simt = run_both(ops, dgrad)
     assert relmax(tc, simt) < 8e-3
+
+
+@pytest.mark.parametrize("E,r,B", [(96, 32, 2), (128, 32, 1), (64, 64, 1)])
+def test_head_layernorm_dot_fused_into_conv_epilogue(ops, E, r, B):
+    """Head: second 3x3 conv with the LayerNorm + 1x1 conv fused into its epilogue (MsuEpilogue.lnd_*, per-row statistics in the
+    epilogue registers, CTA pairs at these shapes) against the separate conv -> msu_ln_fwd(dotw) pair: logits, the saved
+    statistics and every gradient of the head (the backward consumes mean / rstd / dot statistic of either path).
+    network/model_parts.py:468-476, 842-846."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import functional as Fn
+    torch.manual_seed(5)
+    bf = torch.bfloat16
+    T = B * r * r
+    x = (torch.randn(B, r * r, E, device=DEV) * 0.7).to(bf).requires_grad_(True)
+    prm = [torch.randn(16 * E, E, device=DEV) * 0.08,                       # expand
+           torch.randn(E, E, 3, 3, device=DEV) * 0.04, torch.randn(E, device=DEV) * 0.1,
+           torch.randn(E, E, 3, 3, device=DEV) * 0.04, torch.randn(E, device=DEV) * 0.1,
+           1.0 + 0.2 * torch.randn(E, device=DEV), 0.1 * torch.randn(E, device=DEV),
+           torch.randn(1, E, 1, 1, device=DEV) * 0.2]
+    prm = [p.requires_grad_(True) for p in prm]
+    g = torch.randn(B, 1, 4 * r, 4 * r, device=DEV).to(bf)
+
+    def run(fused):
+        old = Fn._FUSED_HEAD_LN
+        Fn._FUSED_HEAD_LN = fused
+        try:
+            for t in [x] + prm:
+                t.grad = None
+            out = Fn.HeadFn.apply(x, *prm, B, r)
+            out.backward(g)
+            torch.cuda.synchronize()
+            return out.detach().float(), [t.grad.detach().float().clone() for t in [x] + prm]
+        finally:
+            Fn._FUSED_HEAD_LN = old
+
+    lo_f, gr_f = run(True)
+    lo_u, gr_u = run(False)
+    # same bf16 rows in, fp32 statistics either way: the logits differ by fp32 summation order and one bf16 rounding
+    assert relmax(lo_f, lo_u) < 1.0e-2
+    assert float((lo_f - lo_u).abs().mean() / lo_u.abs().mean()) < 1.5e-3
+    for a, b in zip(gr_f, gr_u):
+        assert float((a - b).norm() / b.norm().clamp_min(1e-20)) < 5e-3
+    # inference: no gradient wanted -> the rows are not stored at all, the logits are the same
+    with torch.no_grad():
+        lo_i = Fn.HeadFn.apply(x.detach(), *[p.detach() for p in prm], B, r).float()
+    assert torch.equal(lo_i, lo_f)

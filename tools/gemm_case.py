@@ -60,6 +60,20 @@ def conv(B, S, E):
                              B * S * S, E, 9 * E, dev), 2 * B * S * S * E * 9 * E, 2 * B * S * S * E * 2)
 
 
+def conv_lnd(B, S, E):
+    """second head conv with the LayerNorm + 1x1 conv fused into its epilogue (MsuEpilogue.lnd_*)"""
+    x = torch.randn(B * S * S, E, device=dev).to(bf)
+    w = (torch.randn(E, 9 * E, device=dev) * 0.05).to(bf)
+    b = torch.randn(E, device=dev)
+    y = torch.empty(B * S * S, E, dtype=bf, device=dev)
+    g, be, ow = torch.ones(E, device=dev), torch.zeros(E, device=dev), torch.randn(E, device=dev)
+    lo = torch.empty(B * S * S, dtype=bf, device=dev)
+    st = torch.empty(3, B * S * S, device=dev)
+    return (lambda: ops.gemm(ops.operand(x, ld=E, map=ops.MAP_CONV3, geo=[S, S, E]), ops.operand(w),
+                             ops.epilogue(y, bias=b, lnd=(g, be, ow, lo, st[0], st[1], st[2])), B * S * S, E, 9 * E, dev),
+            2 * B * S * S * E * 9 * E, 2 * B * S * S * E * 2)
+
+
 def head_expand(Bn, r, E):
     M, N = Bn * r * r, 16 * E
     a = torch.randn(M, E, device=dev).to(bf)
@@ -91,7 +105,7 @@ cases = {
     "dh_s2": lambda: dgelu(16384, 1536, 384), "fc2_s2": lambda: resid(16384, 384, 1536),
     "dxn_s2": lambda: plain(16384, 384, 1536), "qkv_s2": lambda: plain(19600, 1152, 384),
     "proj_s2": lambda: plain(19600, 384, 384), "fc1_s3": lambda: fc1(4096, 3072, 768),
-    "plain_big": lambda: plain(8192, 4096, 4096), "conv_b16": lambda: conv(16, 512, 96),
+    "plain_big": lambda: plain(8192, 4096, 4096), "conv_b16": lambda: conv(16, 512, 96), "convlnd_b16": lambda: conv_lnd(16, 512, 96),
 }
 for name, mk in cases.items():
     if filt and not any(f in name for f in filt):

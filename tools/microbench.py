@@ -130,7 +130,7 @@ def infer_case(Bn=8, S=1024, steps=5):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         # reference formulas on the same logits (scripts/validation_functions.py:106-108, 219-227)
-        pred = torch.sigmoid(logits.squeeze(1))          # rounded to the logits dtype, like the reference under autocast
+        pred = torch.sigmoid(logits.squeeze(1).float())  # fp32 probabilities (msu_metrics thresholds in fp32 whatever the logits dtype)
         pb, gt = pred > 0.5, y > 0
         ref = torch.stack([(pb & gt).sum((1, 2)), (pb & ~gt).sum((1, 2)), (~pb & gt).sum((1, 2)), (~pb & ~gt).sum((1, 2))], 1)
         exact = bool((ref.cpu() == counts.cpu()).all())
