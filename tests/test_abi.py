@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layout_matches_header(built):
     from semantic_segmentation_of_stylegan2_artifacts_b200._lib import MsuEpilogue, MsuOperand
     assert ctypes.sizeof(MsuOperand) == built.lib().msu_struct_size(0) == 88
-    assert ctypes.sizeof(MsuEpilogue) == built.lib().msu_struct_size(1) == 128
+    assert ctypes.sizeof(MsuEpilogue) == built.lib().msu_struct_size(1) == 184      # 128 + the seven lnd_* pointers
 
 
 @pytest.mark.parametrize("name,kw,img", [("t32_160", dict(embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8]), 160),
