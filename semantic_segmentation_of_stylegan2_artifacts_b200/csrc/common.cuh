@@ -1,5 +1,6 @@
 // Shared device/host helpers for libmsunet_sm100.so (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -221,6 +222,43 @@ struct PerDeviceOnce {
     static thread_local int slot;
 };
 inline thread_local int PerDeviceOnce::slot = 0;
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while the previous kernel of its stream is
+// still running (as soon as every CTA of that kernel has called pdl_trigger() or exited, and an SM has room); it runs its prologue
+// (barrier init, TMEM allocation) and then blocks in pdl_wait() until the previous kernel has completed and its writes are visible.
+// A kernel that is NOT launched this way is unaffected by its predecessor's trigger.
+// OFF by default: measured on the training step (three A/B/C runs per box) the step was 0.2-0.3 ms SLOWER with the GEMM kernel
+// launched this way (22.3-22.5 -> 22.6-22.7 ms) and slower again with the weight-gradient / attention kernels included — the early
+// resident 200 KB CTAs take SMs the side-stream kernels would otherwise fill — and the pinned-host e2e loop showed outliers.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline int pdl_level() {          // MSU_PDL: 0 off, 1 the forward / dgrad GEMM kernel only, 2 also the weight-gradient and attention kernels
+    static const int lv = getenv("MSU_PDL") ? atoi(getenv("MSU_PDL")) : 0;
+    return lv;
+}
+template <int LEVEL = 1, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        n++;
+    }
+    if (pdl_level() >= LEVEL) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int num_sms() {
     static int n = 0;

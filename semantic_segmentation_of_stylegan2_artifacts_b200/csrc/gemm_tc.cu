@@ -227,9 +227,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int a = 0; a < 2 * TC_EPI_WARPS; a++) mbar_init(&auxbar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (LND) {
-        for (int n = threadIdx.x; n < p.N; n += blockDim.x) sGw[n] = p.E.lnd_gamma[n] * p.E.lnd_w[n];
-    }
     if (warp == 1) {
         if (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
@@ -238,6 +235,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
+    }
+    // PDL: everything above overlapped the previous kernel's tail; nothing below may run before that kernel has completed
+    pdl_trigger();
+    pdl_wait();
+    if (LND) {
+        for (int n = threadIdx.x; n < p.N; n += blockDim.x) sGw[n] = p.E.lnd_gamma[n] * p.E.lnd_w[n];
     }
     tc_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -1116,23 +1119,22 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
         cudaMemsetAsync(trace_buf, 0, 148 * 8 * 16 * sizeof(long long), st);
         p.trace = trace_buf;
     }
-    if (p.pair) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);            // whole pairs
-        cfg.blockDim = dim3(32 * (2 + (epi_tma ? TC_EPW_TMA : TC_EPW_GEN)), 1, 1);
-        cfg.dynamicSmemBytes = (size_t)smem;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = lnd ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true, true>, tmA, tmA2, tmB, tmC, tmAux, p)
-                            : (epi_tma ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, TC_EPW_TMA, true>, tmA, tmA2, tmB, tmC, tmAux, p)
-                                       : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPW_GEN, true>, tmA, tmA2, tmB, tmC, tmAux, p));
-        if (e != cudaSuccess) { set_error("gemm_tc (CTA pairs): %s", cudaGetErrorString(e)); return (int)e; }
-    } else if (lnd) gemm_tc_kernel<true, TC_EPW_TMA, false, true><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
-    else if (epi_tma) gemm_tc_kernel<true, TC_EPW_TMA><<<grid, 32 * (2 + TC_EPW_TMA), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
-    else gemm_tc_kernel<false, TC_EPW_GEN><<<grid, 32 * (2 + TC_EPW_GEN), smem, st>>>(tmA, tmA2, tmB, tmC, tmAux, p);
+    {
+        const dim3 blk(32 * (2 + (epi_tma ? TC_EPW_TMA : TC_EPW_GEN)), 1, 1);
+        const dim3 grd((unsigned)(p.pair ? (grid & ~1) : grid), 1, 1);   // CTA pairs: whole clusters of two
+        const int cl = p.pair ? 2 : 1;
+        cudaError_t e;
+        if (p.pair) {
+            e = lnd ? launch_pdl(gemm_tc_kernel<true, TC_EPW_TMA, true, true>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p)
+                    : (epi_tma ? launch_pdl(gemm_tc_kernel<true, TC_EPW_TMA, true>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p)
+                               : launch_pdl(gemm_tc_kernel<false, TC_EPW_GEN, true>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p));
+        } else {
+            e = lnd ? launch_pdl(gemm_tc_kernel<true, TC_EPW_TMA, false, true>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p)
+                    : (epi_tma ? launch_pdl(gemm_tc_kernel<true, TC_EPW_TMA>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p)
+                               : launch_pdl(gemm_tc_kernel<false, TC_EPW_GEN>, grd, blk, (size_t)smem, st, cl, tmA, tmA2, tmB, tmC, tmAux, p));
+        }
+        if (e != cudaSuccess) { set_error("gemm_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     count_launch();
     if (trace_on) {   // debug only: synchronous dump of the per-tile role timeline of two CTAs
         static long long host[148 * 8 * 16];
@@ -1226,6 +1228,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_trigger();
+    pdl_wait();           // PDL: barrier init / TMEM allocation above overlapped the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1442,6 +1446,8 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_trigger();
+    pdl_wait();           // PDL: barrier init / TMEM allocation above overlapped the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1722,7 +1728,10 @@ static int wgrad_conv_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpil
         if (e != cudaSuccess) { set_error("wgrad_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr.set();
     }
-    wgrad_conv_tc_kernel<<<p.n_groups * splits, WG_THREADS, smem, st>>>(tmZ, tmX, p);
+    {
+        const cudaError_t e = launch_pdl<2>(wgrad_conv_tc_kernel, dim3((unsigned)(p.n_groups * splits)), dim3(WG_THREADS), (size_t)smem, st, 1, tmZ, tmX, p);
+        if (e != cudaSuccess) { set_error("wgrad_conv_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     count_launch();
     launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits);
     if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;
@@ -1833,7 +1842,10 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr.set();
     }
-    wgrad_tc_kernel<<<base_ctas * splits, WG_THREADS, smem, st>>>(tmP, tmQ, tmW, p);
+    {
+        const cudaError_t e = launch_pdl<2>(wgrad_tc_kernel, dim3((unsigned)(base_ctas * splits)), dim3(WG_THREADS), (size_t)smem, st, 1, tmP, tmQ, tmW, p);
+        if (e != cudaSuccess) { set_error("wgrad_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     count_launch();
     launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq, A->rowscale, sps);
     if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;

@@ -126,7 +126,6 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5;
     const int C = nH * HD;
     const int h = blockIdx.y;
-    stage_bias_tc(sBias, bias, h, tid);
 
     if (tid == 0) {
         mbar_init(&bar_load[0], 1);
@@ -138,6 +137,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_trigger();
+    pdl_wait();           // PDL: the bias table below comes from the previous kernel (msu_relbias_expand)
+    stage_bias_tc(sBias, bias, h, tid);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -364,7 +366,10 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     // whole waves: 3 CTAs per SM are resident; a few CTAs more would start late and double the tail
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3) / nH));
     dim3 grid(gx, nH);
-    winattn_fwd_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, tm4, tmO, bias, n_windows, nH, g, ad);
+    {
+        const cudaError_t e = launch_pdl<2>(winattn_fwd_tc_kernel, grid, dim3(128), (size_t)AT_SMEM, st, 1, tm, tm4, tmO, bias, n_windows, nH, g, ad);
+        if (e != cudaSuccess) { set_error("winattn_fwd_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     count_launch();
     return check_launch("winattn_fwd_tc");
 }
@@ -571,7 +576,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = nH * HD;
     const int h = blockIdx.y;
-    if (tid < 128) stage_bias_tc(sBias, bias, h, tid);
     if (tid == 0) {
         for (int k = 0; k < AB_STAGES; k++) mbar_init(&full[k], 1);
         for (int k = 0; k < 2; k++) {
@@ -587,6 +591,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_trigger();
+    pdl_wait();           // PDL: everything below reads what earlier kernels wrote
+    if (tid < 128) stage_bias_tc(sBias, bias, h, tid);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -818,8 +825,11 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), st);
     }
 #endif
-    winattn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQKV, tmDO, tmQKV4, tmDO3, tmOut, bias, dbias_partial, n_windows, nH, g, ad,
-                                                             trace_buf);
+    {
+        const cudaError_t e = launch_pdl<2>(winattn_bwd_tc_kernel, grid, dim3(AB_THREADS), (size_t)AB_SMEM, st, 1, tmQKV, tmDO, tmQKV4, tmDO3, tmOut,
+                                         bias, dbias_partial, n_windows, nH, g, ad, trace_buf);
+        if (e != cudaSuccess) { set_error("winattn_bwd_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    }
 #ifdef MSU_ATT_TRACE_BUILD
     if (trace_on) {   // synchronous dump of the per-unit role timeline of two CTAs
         long long* host = (long long*)malloc(trace_n * sizeof(long long));
