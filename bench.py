@@ -82,6 +82,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:                                # let the nvidia-smi process leave the driver before anything else is timed: its exit
+            self.proc.wait(timeout=5)       # was seen to stall the launching thread for 40-50 ms (a 10 % dent in a 10-step e2e loop)
+        except Exception:
+            self.proc.kill()
+        time.sleep(0.2)
         sm, mx, reasons = [], None, set()
         for l in self.lines:
             f = [t.strip() for t in l.split(",")]
@@ -419,45 +424,73 @@ def main():
     # The batches come through the repo's input stager (data.CudaPrefetcher): batch i+1 is copied from pinned host memory
     # on a copy stream while step i runs, exactly one H2D copy of images + masks and one D2H loss read per step.
     from semantic_segmentation_of_stylegan2_artifacts_b200.data import CudaPrefetcher
-    # The loss of every step is read on the host (4 B, pinned buffer): the copy of step i is issued behind the step and waited
-    # for after step i + 1 has been launched, so that the CPU-side launch of a step (a ~0.7 ms graph launch with ~830 kernel
-    # nodes) overlaps the previous step instead of sitting between two steps; the last loss is waited for before the clock stops.
-    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    # The loss of every step is read on the host (4 B, pinned ring buffer): the copy of step i is issued behind the step and waited
+    # for after step i + E2E_DEPTH has been launched, so that (1) the CPU-side launch of a step (a ~0.7 ms graph launch with ~830
+    # kernel nodes) overlaps the previous step instead of sitting between two steps and (2) the device has E2E_DEPTH steps queued when
+    # the host hiccups (a 20-50 ms scheduling stall in a 10-step, 230 ms loop was a 10-20 % outlier with a queue of one).  Every loss
+    # still reaches the host inside the timed region, the last ones before the clock stops.
+    E2E_DEPTH = 3
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(E2E_DEPTH + 1)]
+    loss_ev = [torch.cuda.Event() for _ in range(E2E_DEPTH + 1)]
     losses_read = []
+    e2e_trace = os.environ.get("MSU_BENCH_E2E_TRACE") == "1"
+    gpu_marks = []
 
     def e2e_loop(loader_):
-        pending = None
+        pending = []                     # ring slots of launched steps whose loss has not been read yet, oldest first
+        t_prev = time.perf_counter()
         for i, batch in enumerate(loader_):
+            if e2e_trace:
+                t_now = time.perf_counter()
+                sys.stderr.write(f"[e2e] step {i}: host {1e3 * (t_now - t_prev):.2f} ms since the previous\n")
+                t_prev = t_now
             xd, yd = batch["image"], batch["label"]
+            if e2e_trace:
+                ga = torch.cuda.Event(enable_timing=True); ga.record()
             if graph is not None:
                 x_d.copy_(xd, non_blocking=True)
                 y_d.copy_(yd, non_blocking=True)
                 lt = run_step()
             else:
                 lt = step(xd, yd)
-            k = i & 1
+            if e2e_trace:
+                gb = torch.cuda.Event(enable_timing=True); gb.record()
+                gpu_marks.append((ga, gb))
+            k = i % (E2E_DEPTH + 1)
             loss_host[k].copy_(lt.detach().reshape(1).float(), non_blocking=True)
             loss_ev[k].record()
-            if pending is not None:
-                loss_ev[pending].synchronize()
-                losses_read.append(float(loss_host[pending]))
-            pending = k
-        if pending is not None:
-            loss_ev[pending].synchronize()
-            losses_read.append(float(loss_host[pending]))
+            pending.append(k)
+            if len(pending) > E2E_DEPTH:
+                j = pending.pop(0)
+                loss_ev[j].synchronize()
+                losses_read.append(float(loss_host[j]))
+        for j in pending:
+            loss_ev[j].synchronize()
+            losses_read.append(float(loss_host[j]))
+        if e2e_trace and gpu_marks:
+            torch.cuda.synchronize()
+            sys.stderr.write("[e2e-gpu] step ms: " + " ".join(f"{a.elapsed_time(b):.2f}" for a, b in gpu_marks) + "\n")
+            sys.stderr.write("[e2e-gpu] gap ms:  " + " ".join(f"{gpu_marks[i][1].elapsed_time(gpu_marks[i + 1][0]):.2f}" for i in range(len(gpu_marks) - 1)) + "\n")
+            gpu_marks.clear()
 
     # untimed warm-up of the loop itself (max(3, W) steps): the stager's device buffers come out of the caching allocator's
     # pool afterwards instead of cudaMalloc (a device-wide stall of ~1 ms each, up to 25 % of a 10-step run on some boxes)
-    e2e_loop(CudaPrefetcher([{"image": x_h, "label": y_h} for _ in range(max(3, args.warmup))], dev))
+    # (ONE stager for warm-up and timed loop, as a training run has one: a second instance would bring a new copy stream and new
+    # device buffers, i.e. six cudaMalloc calls of 16-50 MB inside the timed region, 20-80 ms on some boxes)
+    loader = CudaPrefetcher([{"image": x_h, "label": y_h} for _ in range(max(3, args.warmup))], dev)
+    e2e_loop(loader)
     losses_read.clear()
-    loader = CudaPrefetcher([{"image": x_h, "label": y_h} for _ in range(args.steps)], dev)
+    loader.loader = [{"image": x_h, "label": y_h} for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()              # a generation-2 collection inside a 10-step host-paced loop is a 100 ms outlier
     barrier()
     e0.record()
     e2e_loop(loader)
     e1.record()
     barrier()
+    gc.enable()
     assert len(losses_read) == args.steps and all(v == v for v in losses_read), "every step's loss must reach the host"
     te = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -471,14 +504,19 @@ def main():
     xu_h = (x_h.permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
     yu_h = (y_h * 255.0).to(torch.uint8).contiguous().pin_memory()
     fl_h = (torch.arange(B) % 2).to(torch.uint8).pin_memory()
-    e2e_loop(CudaPrefetcher([{"image": xu_h, "label": yu_h, "flip": fl_h} for _ in range(max(3, args.warmup))], dev, stage_uint8=True))
+    loader = CudaPrefetcher([{"image": xu_h, "label": yu_h, "flip": fl_h} for _ in range(max(3, args.warmup))], dev, stage_uint8=True)
+    e2e_loop(loader)
     losses_read.clear()       # untimed warm-up, as above (also the first launch of the staging kernel)
-    loader = CudaPrefetcher([{"image": xu_h, "label": yu_h, "flip": fl_h} for _ in range(args.steps)], dev, stage_uint8=True)
+    loader.loader = [{"image": xu_h, "label": yu_h, "flip": fl_h} for _ in range(args.steps)]
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    gc.collect()
+    gc.disable()
     barrier()
     u0.record()
     e2e_loop(loader)
     u1.record()
+    gc.enable()
     barrier()
     tu = torch.tensor([u0.elapsed_time(u1)], device=dev)
     if world > 1:
@@ -608,8 +646,8 @@ def main():
                        "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                        "l2": "working set >> L2: ~10 GB of activations are written and re-read every step",
                        "e2e_loop": "per step: H2D of that step's images + masks from pinned host memory (copy stream, one step ahead), "
-                                   "the step through the public API, D2H of its loss into a pinned buffer read on the host while "
-                                   "the next step runs (last one before the clock stops)",
+                                   "the step through the public API, D2H of its loss into a pinned ring buffer read on the host up to "
+                                   "3 steps later (the last ones before the clock stops)",
                        "optimizer": {"none": "excluded (metric is fwd+bwd)",
                                      "fused": "included: gradient all-reduce + replicated one-launch FusedAdamW",
                                      "sharded": "included: reduce-scatter -> AdamW on the rank's shard -> all-gather per bucket, "
