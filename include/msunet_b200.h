@@ -66,7 +66,8 @@ typedef struct {
     int64_t ldc, ldr, ldh;
     const float* rowscale;  /* per-sample scale of the branch before the residual add                     */
     int32_t rows_per_sample;
-    int32_t act;            /* 0 none, 1 exact (erf) GELU                                                  */
+    int32_t act;            /* 0 none, 1 exact (erf) GELU, 2 GELU with Cpre := GELU'(pre) (the MLP forward stores  \
+                               the derivative, not the pre-activation), 3 (with H) H already holds GELU'(pre)   */
     int32_t map;            /* MSU_MAP_NONE / WINDOW / SHUFFLE / UNSHUFFLE on the output                  */
     int32_t dtype;          /* dtype of C, Cpre, R, H                                                     */
     int32_t geo[6];

@@ -34,9 +34,9 @@ __device__ __forceinline__ void epilogue_store(const MsuEpilogue& E, int64_t m, 
     RowCol rc = map_rc(E.map, E.geo, m, n);
     if (rc.row < 0) return;  // padding token: output dropped (TV:models/swin_transformer.py:227)
     const int64_t o = rc.row * E.ldc + rc.col;
-    if (E.Cpre != nullptr) st_from_f(E.Cpre, o, E.dtype, v);
-    if (E.act == 1) v = gelu_f(v);
-    if (E.H != nullptr) v *= gelu_grad_f(ld_as_f(E.H, m * E.ldh + n, E.dtype));
+    if (E.Cpre != nullptr) st_from_f(E.Cpre, o, E.dtype, E.act == 2 ? gelu_grad_f(v) : v);   // act 2: Cpre = GELU'(pre)
+    if (E.act == 1 || E.act == 2) v = gelu_f(v);
+    if (E.H != nullptr) v *= (E.act == 3 ? ld_as_f(E.H, m * E.ldh + n, E.dtype) : gelu_grad_f(ld_as_f(E.H, m * E.ldh + n, E.dtype)));
     if (E.rowscale != nullptr) v *= E.rowscale[rc.row / E.rows_per_sample];
     if (E.R != nullptr) v += ld_as_f(E.R, rc.row * E.ldr + rc.col, E.dtype);
     if (E.out_f32) {

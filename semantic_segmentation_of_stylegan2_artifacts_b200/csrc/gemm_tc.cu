@@ -153,6 +153,15 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     const float e = ex2_approx(x2c * -0.72134752044448170368f);   // exp(-x^2 / 2)
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// GELU(x) and GELU'(x) together (they share Phi): the MLP forward stores the derivative instead of the pre-activation
+// (MsuEpilogue.act = 2), so the backward epilogue is a plain multiply (act = 3) instead of 15 instructions per element
+__device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {
+    float x2c;
+    const float cdf = phi_cdf_fast(x, x2c);
+    const float e = ex2_approx(x2c * -0.72134752044448170368f);   // exp(-x^2 / 2)
+    grad = fmaf(x * 0.39894228040143267794f, e, cdf);
+    return x * cdf;
+}
 // the two bf16 halves of a packed word as fp32 (ALU shifts / masks; no XU conversion)
 __device__ __forceinline__ float bf16lo_f(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
@@ -527,6 +536,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             pk[i] = pack_bf16x2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
                             v[g * 8 + 2 * i] = bf16lo_f(pk[i]);
                             v[g * 8 + 2 * i + 1] = bf16hi_f(pk[i]);
+                            if (E.act == 2) {      // Cpre receives GELU'(pre) instead of pre
+                                float g0, g1;
+                                v[g * 8 + 2 * i] = gelu_and_grad_fast(v[g * 8 + 2 * i], g0);
+                                v[g * 8 + 2 * i + 1] = gelu_and_grad_fast(v[g * 8 + 2 * i + 1], g1);
+                                pk[i] = pack_bf16x2(g0, g1);
+                            }
                         }
                         *reinterpret_cast<uint4*>(slab_aux + slab_off(lane, g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
@@ -544,8 +559,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f[8];
                         unpack8(*reinterpret_cast<const uint4*>(ab + slab_off(lane, g)), f);
                         if (E.H != nullptr) {
+                            if (E.act == 3) {      // H already holds GELU'(pre)
 #pragma unroll
-                            for (int i = 0; i < 8; i++) v[g * 8 + i] *= gelu_grad_fast(f[i]);
+                                for (int i = 0; i < 8; i++) v[g * 8 + i] *= f[i];
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) v[g * 8 + i] *= gelu_grad_fast(f[i]);
+                            }
                             if (E.rowscale != nullptr) {
 #pragma unroll
                                 for (int i = 0; i < 8; i++) v[g * 8 + i] *= rs;
@@ -649,7 +669,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nchunks = (p.BN + TC_CW - 1) / TC_CW;
         const int rsub = lane >> 2, q = lane & 3;       // store phase: rows rsub + 8 j (j < 4), 16 B quarter q of the 64 B row
         uint8_t* scr = sScratch + (size_t)(warp - 2) * TC_SCRATCH_BYTES;
-        const bool passthrough = (E.act == 0 && Hp == nullptr && E.rowscale == nullptr && Rp == nullptr);
+        const bool passthrough = ((E.act == 0 || E.act == 3) && Hp == nullptr && E.rowscale == nullptr && Rp == nullptr);
         int acc = 0; uint32_t acc_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
@@ -768,7 +788,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 4; j++) {
                     if (o[j] < 0) continue;
                     const uint4 tv = *reinterpret_cast<const uint4*>(scr + (rsub + 8 * j) * TC_CPITCH_B + q * 16);
-                    if (Cpre != nullptr) *reinterpret_cast<uint4*>(Cpre + o[j]) = tv;
+                    if (Cpre != nullptr && E.act != 2) *reinterpret_cast<uint4*>(Cpre + o[j]) = tv;
                     if (passthrough) {
                         *reinterpret_cast<uint4*>(Cp + o[j]) = tv;
                         continue;
@@ -778,12 +798,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (E.act == 1) {
 #pragma unroll
                         for (int i = 0; i < 8; i++) w[i] = gelu_fast(w[i]);
+                    } else if (E.act == 2) {       // Cpre receives GELU'(pre) instead of pre
+                        float gq[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) w[i] = gelu_and_grad_fast(w[i], gq[i]);
+                        if (Cpre != nullptr)
+                            *reinterpret_cast<uint4*>(Cpre + o[j]) = make_uint4(pack_bf16x2(gq[0], gq[1]), pack_bf16x2(gq[2], gq[3]),
+                                                                                pack_bf16x2(gq[4], gq[5]), pack_bf16x2(gq[6], gq[7]));
                     }
                     if (Hp != nullptr) {
                         float hf[8];
                         unpack8(hraw[j], hf);
+                        if (E.act == 3) {          // H already holds GELU'(pre)
 #pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] *= gelu_grad_fast(hf[i]);
+                            for (int i = 0; i < 8; i++) w[i] *= hf[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) w[i] *= gelu_grad_fast(hf[i]);
+                        }
                     }
                     if (E.rowscale != nullptr) {
 #pragma unroll

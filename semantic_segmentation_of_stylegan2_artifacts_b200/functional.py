@@ -57,6 +57,7 @@ def _al(*ts):
 import os as _os
 
 _WG_ON = _os.environ.get("MSUNET_B200_WGRAD_STREAM", "1") != "0"
+_STORE_GELU_GRAD = _os.environ.get("MSUNET_B200_STORE_GELU_GRAD", "1") != "0"   # MLP forward saves GELU'(h) instead of h
 _FUSED_HEAD_LN = _os.environ.get("MSUNET_B200_FUSED_HEAD_LN", "1") != "0"   # head LayerNorm + 1x1 conv in the second conv's epilogue
 _wg_streams: dict = {}
 
@@ -270,7 +271,9 @@ class SwinBlockFn(Function):
         xn, mean2, rstd2 = ops.ln_fwd(x1, n2w, n2b, T, Cd)
         h = torch.empty(T, hid, dtype=dt, device=dev)
         a = torch.empty(T, hid, dtype=dt, device=dev)
-        gemm(operand(xn), w_fwd(f1w, dt), epilogue(a, Cpre=h, bias=f1b, act=1), T, hid, Cd, dev)
+        # `h` holds GELU'(pre-activation), not the pre-activation (act = 2): the backward's dh epilogue is then a plain multiply
+        # (act = 3) instead of re-deriving GELU' (15 of its 31 instructions per element; MSUNET_B200_STORE_GELU_GRAD=0: keep h)
+        gemm(operand(xn), w_fwd(f1w, dt), epilogue(a, Cpre=h, bias=f1b, act=2 if _STORE_GELU_GRAD else 1), T, hid, Cd, dev)
         x2 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(a), w_fwd(f2w, dt), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
         ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
@@ -305,7 +308,8 @@ class SwinBlockFn(Function):
             wg.run(lambda: gemm(dy2t, operand(a, orient=1), epilogue(dW2, out_f32=True, colsum=db2), Cd, hid, T, dev))
             dh = torch.empty(T, hid, dtype=dt, device=dev)
             gemm(dy2, w_dgrad(f2w, dt),
-                 epilogue(dh, H=h, ldh=hid, rowscale=sd2 if fused_sd else None, rps=HW if fused_sd else 0), T, hid, Cd, dev)
+                 epilogue(dh, H=h, ldh=hid, rowscale=sd2 if fused_sd else None, rps=HW if fused_sd else 0,
+                          act=3 if _STORE_GELU_GRAD else 0), T, hid, Cd, dev)
             db1, dW1 = ops.grad_out(f1b), ops.grad_out(f1w)
             wg.run(lambda: gemm(operand(dh, orient=1), operand(xn, orient=1), epilogue(dW1, out_f32=True, colsum=db1), hid, Cd, T, dev))
             dxn = torch.empty(T, Cd, dtype=dt, device=dev)

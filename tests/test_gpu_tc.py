@@ -549,3 +549,40 @@ def test_head_layernorm_dot_fused_into_conv_epilogue(ops, E, r, B):
     with torch.no_grad():
         lo_i = Fn.HeadFn.apply(x.detach(), *[p.detach() for p in prm], B, r).float()
     assert torch.equal(lo_i, lo_f)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 384, 96), (640, 200, 72)])
+def test_gelu_with_stored_derivative(ops, M, N, K):
+    """MsuEpilogue.act = 2 (forward: C = GELU(pre), Cpre = GELU'(pre) of the dtype-rounded pre-activation) and act = 3 (backward:
+    multiply by the stored derivative) on the TMA-store path (N % 32 == 0) and the generic path, tcgen05 vs the SIMT engine
+    and vs fp64 (TV:ops/misc.py:292-303 forward / its autograd backward)."""
+    torch.manual_seed(3)
+    bf = torch.bfloat16
+    a = torch.randn(M, K, device=DEV).to(bf)
+    w = (torch.randn(N, K, device=DEV) * 0.2).to(bf)
+    b = torch.randn(N, device=DEV) * 0.5
+
+    def fwd():
+        y = torch.empty(M, N, dtype=bf, device=DEV)
+        g = torch.empty(M, N, dtype=bf, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=g, bias=b, act=2), M, N, K, torch.device(DEV))
+        return torch.stack([y.float(), g.float()])
+    tc, simt = run_both(ops, fwd)
+    pre = (a.double() @ w.double().t() + b.double()).to(bf).double()       # the activation sees the rounded pre-activation
+    cdf = 0.5 * (1 + torch.erf(pre / 2 ** 0.5))
+    ref = torch.stack([pre * cdf, cdf + pre * torch.exp(-pre * pre / 2) / (2 * torch.pi) ** 0.5])
+    # a product that lands on a bf16 rounding boundary may round the other way on the two engines: compare against fp64 with a
+    # bound that allows one such flip of the pre-activation (its effect on GELU / GELU' is <= 1 ulp(bf16) of |pre|)
+    assert float((tc.double().cpu() - ref.cpu()).abs().max()) < 4e-2
+    assert float((tc.double().cpu() - ref.cpu()).abs().mean()) < 2.5e-3
+    assert float((simt.double().cpu() - ref.cpu()).abs().mean()) < 2.5e-3
+    g = tc[1].to(bf)
+    dy = torch.randn(M, K, device=DEV).to(bf)                               # backward-like product: [M, K] x [N, K]^T ⊙ g
+
+    def bwd():
+        d = torch.empty(M, N, dtype=bf, device=DEV)
+        ops.gemm(ops.operand(dy), ops.operand(w), ops.epilogue(d, H=g, ldh=N, act=3), M, N, K, torch.device(DEV))
+        return d.float()
+    tb, sb = run_both(ops, bwd)
+    refb = (dy.double() @ w.double().t()) * g.double()
+    assert relmax(tb, refb) < 1.5e-2 and relmax(sb, refb) < 1.5e-2
