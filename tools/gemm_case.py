@@ -51,6 +51,27 @@ def dgelu(M, N, K):
             2 * M * N * K, (M * K + 2 * M * N) * 2)
 
 
+def fc1g(M, N, K):
+    """fc1 with the stored derivative (act = 2: C = GELU, Cpre = GELU')"""
+    a = torch.randn(M, K, device=dev).to(bf)
+    w = (torch.randn(N, K, device=dev) * 0.1).to(bf)
+    b = torch.randn(N, device=dev)
+    y = torch.empty(M, N, dtype=bf, device=dev)
+    pre = torch.empty(M, N, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=b, act=2), M, N, K, dev),
+            2 * M * N * K, (M * K + 2 * M * N) * 2)
+
+
+def dmul(M, N, K):
+    """dh with the stored derivative (act = 3: multiply by H)"""
+    a = torch.randn(M, K, device=dev).to(bf)
+    w = (torch.randn(N, K, device=dev) * 0.1).to(bf)
+    h = torch.randn(M, N, device=dev).to(bf)
+    y = torch.empty(M, N, dtype=bf, device=dev)
+    return (lambda: ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, H=h, ldh=N, act=3), M, N, K, dev),
+            2 * M * N * K, (M * K + 2 * M * N) * 2)
+
+
 def conv(B, S, E):
     x = torch.randn(B * S * S, E, device=dev).to(bf)
     w = (torch.randn(E, 9 * E, device=dev) * 0.05).to(bf)
@@ -99,7 +120,8 @@ def proj_win(Bn, H, C):
 cases = {
     "head_expand": lambda: head_expand(16, 128, 96), "projwin_s0": lambda: proj_win(16, 128, 96),
     "fc1_s0": lambda: fc1(262144, 384, 96), "fc2_s0": lambda: resid(262144, 96, 384),
-    "dh_s0": lambda: dgelu(262144, 384, 96), "qkv_s0": lambda: plain(283024, 288, 96),
+    "dh_s0": lambda: dgelu(262144, 384, 96), "fc1g_s0": lambda: fc1g(262144, 384, 96), "dmul_s0": lambda: dmul(262144, 384, 96),
+    "fc1g_s2": lambda: fc1g(16384, 1536, 384), "dmul_s2": lambda: dmul(16384, 1536, 384), "qkv_s0": lambda: plain(283024, 288, 96),
     "fc1_s1": lambda: fc1(65536, 768, 192), "fc2_s1": lambda: resid(65536, 192, 768),
     "fc1_s2": lambda: fc1(16384, 1536, 384), "plain_s2": lambda: plain(16384, 1536, 384),
     "dh_s2": lambda: dgelu(16384, 1536, 384), "fc2_s2": lambda: resid(16384, 384, 1536),
