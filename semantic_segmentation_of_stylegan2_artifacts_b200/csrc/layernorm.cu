@@ -93,18 +93,16 @@ __device__ __forceinline__ float group_sum_u(float v, int lpr) {   // branch-fre
     return v;
 }
 
-// Forward: persistent warps.  Warp w walks super-groups w, w + P, ... of LN_RG row groups (rpw rows each); the 16 B loads of
-// the NEXT super-group are issued before the current one is reduced (register double buffer), so every warp keeps
-// LN_RG * NV * 512 B of loads in flight all the time instead of only during the first third of a short-lived block's life
-// (the one-shot version: 4.4 TB/s plain, 2.6 TB/s for the head's dot variant).  gamma / beta live in registers for
-// narrow rows.  DOT (head LayerNorm + 1x1 conv, network/model_parts.py:842-846) never forms y:
+// Head forward (LayerNorm + 1x1 conv as a dot product, network/model_parts.py:842-846; the default bf16 path has it in the second
+// conv's epilogue instead, MsuEpilogue.lnd_*).  Persistent warps: warp w walks super-groups w, w + P, ... of LN_RG row groups (rpw
+// rows each); the 16 B loads of the NEXT super-group are issued before the current one is reduced (register double buffer).
+// y is never formed:
 //   logit = sum_c ((x_c - mu) rs gamma_c + beta_c) w_c = rs (sum_c x_c gw_c - mu G) + Bw,   gw = gamma w, G = sum gw, Bw = sum beta w
-// i.e. 3 FMAs per element on top of the statistics.
+// i.e. 3 FMAs per element on top of the statistics, gw in registers (NV <= 3 vectors per lane).
 constexpr int LN_RG = 2;
 template <typename T, int NV>
 struct LnGroup {
-    int64_t r[LN_RG], lr[LN_RG];
-    bool live[LN_RG];
+    int64_t r[LN_RG];
     uint4 xr[LN_RG][NV];
 };
 // window row -> pixel row with 32-bit arithmetic (row counts are far below 2^31; the 64-bit divisions of win_to_pix cost
@@ -130,76 +128,52 @@ __device__ __forceinline__ int64_t pix_to_win32(const WinGeo& g, uint32_t pr) {
     return (int64_t)b * (g.nwin() * WT) + (wy * g.nwx() + wx) * WT + (ry - wy * WS) * WS + (rx - wx * WS);
 }
 
-template <typename T, int NV, int MODE>
-__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_fwd_persist_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, T* __restrict__ Y,
-                                                              float* __restrict__ mean, float* __restrict__ rstd,
-                                                              int64_t rows, int C, float invC, int lpr,
-                                                              WinGeo wg, MergeGeo mg, const float* __restrict__ dotw,
-                                                              float* __restrict__ dot_m2) {
-    constexpr bool DOT = MODE == LNM_DOT;
-    constexpr bool PREG = DOT && NV <= 3;   // DOT: gamma * w in registers; other modes read gamma / beta from shared memory
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_fwd_dot_kernel(const T* __restrict__ X, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, T* __restrict__ Y,
+                                                                      float* __restrict__ mean, float* __restrict__ rstd,
+                                                                      int64_t rows, int C, float invC, int lpr,
+                                                                      const float* __restrict__ dotw, float* __restrict__ dot_m2) {
+    static_assert(NV <= 3, "gamma * w lives in registers");
     constexpr int VW = VecW<T>::N;
     const int lane = threadIdx.x & 31;
     const int rpw = 32 / lpr, sub = lane / lpr, l = lane - sub * lpr;
-    const int Cin = C / 4;
     const int64_t P = (int64_t)gridDim.x * LN_WARPS;
     const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int64_t nsuper = (rows + (int64_t)rpw * LN_RG - 1) / ((int64_t)rpw * LN_RG);
     bool vld[NV];
-#pragma unroll
-    for (int j = 0; j < NV; j++) vld[j] = (l + lpr * j) * VW < C;
-    float pg[PREG ? NV : 1][VW], pb[(PREG && !DOT) ? NV : 1][VW];
+    float pg[NV][VW];
     float Gsum = 0.f, Bsum = 0.f;
-    extern __shared__ float ln_sp[];        // [gamma | beta] (non-DOT)
-    if (!DOT) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) { ln_sp[c] = gamma[c]; ln_sp[C + c] = beta[c]; }
-        __syncthreads();
-    }
-    if (PREG) {
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
-            const int c = (l + lpr * j) * VW;
+    for (int j = 0; j < NV; j++) {
+        const int c = (l + lpr * j) * VW;
+        vld[j] = c < C;
 #pragma unroll
-            for (int e = 0; e < VW; e++) { pg[PREG ? j : 0][e] = 0.f; if (!DOT) pb[(PREG && !DOT) ? j : 0][e] = 0.f; }
-            if (vld[j]) {
-                ldf(gamma + c, pg[PREG ? j : 0], VW);
-                if (DOT) {
-                    float wl[VW], bt[VW];
-                    ldf(dotw + c, wl, VW);
-                    ldf(beta + c, bt, VW);
+        for (int e = 0; e < VW; e++) pg[j][e] = 0.f;
+        if (vld[j]) {
+            float wl[VW], bt[VW];
+            ldf(gamma + c, pg[j], VW);
+            ldf(dotw + c, wl, VW);
+            ldf(beta + c, bt, VW);
 #pragma unroll
-                    for (int e = 0; e < VW; e++) {
-                        pg[PREG ? j : 0][e] *= wl[e];
-                        Gsum += pg[PREG ? j : 0][e];
-                        Bsum = fmaf(bt[e], wl[e], Bsum);
-                    }
-                } else {
-                    ldf(beta + c, pb[(PREG && !DOT) ? j : 0], VW);
-                }
+            for (int e = 0; e < VW; e++) {
+                pg[j][e] *= wl[e];
+                Gsum += pg[j][e];
+                Bsum = fmaf(bt[e], wl[e], Bsum);
             }
         }
-        if (DOT) { Gsum = group_sum_u(Gsum, lpr); Bsum = group_sum_u(Bsum, lpr); }
     }
+    Gsum = group_sum_u(Gsum, lpr);
+    Bsum = group_sum_u(Bsum, lpr);
 
     auto load = [&](int64_t sg, LnGroup<T, NV>& G) {
 #pragma unroll
         for (int g = 0; g < LN_RG; g++) {
             G.r[g] = (sg * LN_RG + g) * rpw + sub;
-            G.lr[g] = G.r[g];       // LayerNorm row (statistics index)
-            G.live[g] = G.r[g] < rows;
-            if (MODE == LNM_WINDOW && G.live[g]) {
-                G.lr[g] = win_to_pix32(wg, (uint32_t)G.r[g]);
-                G.live[g] = G.lr[g] >= 0;  // zero padding token (not masked: TV:models/swin_transformer.py:152-156)
-            }
 #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const int c = (l + lpr * j) * VW;
                 G.xr[g][j] = make_uint4(0, 0, 0, 0);
-                if (G.live[g] && vld[j]) {
-                    const T* p = (MODE == LNM_MERGE) ? X + merge_off(mg, G.lr[g], c, Cin) : X + G.lr[g] * C + c;
-                    G.xr[g][j] = *reinterpret_cast<const uint4*>(p);
-                }
+                if (G.r[g] < rows && vld[j]) G.xr[g][j] = *reinterpret_cast<const uint4*>(X + G.r[g] * C + (l + lpr * j) * VW);
             }
         }
     };
@@ -219,7 +193,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_fwd_persist
 #pragma unroll
                 for (int e = 0; e < VW; e++) {
                     s += x[j][e];
-                    if (DOT && PREG) d = fmaf(x[j][e], pg[PREG ? j : 0][e], d);
+                    d = fmaf(x[j][e], pg[j][e], d);
                 }
             }
             const float mu = group_sum_u(s, lpr) * invC;
@@ -232,58 +206,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1) ln_fwd_persist
                 }
             }
             const float rs = rsqrtf(group_sum_u(v, lpr) * invC + LN_EPS);
-            const float nmr = -mu * rs;
-            if (cur.live[g] && l == 0) {
-                mean[cur.lr[g]] = mu;
-                rstd[cur.lr[g]] = rs;
-            }
-            const bool in_range = cur.r[g] < rows;
-            if (DOT && PREG) {
-                d = group_sum_u(d, lpr);
-                if (in_range && l == 0) {
-                    const float dc = fmaf(-mu, Gsum, d) * rs;           // sum_c gw_c x-hat_c
-                    Y[cur.r[g]] = from_f<T>(dc + Bsum);
-                    dot_m2[cur.r[g]] = dc * invC;                         // the backward's row mean of g * x-hat, per unit d(logit)
-                }
-                continue;
-            }
-            float dot = 0.f;
-#pragma unroll
-            for (int j = 0; j < NV; j++) {
-                const int c = (l + lpr * j) * VW;
-                if (in_range && vld[j]) {
-                    float y[VW];
-                    if (cur.live[g]) {
-                        float gl[VW], bl[VW];
-                        if (PREG) {
-#pragma unroll
-                            for (int e = 0; e < VW; e++) { gl[e] = pg[PREG ? j : 0][e]; bl[e] = pb[(PREG && !DOT) ? j : 0][e]; }
-                        } else if (DOT) {
-                            ldf(gamma + c, gl, VW);
-                            ldf(beta + c, bl, VW);
-                        } else {
-                            ldf(ln_sp + c, gl, VW);
-                            ldf(ln_sp + C + c, bl, VW);
-                        }
-#pragma unroll
-                        for (int e = 0; e < VW; e++) y[e] = fmaf(fmaf(x[j][e], rs, nmr), gl[e], bl[e]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < VW; e++) y[e] = 0.f;
-                    }
-                    if (DOT) {
-                        float wl[VW];
-                        ldf(dotw + c, wl, VW);
-#pragma unroll
-                        for (int e = 0; e < VW; e++) dot = fmaf(y[e], wl[e], dot);
-                    } else {
-                        VecW<T>::st(Y + cur.r[g] * C + c, y);
-                    }
-                }
-            }
-            if (DOT) {
-                dot = group_sum_u(dot, lpr);
-                if (in_range && l == 0) Y[cur.r[g]] = from_f<T>(dot);
+            d = group_sum_u(d, lpr);
+            if (cur.r[g] < rows && l == 0) {
+                const float dc = fmaf(-mu, Gsum, d) * rs;           // sum_c gw_c x-hat_c
+                mean[cur.r[g]] = mu;
+                rstd[cur.r[g]] = rs;
+                Y[cur.r[g]] = from_f<T>(dc + Bsum);
+                dot_m2[cur.r[g]] = dc * invC;                         // the backward's row mean of g * x-hat, per unit d(logit)
             }
         }
         cur = nxt;
@@ -774,10 +703,11 @@ static int launch_fwd(const void* X, const float* gamma, const float* beta, void
     if (dotw != nullptr) {
         if (in_map != MSU_MAP_NONE || out_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: dotw with a row map is not supported"); return -1; }
         if (NV > 3 || dot_m2 == nullptr) { set_error("msu_ln_fwd: dotw needs C <= %d and a dot_m2 output", 96 * VecW<T>::N); return -1; }
-        // persistent variant (register-prefetched, y never formed): the resident block count, 2 per SM for narrow rows
-        const unsigned pgrid = (unsigned)imax(1, imin(want, (int64_t)num_sms() * (NV <= 3 ? 2 : 1)));
-        ln_fwd_persist_kernel<T, NV, LNM_DOT><<<pgrid, LN_WARPS * 32, 2 * C * sizeof(float), st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd,
-                                                                                                  rows, C, invC, lpr, wg, mg, dotw, dot_m2);
+        // persistent, register-prefetched, y never formed: the resident block count (2 per SM)
+        if constexpr (NV <= 3) {
+            const unsigned pgrid = (unsigned)imax(1, imin(want, (int64_t)num_sms() * 2));
+            ln_fwd_dot_kernel<T, NV><<<pgrid, LN_WARPS * 32, 0, st>>>((const T*)X, gamma, beta, (T*)Y, mean, rstd, rows, C, invC, lpr, dotw, dot_m2);
+        }
     } else if (out_map == MSU_MAP_WINDOW) {
         if (in_map != MSU_MAP_NONE) { set_error("msu_ln_fwd: in_map and out_map together are not supported"); return -1; }
         LN_FWD_LAUNCH(LNM_WINDOW);

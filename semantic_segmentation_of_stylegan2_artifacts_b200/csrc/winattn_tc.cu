@@ -1,11 +1,13 @@
-// Shifted-window attention core on tcgen05 (bf16): S = Q K^T and O = P V run on the 5th-gen tensor cores with
-// TMEM accumulators; the softmax (scale, relative-position bias, -100 shift mask, fp32 statistics) runs on
-// the TMEM lanes: one thread owns one query row.  TV:models/swin_transformer.py:181-214.
+// Shifted-window attention core on tcgen05 (bf16): S = Q K^T, O = P V and the five backward products run on the 5th-gen tensor
+// cores with TMEM accumulators; the softmax (scale, relative-position bias, -100 shift mask, fp32 statistics) runs on the TMEM
+// lanes (forward: one thread per query row; backward: two).  TV:models/swin_transformer.py:181-214.
 //
-// Tiny-tile strategy (49 tokens x head-dim 32): two windows are packed into one M=128 MMA; Q/K/V(/dO) tiles are
-// [64 rows x 32] bf16 TMA boxes (64B swizzle) taken directly from the window-ordered qkv rows (rows 49..63 of a box
-// belong to the next window: finite values that meet exact zeros in P), double buffered so that the loads of the
-// next unit are in flight while the current one is computed.  Kernel-specific notes precede each kernel.
+// Tiny-tile strategy (49 tokens x head-dim 32): two windows are packed into one M=128 MMA; the Q / K / V (/ dO) tiles of a unit
+// (window pair x head) are [64 rows x 32] bf16 blocks (64B swizzle) that arrive as ONE 4-D TMA box straight from the window-ordered
+// qkv rows (rows 49..63 of a block belong to the next window: finite values that meet exact zeros in P), the unit's outputs leave as
+// ONE TMA box store.  Forward: 128-thread CTAs, three per SM, operand tiles double buffered.  Backward: one persistent
+// warp-specialised CTA per SM (softmax group / epilogue group / MMA-issuing warp, two TMEM buffers, three operand stages).
+// Kernel-specific notes precede each kernel.
 #include <stdio.h>
 #include <stdlib.h>
 

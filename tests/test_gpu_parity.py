@@ -332,6 +332,16 @@ def test_cuda_prefetcher_yields_every_batch_in_order():
     assert seen == [(float(i), float(-i)) for i in range(5)]
     with pytest.raises(RuntimeError):
         CudaPrefetcher(batches, "cpu")
+    # ring of persistent device buffers: a batch stays valid while RING - 1 further batches are drawn, the same stager can be
+    # iterated again, and a batch of another shape gets its own buffer
+    pf = CudaPrefetcher(batches + [{"image": torch.full((1, 3, 8, 8), 9.0), "label": torch.full((1, 8, 8), -9.0), "case_name": ["c9"]}], dev)
+    for _ in range(2):
+        held = []
+        for b in pf:
+            held.append((b["image"], float(b["image"].flatten()[0])))
+            for t, v in held[-(CudaPrefetcher.RING - 1):]:
+                assert float(t.mean()) == v
+        assert [v for _, v in held] == [0.0, 1.0, 2.0, 3.0, 4.0, 9.0] and held[-1][0].shape[0] == 1
 
 
 @pytest.mark.gpu

@@ -546,8 +546,13 @@ def test_head_layernorm_dot_fused_into_conv_epilogue(ops, E, r, B):
     for a, b in zip(gr_f, gr_u):
         assert float((a - b).norm() / b.norm().clamp_min(1e-20)) < 5e-3
     # inference: no gradient wanted -> the rows are not stored at all, the logits are the same
-    with torch.no_grad():
-        lo_i = Fn.HeadFn.apply(x.detach(), *[p.detach() for p in prm], B, r).float()
+    old = Fn._FUSED_HEAD_LN
+    Fn._FUSED_HEAD_LN = True
+    try:
+        with torch.no_grad():
+            lo_i = Fn.HeadFn.apply(x.detach(), *[p.detach() for p in prm], B, r).float()
+    finally:
+        Fn._FUSED_HEAD_LN = old
     assert torch.equal(lo_i, lo_f)
 
 
