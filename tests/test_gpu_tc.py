@@ -591,3 +591,35 @@ def test_gelu_with_stored_derivative(ops, M, N, K):
     tb, sb = run_both(ops, bwd)
     refb = (dy.double() @ w.double().t()) * g.double()
     assert relmax(tb, refb) < 1.5e-2 and relmax(sb, refb) < 1.5e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(640, 384, 768), (1000, 200, 1024), (129, 96, 1536)])
+def test_cta_pair_gemm_with_odd_tile_count(ops, M, N, K):
+    """Plain GEMMs at K >= 768 run as CTA pairs (cta_group::2): an odd number of 128-row tiles is rounded up to whole pairs (the
+    extra tile loads zeros and stores nothing), M tails are clipped; bias + residual, GELU + pre-activation copy and the
+    unmapped generic epilogue (N not a multiple of 32).  tcgen05 vs the SIMT engine vs fp64."""
+    torch.manual_seed(11)
+    bf = torch.bfloat16
+    a = torch.randn(M, K, device=DEV).to(bf)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(bf)
+    b = torch.randn(N, device=DEV)
+    r = torch.randn(M, N, device=DEV).to(bf)
+    guard = torch.full((256, N), 7.0, device=DEV).to(bf)      # rows past M must stay untouched
+
+    def resid():
+        y = torch.cat([torch.empty(M, N, dtype=bf, device=DEV), guard])
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y[:M], bias=b, R=r), M, N, K, torch.device(DEV))
+        assert torch.equal(y[M:], guard)
+        return y[:M].float()
+    t, s_ = run_both(ops, resid)
+    ref = a.double() @ w.double().t() + b.double() + r.double()
+    assert relmax(t, ref) < 1.5e-2 and relmax(s_, ref) < 1.5e-2 and relmax(t, s_) < 1.5e-2
+
+    def act():
+        y = torch.empty(M, N, dtype=bf, device=DEV)
+        pre = torch.empty(M, N, dtype=bf, device=DEV)
+        ops.gemm(ops.operand(a), ops.operand(w), ops.epilogue(y, Cpre=pre, bias=b, act=1), M, N, K, torch.device(DEV))
+        return torch.stack([y.float(), pre.float()])
+    t, s_ = run_both(ops, act)
+    pre = (a.double() @ w.double().t() + b.double())
+    assert relmax(t[1], pre) < 1.5e-2 and relmax(t[0], s_[0]) < 3e-2
