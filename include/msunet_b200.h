@@ -137,7 +137,10 @@ int msu_ln_param_reduce(const float* partial, int32_t partial_rows, int32_t C, f
  * geo = {H, W, Ph, Pw, shift_h, shift_w}: the -100 shift mask is derived from the window index.
  * Replaces TV:models/swin_transformer.py:181-214. */
 int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
-                    const int32_t* geo, float p_drop, const uint32_t* seed, void* stream);
+                    const int32_t* geo, float p_drop, const uint32_t* seed, float* lse, void* stream);
+/* `lse` (optional, fp32 [n_windows * 49, nH]): the log2-domain log-sum-exp of every softmax row, log2(sum_j 2^(l_j)) with
+ * l_j = log2(e) * (q.k / sqrt(32) + bias + mask).  Handed to msu_winattn_bwd it lets the backward form P = 2^(l - lse) directly:
+ * no row maximum, no row sum, no normalisation (a quarter of the instructions of its softmax part). */
 /* Attention dropout (TV:...:205): p_drop > 0 with `seed` = device pointer to two 32-bit words drops softmax outputs with a
  * counter-based mask (hash of window, head, query, key and the seed; kept values scaled by 1/(1-p)); the backward must get the
  * same p_drop and seed words.  p_drop = 0 or seed = NULL: no dropout. */
@@ -148,7 +151,7 @@ int msu_set_attn_backend(int backend);
 int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH);
 int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
                     float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
-                    const uint32_t* seed, void* stream);
+                    const uint32_t* seed, const float* lse, void* stream);   /* lse: the forward's, or NULL (recomputed) */
 /* bias[h,i,j] = table[index(i,j), h]  (TV:...:49-56) and its deterministic transpose-reduction. */
 int msu_relbias_expand(const float* table, float* bias, int32_t nH, void* stream);
 int msu_relbias_reduce(const float* dbias_partial, int32_t grid, int32_t nH, float* dtable, int accumulate,

@@ -79,7 +79,8 @@ __device__ __forceinline__ void store_row(T* dst, const float* reg, float scale)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(AW * 32) winattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ bias,
-                                                             T* __restrict__ O, int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
+                                                             T* __restrict__ O, int64_t n_windows, int nH, WinGeo g, AttnDrop ad,
+                                                             float* __restrict__ lse) {
     extern __shared__ __align__(16) float smem[];
     float* sbias = smem;                                   // [49*49]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(AW * 32) winattn_fwd_kernel(const T* __restric
                 if (ad.thr == 0 || attn_drop_keep(rowkey, j, ds0, ds1, ad.thr)) axpy_row(o, p, sV + j * HD);
             }
             if (act) store_row<T>(O + (win * WT + i) * (int64_t)C + h * HD, o, ad.inv_keep / sum);
+            if (act && lse != nullptr) lse[(win * WT + i) * nH + h] = (mx + logf(sum)) * 1.4426950408889634f;   // log2 domain
         }
         __syncwarp();
     }
@@ -303,10 +305,11 @@ static int attn_grid(int64_t n_windows, int nH) {
 }  // namespace msu
 
 namespace msu {
-int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st);
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad,
+                   float* lse, cudaStream_t st);
 int winattn_bwd_tc_grid(int64_t n_windows, int nH);
 int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
-                   int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st);
+                   int nH, const WinGeo& g, const AttnDrop& ad, const float* lse, cudaStream_t st);
 static int g_attn_backend = 0;  // 0 auto (tcgen05 for bf16), 1 force the SIMT kernels
 }
 
@@ -315,7 +318,7 @@ using namespace msu;
 extern "C" int msu_set_attn_backend(int backend) { g_attn_backend = backend; return 0; }
 
 extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int64_t n_windows, int32_t nH,
-                               const int32_t* geo, float p_drop, const uint32_t* seed, void* stream) {
+                               const int32_t* geo, float p_drop, const uint32_t* seed, float* lse, void* stream) {
     MSU_REQUIRE(qkv && bias && O && geo, "msu_winattn_fwd: null pointer");
     MSU_REQUIRE(nH > 0 && nH <= 65535, "msu_winattn_fwd: bad head count %d", nH);
     MSU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "msu_winattn_fwd: bad dropout probability %f", (double)p_drop);
@@ -325,17 +328,17 @@ extern "C" int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, vo
     dim3 grid(attn_grid(n_windows, nH), nH);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MSU_BF16 && g_attn_backend == 0) {
-        const int rc = winattn_fwd_tc(qkv, bias, O, n_windows, nH, g, ad, st);
+        const int rc = winattn_fwd_tc(qkv, bias, O, n_windows, nH, g, ad, lse, st);
         if (rc != 1) return rc;
     }
     if (dtype == MSU_F32) {
         static PerDeviceOnce attr;
         if (attr.need()) { cudaFuncSetAttribute(winattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr.set(); }
-        winattn_fwd_kernel<float><<<grid, AW * 32, FWD_SMEM, st>>>((const float*)qkv, bias, (float*)O, n_windows, nH, g, ad);
+        winattn_fwd_kernel<float><<<grid, AW * 32, FWD_SMEM, st>>>((const float*)qkv, bias, (float*)O, n_windows, nH, g, ad, lse);
     } else if (dtype == MSU_BF16) {
         static PerDeviceOnce attr;
         if (attr.need()) { cudaFuncSetAttribute(winattn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); attr.set(); }
-        winattn_fwd_kernel<__nv_bfloat16><<<grid, AW * 32, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)O, n_windows, nH, g, ad);
+        winattn_fwd_kernel<__nv_bfloat16><<<grid, AW * 32, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)O, n_windows, nH, g, ad, lse);
     } else {
         MSU_REQUIRE(false, "msu_winattn_fwd: unsupported dtype %d", dtype);
     }
@@ -351,7 +354,7 @@ extern "C" int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH) {
 // O (the forward output) supplies delta_i = dO_i . O_i without a second P.V product.
 extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
                                float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
-                               const uint32_t* seed, void* stream) {
+                               const uint32_t* seed, const float* lse, void* stream) {
     MSU_REQUIRE(qkv && bias && O && dO && dqkv && dbias_partial && geo, "msu_winattn_bwd: null pointer");
     MSU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "msu_winattn_bwd: bad dropout probability %f", (double)p_drop);
     WinGeo g = make_wingeo(geo);
@@ -360,7 +363,7 @@ extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, co
     dim3 grid(gx, nH);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MSU_BF16 && g_attn_backend == 0) {
-        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, ad, st);
+        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, ad, lse, st);
         if (rc != 1) return rc;
         MSU_REQUIRE(false, "msu_winattn_bwd: tcgen05 path unavailable for these pointers (workspace was sized for it)");
     }

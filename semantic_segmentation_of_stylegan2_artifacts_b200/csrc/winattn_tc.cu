@@ -116,7 +116,7 @@ constexpr int AT_SMEM = AT_P_BYTES + 2 * AT_OPS_BYTES + AT_BIAS_BYTES + 64 + 102
 __global__ void __launch_bounds__(128, 3)
 winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm4,
                       const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
-                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad) {
+                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad, float* __restrict__ lse) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sP = smem;
@@ -249,6 +249,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
             }
             const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             inv = __fdividef(ad.inv_keep, sum);
+            if (lse != nullptr) {      // log2-domain log-sum-exp of the row: the backward forms P = 2^(l - lse) from it
+                float lg;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
+                lse[(win * WT + i) * nH + h] = mx + lg;
+            }
             if (ad.thr) {   // attention dropout: dropped probabilities leave the P tile (the row sum above is the undropped one)
                 const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
 #pragma unroll
@@ -343,7 +348,8 @@ static bool make_pair_map(CUtensorMap* tm, const void* ptr, int64_t n_windows, i
 }
 
 // returns 0 launched, 1 unsupported
-int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st) {
+int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad,
+                   float* lse, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15)) return 1;
@@ -369,7 +375,7 @@ int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_window
     const int gx = (int)imax(1, imin(pairs, ((int64_t)num_sms() * 3) / nH));
     dim3 grid(gx, nH);
     {
-        const cudaError_t e = launch_pdl<2>(winattn_fwd_tc_kernel, grid, dim3(128), (size_t)AT_SMEM, st, 1, tm, tm4, tmO, bias, n_windows, nH, g, ad);
+        const cudaError_t e = launch_pdl<2>(winattn_fwd_tc_kernel, grid, dim3(128), (size_t)AT_SMEM, st, 1, tm, tm4, tmO, bias, n_windows, nH, g, ad, lse);
         if (e != cudaSuccess) { set_error("winattn_fwd_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     count_launch();
@@ -425,7 +431,7 @@ template <int PART>
 __device__ __forceinline__ void winattn_bwd_rows(uint32_t trow, const float* __restrict__ brow_base, bool row_ok, const MaskInfoTc& mi,
                                                  int i, int row, int wq, float* xch, const AttnDrop& ad, uint32_t rowkey,
                                                  uint32_t ds0, uint32_t ds1, float (&acc)[25], uint8_t* prow, uint8_t* srow,
-                                                 uint64_t* tile_free, uint32_t tile_parity, bool tile_wait) {
+                                                 uint64_t* tile_free, uint32_t tile_parity, bool tile_wait, bool have_lse, float lse_row) {
     constexpr int KB = PART == 0 ? 0 : AB_KSPLIT;           // first key of this part
     constexpr int NK = PART == 0 ? AB_KSPLIT : WT - AB_KSPLIT;   // 24 / 25 keys
     float s[32], dp[32];
@@ -463,14 +469,21 @@ __device__ __forceinline__ void winattn_bwd_rows(uint32_t trow, const float* __r
             for (int j = 0; j < NK; j++)
                 if (!((allowed >> j) & 1ull)) s[j] += -100.0f * LOG2E;
         }
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (!have_lse) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < NK; j++) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
-        mpart = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            for (int j = 0; j < NK; j++) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+            mpart = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
     }
-    x_max[PART * 128 + row] = mpart;
-    pair_sync(wq);
-    const float mx = fmaxf(mpart, x_max[(PART ^ 1) * 128 + row]);
+    // with the forward's log-sum-exp the probabilities come out normalised (P = 2^(l - lse)): no row maximum, no row sum, one
+    // exchange (sum_j P dP) instead of two
+    float mx = lse_row;
+    if (!have_lse) {
+        x_max[PART * 128 + row] = mpart;
+        pair_sync(wq);
+        mx = fmaxf(mpart, x_max[(PART ^ 1) * 128 + row]);
+    }
     float spart = 0.f, dpart = 0.f;
     if (row_ok) {
         if (ad.thr) {   // attention dropout: dP = m * dP~ with the forward's mask m in {0, 1/keep}
@@ -491,7 +504,7 @@ __device__ __forceinline__ void winattn_bwd_rows(uint32_t trow, const float* __r
         spart = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         dpart = (d4[0] + d4[1]) + (d4[2] + d4[3]);
     }
-    x_sum[PART * 128 + row] = spart;
+    if (!have_lse) x_sum[PART * 128 + row] = spart;
     x_dot[PART * 128 + row] = dpart;
     pair_sync(wq);
     uint32_t pk[16], dk_[16];
@@ -499,11 +512,13 @@ __device__ __forceinline__ void winattn_bwd_rows(uint32_t trow, const float* __r
     for (int j = 0; j < 16; j++) { pk[j] = 0u; dk_[j] = 0u; }
     if (row_ok) {
         // both threads of the row add the two partial sums in the same order: identical inv / delta
-        const float sum = x_sum[row] + x_sum[128 + row];
-        const float inv = __fdividef(1.0f, sum);
-        const float delta = (x_dot[row] + x_dot[128 + row]) * inv;
+        float delta = x_dot[row] + x_dot[128 + row];
+        if (!have_lse) {
+            const float inv = __fdividef(1.0f, x_sum[row] + x_sum[128 + row]);
+            delta *= inv;
 #pragma unroll
-        for (int j = 0; j < NK; j++) s[j] *= inv;                      // P
+            for (int j = 0; j < NK; j++) s[j] *= inv;                  // P
+        }
         if (!ad.thr) {
 #pragma unroll
             for (int j = 0; j < NK; j += 2) pk[j >> 1] = pk2(s[j], (j + 1 < NK) ? s[j + 1] : 0.f);
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmQKV4, const __grid_constant__ CUtensorMap tmDO3,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
-                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad, long long* trace) {
+                      int64_t n_windows, int nH, WinGeo g, AttnDrop ad, const float* __restrict__ lse, long long* trace) {
 #ifdef MSU_ATT_TRACE_BUILD   // phase timeline (debug builds only), first 8 units of CTAs with blockIdx.y == 0: [cta][unit][16 events]
 #define AB_TRACE(ev) do { if (trace != nullptr && lane == 0 && blockIdx.y == 0 && n < 8) trace[((size_t)blockIdx.x * 8 + n) * 16 + (ev)] = clock64(); } while (0)
 #else
@@ -625,15 +640,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             const uint32_t rowkey = (uint32_t)((win * nH + h) * WT + i);
             uint8_t* sXP = sTiles + b * 2 * AB_X;
             uint8_t* sXS = sXP + AB_X;
+            const bool have_lse = lse != nullptr;
+            const float lse_row = (have_lse && row_ok) ? lse[(win * WT + i) * nH + h] : 0.f;
             if (warp == 0) AB_TRACE(0);
             mbar_wait(&s_ready[b], par);
             tc_fence_after();
             if (warp == 0) AB_TRACE(1);
             const uint32_t trow = tmem + b * 256 + ((uint32_t)(wq * 32) << 16) + half * 64;
             if (part == 0) winattn_bwd_rows<0>(trow, brow, row_ok, mi, i, row, wq, sXch, ad, rowkey, ds0, ds1, acc, sXP + row * 128, sXS + row * 128,
-                                               &tile_free[b], par ^ 1u, n >= 2);
+                                               &tile_free[b], par ^ 1u, n >= 2, have_lse, lse_row);
             else winattn_bwd_rows<1>(trow, brow, row_ok, mi, i, row, wq, sXch, ad, rowkey, ds0, ds1, acc, sXP + row * 128, sXS + row * 128,
-                                     &tile_free[b], par ^ 1u, n >= 2);
+                                     &tile_free[b], par ^ 1u, n >= 2, have_lse, lse_row);
             fence_proxy_async_smem();               // tile rows (generic proxy) -> visible to the MMAs (async proxy)
             tc_fence_before();
             __syncwarp();
@@ -802,7 +819,7 @@ int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
 
 // returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
 int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
-                   int nH, const WinGeo& g, const AttnDrop& ad, cudaStream_t st) {
+                   int nH, const WinGeo& g, const AttnDrop& ad, const float* lse, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15)) return 1;
@@ -829,7 +846,7 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
 #endif
     {
         const cudaError_t e = launch_pdl<2>(winattn_bwd_tc_kernel, grid, dim3(AB_THREADS), (size_t)AB_SMEM, st, 1, tmQKV, tmDO, tmQKV4, tmDO3, tmOut,
-                                         bias, dbias_partial, n_windows, nH, g, ad, trace_buf);
+                                         bias, dbias_partial, n_windows, nH, g, ad, lse, trace_buf);
         if (e != cudaSuccess) { set_error("winattn_bwd_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
 #ifdef MSU_ATT_TRACE_BUILD

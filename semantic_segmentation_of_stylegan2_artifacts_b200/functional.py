@@ -263,7 +263,7 @@ class SwinBlockFn(Function):
         qkv = torch.empty(Tw, 3 * Cd, dtype=dt, device=dev)
         gemm(operand(xw), w_fwd(qkvw, dt), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
         bias = ops.relbias_expand(table, nH)
-        o = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed)
+        o, lse = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed, want_lse=True)
         # proj + window reverse + un-roll + crop + stochastic depth + residual in the GEMM epilogue
         x1 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(o), w_fwd(projw, dt),
@@ -277,7 +277,7 @@ class SwinBlockFn(Function):
         x2 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(a), w_fwd(f2w, dt), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
         ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
-                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b)
+                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b, lse)
         ctx.cfg = (B, H, W, nH, geo, nW)
         ctx.drop = (attn_p, drop_seed)
         return x2.view(B, H, W, Cd)
@@ -286,7 +286,7 @@ class SwinBlockFn(Function):
     @once_differentiable
     def backward(ctx, dx2):
         (x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
-         xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b) = ctx.saved_tensors
+         xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b, lse) = ctx.saved_tensors
         B, H, W, nH, geo, nW = ctx.cfg
         dev, dt = x.device, x.dtype
         Cd = x.shape[-1]
@@ -327,7 +327,7 @@ class SwinBlockFn(Function):
             wg.run(lambda: gemm(dy1t, operand(o, orient=1), epilogue(dWp, out_f32=True, colsum=dbp), Cd, Cd, Tw, dev))
             do = torch.empty(Tw, Cd, dtype=dt, device=dev)
             gemm(dy1, w_dgrad(projw, dt), epilogue(do), Tw, Cd, Cd, dev)
-            dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo, *ctx.drop, table=table)
+            dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, B * nW, nH, geo, *ctx.drop, table=table, lse=lse)
             dbqkv, dWqkv = ops.grad_out(qkvb), ops.grad_out(qkvw)
             wg.run(lambda: gemm(operand(dqkv, orient=1), operand(xw, orient=1), epilogue(dWqkv, out_f32=True, colsum=dbqkv),
                                 3 * Cd, Cd, Tw, dev))

@@ -316,20 +316,23 @@ def relbias_expand(table: torch.Tensor, nH: int) -> torch.Tensor:
 
 
 def winattn_fwd(qkv: torch.Tensor, bias: torch.Tensor, n_windows: int, nH: int, geo, p_drop: float = 0.0,
-                seed: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """`seed`: int32[2] device tensor (two 32-bit words of the dropout counter hash); the backward needs the same."""
+                seed: Optional[torch.Tensor] = None, want_lse: bool = False):
+    """`seed`: int32[2] device tensor (two 32-bit words of the dropout counter hash); the backward needs the same.
+    `want_lse`: also return the rows' log2-domain log-sum-exp [n_windows * 49, nH] fp32 for `winattn_bwd(lse=...)`."""
     o = torch.empty(n_windows * 49, nH * 32, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(n_windows * 49, nH, dtype=torch.float32, device=qkv.device) if want_lse else None
     g = L.geo6(geo)
     e0 = _p0()
     L.check(L.lib().msu_winattn_fwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), n_windows, nH,
-                                    C.cast(g, C.c_void_p), float(p_drop), L.ptr(seed), L.stream_ptr()), "msu_winattn_fwd")
+                                    C.cast(g, C.c_void_p), float(p_drop), L.ptr(seed), L.ptr(lse), L.stream_ptr()), "msu_winattn_fwd")
     _p1(e0, (n_windows, nH, 0, "winattn_fwd"), (qkv.numel() + o.numel()) * qkv.element_size(),
         2 * 2 * n_windows * nH * 49 * 49 * 32)
-    return o
+    return (o, lse) if want_lse else o
 
 
-def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 0.0, seed=None, table=None):
-    """Returns (dqkv, dtable[169, nH]).  `table`: the bias-table parameter (its gradient slot is used when one is registered)."""
+def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 0.0, seed=None, table=None, lse=None):
+    """Returns (dqkv, dtable[169, nH]).  `table`: the bias-table parameter (its gradient slot is used when one is registered);
+    `lse`: the forward's log-sum-exp (`winattn_fwd(want_lse=True)`), or None (the kernel recomputes the row statistics)."""
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
     gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
@@ -338,7 +341,7 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 
     e0 = _p0()
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
                                     dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p), float(p_drop),
-                                    L.ptr(seed), L.stream_ptr()), "msu_winattn_bwd")
+                                    L.ptr(seed), L.ptr(lse), L.stream_ptr()), "msu_winattn_bwd")
     dtable = grad_out(table, (169, nH)) if table is not None else torch.empty(169, nH, dtype=torch.float32, device=dev)
     _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
                               "msu_relbias_reduce"), part)

@@ -389,6 +389,19 @@ def test_window_attention_bwd_tcgen05(ops, geom):
     assert rl2(res["tc"][0], x.grad) < 1.2e-2, rl2(res["tc"][0], x.grad)
     assert rl2(res["tc"][1], tb.grad) < 6e-3, rl2(res["tc"][1], tb.grad)
     assert relmax(res["tc"][0], x.grad) < 4e-2
+    # the training path: the forward hands its rows' log-sum-exp to the backward (P = 2^(l - lse): no row maximum / sum there)
+    o_l, lse = ops.winattn_fwd(qkv, bias, nwin, nH, geo, want_lse=True)
+    lref = torch.logsumexp(att.detach(), -1).permute(0, 1, 3, 2).reshape(nwin * 49, nH) * 1.4426950408889634   # [rows, nH], log2
+    assert float((lse.double().cpu() - lref).abs().max()) < 2e-2
+    dq3, dt3 = ops.winattn_bwd(qkv, bias, o_l, do, nwin, nH, geo, lse=lse)
+    assert rl2(dq3.float().cpu(), x.grad) < 1.2e-2 and rl2(dt3.cpu(), tb.grad) < 6e-3
+    assert relmax(dq3.float().cpu(), x.grad) < 4e-2
+    lib.msu_set_attn_backend(1)                # the fp32-FMA kernels write the same statistic
+    try:
+        _, lse_s = ops.winattn_fwd(qkv, bias, nwin, nH, geo, want_lse=True)
+    finally:
+        lib.msu_set_attn_backend(0)
+    assert float((lse_s.double().cpu() - lref).abs().max()) < 2e-2
 
 
 def test_gelu_grad_epilogue(ops):

@@ -26,9 +26,10 @@ for k in range(4):
     qkv = (torch.randn(nW * 49, 3 * C, device=dev) * 0.5).to(bf)
     bias = ops.relbias_expand(torch.randn(169, nH, device=dev) * 0.1, nH)
     do = torch.randn(nW * 49, C, device=dev).to(bf)
-    o = ops.winattn_fwd(qkv, bias, nW, nH, geo)
-    fns = {"fwd": (lambda: ops.winattn_fwd(qkv, bias, nW, nH, geo), (qkv.numel() + o.numel()) * 2),
-           "bwd": (lambda: ops.winattn_bwd(qkv, bias, o, do, nW, nH, geo), (2 * qkv.numel() + do.numel()) * 2)}
+    o, lse = ops.winattn_fwd(qkv, bias, nW, nH, geo, want_lse=True)
+    use_lse = os.environ.get("LSE", "1") != "0"      # the training path hands the forward's log-sum-exp to the backward
+    fns = {"fwd": (lambda: ops.winattn_fwd(qkv, bias, nW, nH, geo, want_lse=True), (qkv.numel() + o.numel()) * 2),
+           "bwd": (lambda: ops.winattn_bwd(qkv, bias, o, do, nW, nH, geo, lse=lse if use_lse else None), (2 * qkv.numel() + do.numel()) * 2)}
     for name, (fn, byts) in fns.items():
         for _ in range(2):
             fn()
