@@ -245,6 +245,12 @@ int msu_refresh_shadows(const MsuShadowJob* jobs, const int32_t* blk_job, const 
 int msu_stage_u8(const uint8_t* img_hwc, const uint8_t* label, const uint8_t* flip, float* image_out, float* label_out,
                  int32_t B, int32_t H, int32_t W, void* stream);
 
+/* Weight-gradient GEMMs split the token axis over the SMs.  0 (default; MSU_DETERMINISTIC=1 in the environment flips it): every
+ * split adds its fp32 tile into the output with a TMA reduce (L2 atomics) - no workspace pass, but the order of the additions varies
+ * from run to run (as it does for cuBLAS / cuDNN split-K under the reference, which sets no torch.use_deterministic_algorithms).
+ * 1: partial tiles go to the workspace and a second kernel adds them in a fixed order (bit-reproducible gradients).
+ * Returns the previous setting. */
+int msu_set_deterministic(int on);
 int msu_version(void);
 /* sizeof(MsuOperand) (which=0) / sizeof(MsuEpilogue) (which=1): lets a binding verify its struct layout. */
 int msu_struct_size(int which);

@@ -63,6 +63,7 @@ _SIGS = {
     "msu_ln_param_reduce": [_P, _I32, _I32, _P, _P, _P, C.c_int, _P],
     "msu_winattn_fwd": [C.c_int, _P, _P, _P, _I64, _I32, _P, C.c_float, _P, _P, _P],
     "msu_set_attn_backend": [C.c_int],
+    "msu_set_deterministic": [C.c_int],
     "msu_winattn_bwd_grid": [C.c_int, _I64, _I32],
     "msu_winattn_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, C.c_float, _P, _P, _P],
     "msu_relbias_expand": [_P, _P, _I32, _P],

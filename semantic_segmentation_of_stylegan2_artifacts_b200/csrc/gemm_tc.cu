@@ -19,6 +19,7 @@
 // B is always a K-major [N, K] bf16 weight shadow.  K tails are zero-filled by TMA (out-of-bounds).
 // Every output map / fused epilogue of MsuEpilogue is honoured (each epilogue thread owns one output row).
 #include <stdio.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -1209,6 +1210,12 @@ struct WgParams {
     int stages, qboxes;
     float* ws;
     float* bws;         // bias-gradient partials [split][Pn] (column sums of the M-side operand), or nullptr
+    // red = 1: no workspace, no reduce kernel.  The output [I, J] fp32 (zeroed by the host unless it accumulates) takes every
+    // split's tile as a TMA reduce-add (L2 atomics; the order of the fp32 additions is then not fixed) and the bias partials
+    // as red.global.add; the per-sample scale of the token rows is applied to the split's tile in registers.
+    int red, sps;
+    const float* sscale;
+    float* colsum;
 };
 
 constexpr int WG_BK = 64;            // tokens per stage
@@ -1247,8 +1254,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     // MMA against a tile of ones cost +20 % kernel time: MN-major MMAs are shared-memory-read bound).  Only the CTAs of the
     // first tile along the other axis do it (sharing the stages among all tiles measured slower: every CTA then pays
     // the later slot release).
-    const bool do_bias = (p.bws != nullptr) && (p.swap ? sup == 0 : qt == 0);
+    const bool do_bias = (p.bws != nullptr || (p.red && p.colsum != nullptr)) && (p.swap ? sup == 0 : qt == 0);
     constexpr int nq = 1, myq = 0;
+    const float red_scale = (p.red && p.sscale != nullptr) ? p.sscale[split / p.sps] : 1.f;
 
     if (warp == 0 && lane == 0) {
         // a stage is free when its MMAs have retired (+ when the four column-sum warps have read it)
@@ -1355,6 +1363,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
                 float2 t = comb[(0 * 8 + b) * 32 + l];
                 for (int w = 1; w < 4; w++) { const float2 u = comb[(w * 8 + b) * 32 + l]; t.x += u.x; t.y += u.y; }
                 const int c = org + b * 64 + l * 2;
+                if (p.red) {
+                    if (c < ext) atomicAdd(&p.colsum[c], t.x * red_scale);
+                    if (c + 1 < ext) atomicAdd(&p.colsum[c + 1], t.y * red_scale);
+                    continue;
+                }
                 if (c < ext) p.bws[((int64_t)split * nq + myq) * ldb + c] = t.x;
                 if (c + 1 < ext) p.bws[((int64_t)split * nq + myq) * ldb + c + 1] = t.y;
             }
@@ -1379,6 +1392,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 32; i++) raw[i] = 0u;
                 }
+                if (p.red && p.sscale != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * red_scale);
+                }
                 if (!p.swap) {          // slab[row = lane (i)][col = j]: 8 x 16 B per lane
 #pragma unroll
                     for (int g = 0; g < 8; g++)
@@ -1394,7 +1411,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (!p.swap) tma_store_3d(sl, &tmW, q0 + c * 32, prow0, split);
+                    if (p.red) {
+                        if (!p.swap) tma_red_add_3d(sl, &tmW, q0 + c * 32, prow0, 0);
+                        else tma_red_add_3d(sl, &tmW, prow0, q0 + c * 32, 0);
+                    } else if (!p.swap) tma_store_3d(sl, &tmW, q0 + c * 32, prow0, split);
                     else tma_store_3d(sl, &tmW, prow0, q0 + c * 32, split);
                     tma_store_commit();
                 }
@@ -1774,6 +1794,17 @@ static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, in
     return make_map_2d(tm, ptr, rows, cols, ld, 64);
 }
 
+static std::atomic<int> g_deterministic{-1};
+static int deterministic_mode() {
+    int v = g_deterministic.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MSU_DETERMINISTIC");
+        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+        g_deterministic.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 // returns 0 = launched, 1 = unsupported (SIMT fallback), other = error.  A(i, t) and B(j, t) both orient=1.
 int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
              float* ws, int64_t ws_elems, cudaStream_t st, int* fused_colsum) {
@@ -1853,17 +1884,30 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     splits = (int)((T + tps - 1) / tps);
     p.splits = splits; p.tok_per_split = tps;
     p.bws = want_bias ? ws + (int64_t)splits * I * J : nullptr;
+    // msu_set_deterministic(1): fp32 partials in the workspace + splitk_reduce_kernel, fixed order of additions
+    const int env_red = !deterministic_mode();
+    const int64_t ldc = E->ldc > 0 ? E->ldc : J;
+    p.red = (env_red && aligned16(E->C) && ldc % 4 == 0) ? 1 : 0;  // 16-byte rows (J % 8 == 0 already)
+    if (p.red) {
+        p.bws = nullptr;
+        p.colsum = want_bias ? E->colsum : nullptr;
+        p.sscale = A->rowscale; p.sps = sps;
+        cudaError_t e = cudaSuccess;
+        if (!E->accumulate) e = cudaMemset2DAsync(E->C, (size_t)ldc * sizeof(float), 0, (size_t)J * sizeof(float), (size_t)I, st);
+        if (e == cudaSuccess && want_bias) e = cudaMemsetAsync(E->colsum, 0, (size_t)I * sizeof(float), st);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     CUtensorMap tmP, tmQ;
     if (!make_map_2d_box64(&tmP, P->ptr, T, p.Pn, P->ld)) return 1;
     if (!make_map_2d_box64(&tmQ, Q->ptr, T, p.Qn, Q->ld)) return 1;
     // partials ws[split][I][J] fp32 as a 3-D map, box = [32 cols, 32 rows, 1], 128B swizzle
     CUtensorMap tmW;
     {
-        cuuint64_t gdim[3] = {(cuuint64_t)J, (cuuint64_t)I, (cuuint64_t)splits};
-        cuuint64_t gstr[2] = {(cuuint64_t)J * 4, (cuuint64_t)I * J * 4};
+        cuuint64_t gdim[3] = {(cuuint64_t)J, (cuuint64_t)I, (cuuint64_t)(p.red ? 1 : splits)};
+        cuuint64_t gstr[2] = {(cuuint64_t)(p.red ? ldc : J) * 4, (cuuint64_t)I * (p.red ? ldc : J) * 4};
         cuuint32_t box[3] = {32, 32, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        if (get_encode()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (get_encode()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.red ? (float*)E->C : ws, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 1;
     }
@@ -1879,9 +1923,15 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
         if (e != cudaSuccess) { set_error("wgrad_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     count_launch();
-    launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq, A->rowscale, sps);
+    if (!p.red) launch_splitk_reduce(*E, I, J, splits, ws, st, p.bws, splits * nq, A->rowscale, sps);
     if (fused_colsum) *fused_colsum = want_bias ? 1 : 0;
     return check_launch("wgrad_tc");
 }
 
 }  // namespace msu
+
+extern "C" int msu_set_deterministic(int on) {
+    const int prev = msu::deterministic_mode();
+    msu::g_deterministic.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}

@@ -59,6 +59,11 @@ __device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap*
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// TMA reduction: global[box] += shared box, element type of the tensor map (fp32), performed by the L2 atomic units
+__device__ __forceinline__ void tma_red_add_3d(const void* src, const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");

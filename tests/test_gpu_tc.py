@@ -165,17 +165,28 @@ def test_wgrad_mn_major(ops, shape):
         ops.gemm(ops.operand(dy, orient=1), ops.operand(x, orient=1), ops.epilogue(dw, out_f32=True, colsum=db), I, J, T, dy.device)
         return torch.cat([dw.flatten(), db])
 
-    tc, simt = run_both(ops, go)
     ref = dy.double().cpu().t() @ x.double().cpu()
-    assert relmax(tc, ref) < 2e-5
-    assert relmax(tc, simt) < 2e-5
-    tc2, _ = run_both(ops, go)
-    assert torch.equal(tc, tc2)  # fixed reduction order
-    tcb, simtb = run_both(ops, go_bias)
-    assert torch.equal(tcb[:I * J].view(I, J), tc)
     refb = dy.double().cpu().sum(0)
-    assert relmax(tcb[I * J:], refb) < 2e-5 and relmax(simtb[I * J:], refb) < 2e-5
-    assert torch.equal(tcb, run_both(ops, go_bias)[0])
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    lib = _lib.lib()
+    for det in (0, 1):           # 0: every split adds its tile with a TMA reduce (default); 1: workspace + fixed-order reduce kernel
+        prev = lib.msu_set_deterministic(det)
+        try:
+            tc, simt = run_both(ops, go)
+            assert relmax(tc, ref) < 2e-5
+            assert relmax(tc, simt) < 2e-5
+            tc2, _ = run_both(ops, go)
+            tcb, simtb = run_both(ops, go_bias)
+            tcb2 = run_both(ops, go_bias)[0]
+        finally:
+            lib.msu_set_deterministic(prev)
+        assert relmax(tcb[I * J:], refb) < 2e-5 and relmax(simtb[I * J:], refb) < 2e-5
+        if det:
+            assert torch.equal(tc, tc2)  # fixed reduction order
+            assert torch.equal(tcb[:I * J].view(I, J), tc)
+            assert torch.equal(tcb, tcb2)
+        else:
+            assert relmax(tc, tc2) < 1e-6 and relmax(tcb, tcb2) < 1e-6 and relmax(tcb[:I * J].view(I, J), tc) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(4, 4096, 96, 384), (3, 1024, 384, 96), (16, 256, 192, 192), (2, 16384, 96, 96)])
@@ -200,7 +211,14 @@ def test_wgrad_per_sample_rowscale(ops, shape):
     dys = dy.double().cpu() * sd.double().cpu().repeat_interleave(HW)[:, None]
     ref = torch.cat([(dys.t() @ x.double().cpu()).flatten(), dys.sum(0)])
     assert relmax(tc, ref) < 2e-5 and relmax(simt, ref) < 2e-5
-    assert torch.equal(tc, run_both(ops, go)[0])
+    assert relmax(tc, run_both(ops, go)[0]) < 1e-6
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    prev = _lib.lib().msu_set_deterministic(1)
+    try:
+        d1, d2 = run_both(ops, go)[0], run_both(ops, go)[0]
+    finally:
+        _lib.lib().msu_set_deterministic(prev)
+    assert relmax(d1, ref) < 2e-5 and torch.equal(d1, d2)
 
 
 @pytest.mark.parametrize("geom", [(2, 64, 96), (1, 128, 96), (2, 32, 32), (1, 224, 96), (1, 64, 128), (3, 48, 64)])
