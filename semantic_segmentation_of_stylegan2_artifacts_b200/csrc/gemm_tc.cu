@@ -93,6 +93,7 @@ struct TcParams {
     int epi_bytes;            // shared memory per epilogue warp
     int a_stage, b_stage;     // bytes per pipeline stage of the A / B operand rings
     long long* trace;         // debug (MSU_TC_TRACE=1): clock64 stamps [cta][tile < 8][16 events]
+    int dbg_skip;             // debug (MSU_CONV_SKIP bit mask, pair conv only): 1 no weight loads, 2 no halo loads, 4 no output stores after a CTA's first tile
     MsuEpilogue E;
 };
 #define TC_TRACE(ev) do { if (p.trace != nullptr && lane == 0 && it < 8) p.trace[((size_t)blockIdx.x * 8 + it) * 16 + (ev)] = clock64(); } while (0)
@@ -259,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
@@ -286,6 +287,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // own two halo rows + own HALF of the three weight tiles (rows [BN/2 rank, +BN/2) of each); the bytes
                             // of both CTAs are counted by the leader's barrier
                             const int hb = (p.BN / 2) * 64;
+                            if (p.box2 && p.dbg_skip != 0 && it > 0) {   // timing experiments only (MSU_CONV_SKIP): results are wrong
+                                const bool la = !(p.dbg_skip & 2), lb = !(p.dbg_skip & 1);
+                                if (leader && (la || lb)) mbar_arrive_expect_tx(&full[stage], 2 * ((la ? 2 * 130 * 64 : 0) + (lb ? 3 * hb : 0)));
+                                if (la) tma_load_4d_pair(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
+                                if (lb) tma_load_3d_pair(b_dst, &tmB, &full[stage], dyi * 3 * p.C + c0, nt * p.BN + (int)cta_rank * (p.BN / 2), 0);
+                                if (!la && !lb && leader) mbar_arrive(&full[stage]);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (2 * 130 * 64 + 3 * hb));
                             if (p.box2) {   // two boxes per K block: both halo rows, all three taps' half tiles
                                 tma_load_4d_pair(a_dst, &tmA, &full[stage], c0, cx - 1, cy + dyi - 1, cb);
@@ -362,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread; the leader CTA's in a pair) =====================
-        if (lane == 0 && leader) {
+        if (leader && elect_one()) {
             const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -623,7 +633,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (warp == 2 && first) TC_TRACE(8);
-                if (lane == 0 && E.C != nullptr) {
+                if (lane == 0 && E.C != nullptr && !((p.dbg_skip & 4) && it > 0)) {
                     if (E.map == MSU_MAP_NONE) {
                         tma_store_2d(slab_out, &tmC, n0, row0);
                         if (E.Cpre != nullptr) tma_store_2d(slab_aux, &tmAux, n0, row0);
@@ -1145,6 +1155,8 @@ int gemm_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int6
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    static const int dbg_skip = getenv("MSU_CONV_SKIP") ? atoi(getenv("MSU_CONV_SKIP")) : 0;
+    p.dbg_skip = dbg_skip;
     static const int trace_on = getenv("MSU_TC_TRACE") ? atoi(getenv("MSU_TC_TRACE")) : 0;
     static long long* trace_buf = nullptr;
     if (trace_on) {
@@ -1276,7 +1288,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < KB; kb++) {
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -1290,7 +1302,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
             // The issuing thread is the critical resource of this loop (ncu / SASS: ~21 instructions per MMA when every
@@ -1506,7 +1518,7 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < KB; kb++) {
                 const int64_t slab = s0 + kb;
@@ -1543,7 +1555,7 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
             // descriptors built once, advanced through the 14-bit address field (the issuing thread is the critical
@@ -1836,7 +1848,9 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
     // Long token axis (stage 0/1): activation reads dominate -> wide N tile and several M accumulators per CTA so
     // that each activation element is fetched once.  Short token axis with a large output (stage 2/3): many
     // output tiles, few splits -> small deterministic split-K partial traffic.
-    const bool out_heavy = (int64_t)I * J * 8 > T * (I + J);
+    // (only where the partials make a round trip through the workspace: with the TMA reduce-add the wide tiling wins everywhere,
+    //  4096 x 3072 x 768: 32 -> 24 us)
+    const bool out_heavy = deterministic_mode() && (int64_t)I * J * 8 > T * (I + J);
     if (out_heavy) {
         p.BN = p.Qn <= 128 ? (p.Qn + 15) / 16 * 16 : pick_bn(p.Qn, 128, 32);   // several q tiles: whole 32-column store boxes
         p.MT = 1;

@@ -59,6 +59,14 @@ __device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap*
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// One lane of a converged warp (elect.sync).  Unlike `lane == 0`, ptxas knows the guarded region runs in exactly one thread, so the
+// instructions that take uniform-register operands (UTCHMMA descriptors, UTMALDG coordinates) are emitted directly instead of
+// inside a per-active-lane ELECT / R2UR.BROADCAST / BRA.U.ANY loop (8 dependent instructions per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // TMA reduction: global[box] += shared box, element type of the tensor map (fp32), performed by the L2 atomic units
 __device__ __forceinline__ void tma_red_add_3d(const void* src, const CUtensorMap* tm, int c0, int c1, int c2) {
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),

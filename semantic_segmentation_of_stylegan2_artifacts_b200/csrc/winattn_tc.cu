@@ -185,7 +185,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         uint8_t* sQ = sOps + buf * AT_OPS_BYTES;
         uint8_t* sK = sQ + 8192;
         uint8_t* sV = sQ + 16384;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // == thread 0 (the warp is converged here); elect: see tc_common.cuh
             mbar_wait(&bar_load[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint64_t qd = make_desc_kmajor_sw64(smem_u32(sQ)), kd = make_desc_kmajor_sw64(smem_u32(sK));
@@ -277,7 +277,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();   // all S rows are read (MMA 2 overwrites columns 0..63) and all P rows are written
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
@@ -318,7 +318,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();   // TMEM columns are free for the next unit; the staged rows are complete
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tma_store_3d(sP, &tmO, h * HD, 0, (int)(pair * 2));      // a window index past the end (odd count) is clipped by TMA
             tma_store_commit();
         }
@@ -739,7 +739,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             }
         }
         if (is_tma) tma_store_wait_all();
-    } else if (lane == 0) {
+    } else if (elect_one()) {
         // ===================== MMA issuer (one thread) =====================
         const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
         const uint32_t id_kv = make_idesc_bf16(128, 64, 1, 1);     // dV, dK: A MN-major, B MN-major (both windows' columns)

@@ -105,7 +105,89 @@ __global__ void __launch_bounds__(128, 1) k3(int N, int iters, long long* out) {
     }
 }
 
-int main() {
+// The conv kernel's K block (mode 4): operands as 32-channel chunks = 64 B rows, SWIZZLE_64B; 12 MMAs = 2 image rows x 3 pixel
+// shifts (+64 B on the A start address) x 2 K halves (+32 B), accumulators r * 128.  variant 0: that pattern; 1: the same MMAs
+// with an unshifted A start (dx = 0 always); 2: SWIZZLE_128B descriptors over the same bytes (rate reference).
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+template <int VAR>
+__global__ void __launch_bounds__(128, 1) kconv(int N, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+        const uint64_t ad = VAR == 2 ? make_desc_kmajor_sw128(a0) : desc_kmajor_sw64(a0);
+        const uint64_t bd = VAR == 2 ? make_desc_kmajor_sw128(b0) : desc_kmajor_sw64(b0);
+        const uint32_t bstep = (uint32_t)(N * 4), rstep = 8704 >> 4;
+        long long t0 = clock64();
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const uint64_t ar = ad + (uint64_t)(r * rstep);
+                const uint32_t d = tmem + r * 128;
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const uint64_t a_ = VAR == 0 ? ar + 4 * dx : ar;
+                    tc_mma_bf16(d, a_, bd + dx * bstep, idesc, 1);
+                    tc_mma_bf16(d, a_ + 2, bd + dx * bstep + 2, idesc, 1);
+                }
+            }
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) {          // conv K-block pattern only
+        long long* d;
+        cudaMalloc(&d, 8);
+        const int iters = 2000;
+        for (int N : {48, 96, 128}) {
+            for (int v = 0; v < 3; v++) {
+                auto kern = v == 0 ? kconv<0> : v == 1 ? kconv<1> : kconv<2>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                kern<<<148, 128, 100 * 1024>>>(N, iters, d);
+                long long h = 0;
+                cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+                cudaError_t e = cudaGetLastError();
+                printf("conv K block, N=%3d, %s : %7.1f clk/MMA  (MMA ideal %5.1f)  %s\n", N,
+                       v == 0 ? "64B swizzle, shifted A starts" : v == 1 ? "64B swizzle, unshifted       " : "128B swizzle descriptors     ",
+                       (double)h / (iters * 12), 128.0 * N * 16 * 2 / 8192, e == cudaSuccess ? "" : cudaGetErrorString(e));
+            }
+        }
+        return 0;
+    }
     long long* d;
     cudaMalloc(&d, 8);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
