@@ -81,6 +81,28 @@ def conv(B, S, E):
                              B * S * S, E, 9 * E, dev), 2 * B * S * S * E * 9 * E, 2 * B * S * S * E * 2)
 
 
+def conv_ep(B, S, E, kind):
+    """the head's other conv launches: fwd = bias + GELU with a second output (act 1: pre-activation, act 2: GELU'),
+    dgrad = x GELU'(H) (act 0: computed from the pre-activation, act 3: H holds the derivative), dgrad_un = the same through the
+    inverse depth-to-space store"""
+    x = torch.randn(B * S * S, E, device=dev).to(bf)
+    w = (torch.randn(E, 9 * E, device=dev) * 0.05).to(bf)
+    b = torch.randn(E, device=dev)
+    y = torch.empty(B * S * S, E, dtype=bf, device=dev)
+    aux = torch.randn(B * S * S, E, device=dev).to(bf)
+    A = ops.operand(x, ld=E, map=ops.MAP_CONV3, geo=[S, S, E])
+    M = B * S * S
+    if kind.startswith("fwd"):
+        ep = lambda: ops.epilogue(y, Cpre=aux, bias=b, act=int(kind[-1]))
+    elif kind.startswith("dgrad_un"):
+        r = S // 4
+        y = torch.empty(B * r * r, 16 * E, dtype=bf, device=dev)
+        ep = lambda: ops.epilogue(y, ldc=16 * E, H=aux, ldh=E, act=int(kind[-1]), map=ops.MAP_UNSHUFFLE, geo=[r, r, 4, E])
+    else:
+        ep = lambda: ops.epilogue(y, H=aux, ldh=E, act=int(kind[-1]))
+    return (lambda: ops.gemm(A, ops.operand(w), ep(), M, E, 9 * E, dev), 2 * M * E * 9 * E, 3 * M * E * 2)
+
+
 def conv_lnd(B, S, E):
     """second head conv with the LayerNorm + 1x1 conv fused into its epilogue (MsuEpilogue.lnd_*)"""
     x = torch.randn(B * S * S, E, device=dev).to(bf)
@@ -127,6 +149,9 @@ cases = {
     "dh_s2": lambda: dgelu(16384, 1536, 384), "fc2_s2": lambda: resid(16384, 384, 1536),
     "dxn_s2": lambda: plain(16384, 384, 1536), "qkv_s2": lambda: plain(19600, 1152, 384),
     "proj_s2": lambda: plain(19600, 384, 384), "fc1_s3": lambda: fc1(4096, 3072, 768),
+    "convfwd1_b16": lambda: conv_ep(16, 512, 96, "fwd1"), "convfwd2_b16": lambda: conv_ep(16, 512, 96, "fwd2"),
+    "convdgrad0_b16": lambda: conv_ep(16, 512, 96, "dgrad0"), "convdgrad3_b16": lambda: conv_ep(16, 512, 96, "dgrad3"),
+    "convdgrad_un0_b16": lambda: conv_ep(16, 512, 96, "dgrad_un0"), "convdgrad_un3_b16": lambda: conv_ep(16, 512, 96, "dgrad_un3"),
     "plain_big": lambda: plain(8192, 4096, 4096), "conv_b16": lambda: conv(16, 512, 96), "convlnd_b16": lambda: conv_lnd(16, 512, 96),
 }
 for name, mk in cases.items():
