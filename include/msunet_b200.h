@@ -147,10 +147,14 @@ int msu_winattn_fwd(int dtype, const void* qkv, const float* bias, void* O, int6
 /* 0 = auto (tcgen05 kernels for bf16), 1 = force the SIMT fp32-FMA kernels (parity checks of the tensor-core path). */
 int msu_set_attn_backend(int backend);
 /* Backward (recomputes P from qkv; O is the forward output): dqkv [.,3C];
- * dbias_partial fp32 [msu_winattn_bwd_grid(dtype,n_windows,nH), nH, 2401], reduced by msu_relbias_reduce. */
+ * dbias_partial fp32 [msu_winattn_bwd_grid(dtype,n_windows,nH), nH, 2401], reduced by msu_relbias_reduce.
+ * When msu_winattn_bwd_direct(dtype) returns 1 (tcgen05 backend, not msu_set_deterministic(1)) the caller may instead pass
+ * `dtable` = the bias-table gradient [169, nH] fp32 itself, zeroed (or holding a gradient to add to): the kernel adds every CTA's
+ * contribution with red.global.add, dbias_partial may be NULL and no msu_relbias_reduce is needed.  Otherwise dtable must be NULL. */
+int msu_winattn_bwd_direct(int dtype);
 int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH);
 int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
-                    float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
+                    float* dbias_partial, float* dtable, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
                     const uint32_t* seed, const float* lse, void* stream);   /* lse: the forward's, or NULL (recomputed) */
 /* bias[h,i,j] = table[index(i,j), h]  (TV:...:49-56) and its deterministic transpose-reduction. */
 int msu_relbias_expand(const float* table, float* bias, int32_t nH, void* stream);

@@ -65,7 +65,8 @@ _SIGS = {
     "msu_set_attn_backend": [C.c_int],
     "msu_set_deterministic": [C.c_int],
     "msu_winattn_bwd_grid": [C.c_int, _I64, _I32],
-    "msu_winattn_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, C.c_float, _P, _P, _P],
+    "msu_winattn_bwd_direct": [C.c_int],
+    "msu_winattn_bwd": [C.c_int, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, C.c_float, _P, _P, _P],
     "msu_relbias_expand": [_P, _P, _I32, _P],
     "msu_relbias_reduce": [_P, _I32, _I32, _P, C.c_int, _P],
     "msu_prep_weight": [C.c_int, C.c_int, _P, _P, _I64, _I64, _P],

@@ -18,6 +18,17 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int> g_deterministic{-1};
+int deterministic_mode() {
+    int v = g_deterministic.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MSU_DETERMINISTIC");
+        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+        g_deterministic.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+void set_deterministic_mode(int on) { g_deterministic.store(on ? 1 : 0, std::memory_order_relaxed); }
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -75,4 +86,9 @@ extern "C" int msu_version(void) { return 100; }
 extern "C" int msu_struct_size(int which) { return which == 0 ? (int)sizeof(MsuOperand) : (int)sizeof(MsuEpilogue); }
 extern "C" const char* msu_last_error_string(void) { return g_err; }
 extern "C" long long msu_launch_count(void) { return g_launches.load(); }
+extern "C" int msu_set_deterministic(int on) {
+    const int prev = msu::deterministic_mode();
+    msu::set_deterministic_mode(on);
+    return prev;
+}
 extern "C" int msu_last_gemm_backend(void) { return g_last_backend; }

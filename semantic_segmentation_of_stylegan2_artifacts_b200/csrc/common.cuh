@@ -14,6 +14,7 @@ namespace msu {
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int deterministic_mode();        // msu_set_deterministic / MSU_DETERMINISTIC: 1 = fixed-order reductions only (no atomics)
 int check_launch(const char* what);  // cudaGetLastError -> code, records message
 
 #define MSU_REQUIRE(cond, ...)          \

@@ -19,7 +19,6 @@
 // B is always a K-major [N, K] bf16 weight shadow.  K tails are zero-filled by TMA (out-of-bounds).
 // Every output map / fused epilogue of MsuEpilogue is honoured (each epilogue thread owns one output row).
 #include <stdio.h>
-#include <atomic>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -233,10 +232,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        if (p.kb2 > 0) prefetch_tmap(&tmA2);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         for (int a = 0; a < 2 * TC_EPI_WARPS; a++) mbar_init(&auxbar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (EPI_TMA && warp == 2 && lane == 0) {
+        if (p.E.C != nullptr) prefetch_tmap(&tmC);
+        if (p.E.Cpre != nullptr || p.E.R != nullptr || p.E.H != nullptr) prefetch_tmap(&tmAux);
     }
     if (warp == 1) {
         if (PAIR) {
@@ -1275,6 +1281,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     const float red_scale = (p.red && p.sscale != nullptr) ? p.sscale[split / p.sps] : 1.f;
 
     if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmP);
+        prefetch_tmap(&tmQ);
+        prefetch_tmap(&tmW);
         // a stage is free when its MMAs have retired (+ when the four column-sum warps have read it)
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
         mbar_init(tfull, 1);
@@ -1506,6 +1515,8 @@ wgrad_conv_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int slabs_per_row = p.W / p.WB;
 
     if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmZ);
+        prefetch_tmap(&tmX);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1810,17 +1821,6 @@ static bool make_map_2d_box64(CUtensorMap* tm, const void* ptr, int64_t rows, in
     return make_map_2d(tm, ptr, rows, cols, ld, 64);
 }
 
-static std::atomic<int> g_deterministic{-1};
-static int deterministic_mode() {
-    int v = g_deterministic.load(std::memory_order_relaxed);
-    if (v < 0) {
-        const char* e = getenv("MSU_DETERMINISTIC");
-        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-        g_deterministic.store(v, std::memory_order_relaxed);
-    }
-    return v;
-}
-
 // returns 0 = launched, 1 = unsupported (SIMT fallback), other = error.  A(i, t) and B(j, t) both orient=1.
 int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int64_t I, int64_t J, int64_t T,
              float* ws, int64_t ws_elems, cudaStream_t st, int* fused_colsum) {
@@ -1948,8 +1948,3 @@ int wgrad_tc(const MsuOperand* A, const MsuOperand* B, const MsuEpilogue* E, int
 
 }  // namespace msu
 
-extern "C" int msu_set_deterministic(int on) {
-    const int prev = msu::deterministic_mode();
-    msu::g_deterministic.store(on ? 1 : 0, std::memory_order_relaxed);
-    return prev;
-}

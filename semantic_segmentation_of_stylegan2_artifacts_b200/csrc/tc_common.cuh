@@ -59,6 +59,11 @@ __device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap*
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// Fetch a kernel-parameter tensor map into the descriptor cache ahead of its first use (the first TMA instruction of a CTA otherwise
+// waits for the 128 B descriptor behind barrier init / TMEM allocation)
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
 // One lane of a converged warp (elect.sync).  Unlike `lane == 0`, ptxas knows the guarded region runs in exactly one thread, so the
 // instructions that take uniform-register operands (UTCHMMA descriptors, UTMALDG coordinates) are emitted directly instead of
 // inside a per-active-lane ELECT / R2UR.BROADCAST / BRA.U.ANY loop (8 dependent instructions per MMA on the issuing thread).

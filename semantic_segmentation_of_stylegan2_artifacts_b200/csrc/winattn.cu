@@ -308,7 +308,7 @@ namespace msu {
 int winattn_fwd_tc(const void* qkv, const float* bias, void* O, int64_t n_windows, int nH, const WinGeo& g, const AttnDrop& ad,
                    float* lse, cudaStream_t st);
 int winattn_bwd_tc_grid(int64_t n_windows, int nH);
-int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
+int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, float* dtable, int64_t n_windows,
                    int nH, const WinGeo& g, const AttnDrop& ad, const float* lse, cudaStream_t st);
 static int g_attn_backend = 0;  // 0 auto (tcgen05 for bf16), 1 force the SIMT kernels
 }
@@ -352,10 +352,18 @@ extern "C" int msu_winattn_bwd_grid(int dtype, int64_t n_windows, int32_t nH) {
 }
 
 // O (the forward output) supplies delta_i = dO_i . O_i without a second P.V product.
+extern "C" int msu_winattn_bwd_direct(int dtype) {
+    return (dtype == MSU_BF16 && g_attn_backend == 0 && !deterministic_mode()) ? 1 : 0;
+}
+
 extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, const void* O, const void* dO, void* dqkv,
-                               float* dbias_partial, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
+                               float* dbias_partial, float* dtable, int64_t n_windows, int32_t nH, const int32_t* geo, float p_drop,
                                const uint32_t* seed, const float* lse, void* stream) {
-    MSU_REQUIRE(qkv && bias && O && dO && dqkv && dbias_partial && geo, "msu_winattn_bwd: null pointer");
+    MSU_REQUIRE(qkv && bias && O && dO && dqkv && geo, "msu_winattn_bwd: null pointer");
+    const bool direct = dtable != nullptr;
+    MSU_REQUIRE(!direct || msu_winattn_bwd_direct(dtype), "msu_winattn_bwd: dtable given, but this dtype / backend / deterministic mode "
+                "writes partials (ask msu_winattn_bwd_direct first)");
+    MSU_REQUIRE(direct || dbias_partial, "msu_winattn_bwd: neither dbias_partial nor dtable");
     MSU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "msu_winattn_bwd: bad dropout probability %f", (double)p_drop);
     WinGeo g = make_wingeo(geo);
     const AttnDrop ad = make_attn_drop(p_drop, seed);
@@ -363,7 +371,7 @@ extern "C" int msu_winattn_bwd(int dtype, const void* qkv, const float* bias, co
     dim3 grid(gx, nH);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MSU_BF16 && g_attn_backend == 0) {
-        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, n_windows, nH, g, ad, lse, st);
+        const int rc = winattn_bwd_tc(qkv, bias, dO, dqkv, dbias_partial, dtable, n_windows, nH, g, ad, lse, st);
         if (rc != 1) return rc;
         MSU_REQUIRE(false, "msu_winattn_bwd: tcgen05 path unavailable for these pointers (workspace was sized for it)");
     }

@@ -130,6 +130,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     const int h = blockIdx.y;
 
     if (tid == 0) {
+        prefetch_tmap(&tm);
+        prefetch_tmap(&tm4);
+        prefetch_tmap(&tmO);
         mbar_init(&bar_load[0], 1);
         mbar_init(&bar_load[1], 1);
         mbar_init(bar_mma, 1);
@@ -399,7 +402,8 @@ constexpr int AB_X = 16 * 1024;            // one [128 x 64] bf16 P / dS tile
 constexpr int AB_OPS = 4 * AB_TILE;        // one stage of Q, K, V, dO
 constexpr int AB_XCH = 3 * 2 * 128 * 4;    // row-pair exchange slots: [max | sum | dot][part][row]
 constexpr int AB_STAGES = 3;               // operand stages
-constexpr int AB_SMEM = 2 * 2 * AB_X + AB_STAGES * AB_OPS + AT_BIAS_BYTES + AB_XCH + 256 + 1024;
+constexpr int AB_NTAB = (2 * WS - 1) * (2 * WS - 1);   // 169 entries of one head's relative-position-bias table
+constexpr int AB_SMEM = 2 * 2 * AB_X + AB_STAGES * AB_OPS + AT_BIAS_BYTES + AB_XCH + 256 + 1024 + 1024;
 constexpr int AB_THREADS = 13 * 32;
 constexpr int AB_KSPLIT = 24;              // part 0 owns keys [0, 24), part 1 keys [24, 49)
 
@@ -570,6 +574,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmQKV4, const __grid_constant__ CUtensorMap tmDO3,
                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ dbias_partial,
+                      float* __restrict__ dtable,
                       int64_t n_windows, int nH, WinGeo g, AttnDrop ad, const float* __restrict__ lse, long long* trace) {
 #ifdef MSU_ATT_TRACE_BUILD   // phase timeline (debug builds only), first 8 units of CTAs with blockIdx.y == 0: [cta][unit][16 events]
 #define AB_TRACE(ev) do { if (trace != nullptr && lane == 0 && blockIdx.y == 0 && n < 8) trace[((size_t)blockIdx.x * 8 + n) * 16 + (ev)] = clock64(); } while (0)
@@ -590,10 +595,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     uint64_t* buf_free = out_ready + 2;                 // [2] the epilogue group has drained the TMEM buffer (4 warps)
     uint64_t* tile_free = buf_free + 2;                 // [2] the staging box has left the tile buffer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 2);
+    float* sTab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [169] this CTA's bias-table gradient (dtable mode)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = nH * HD;
     const int h = blockIdx.y;
+    if (tid >= 128 && tid < 128 + AB_NTAB) sTab[tid - 128] = 0.f;
     if (tid == 0) {
+        prefetch_tmap(&tmQKV);
+        prefetch_tmap(&tmDO);
+        prefetch_tmap(&tmQKV4);
+        prefetch_tmap(&tmDO3);
+        prefetch_tmap(&tmOut);
         for (int k = 0; k < AB_STAGES; k++) mbar_init(&full[k], 1);
         for (int k = 0; k < 2; k++) {
             mbar_init(&s_ready[k], 1);
@@ -658,7 +670,25 @@ winattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             if (warp == 0) AB_TRACE(2);
         }
         // d(bias) partial of this CTA: slab (2*blockIdx.x + half), head h, row i, this part's keys
-        if (i < WT) {
+        if (dtable != nullptr) {
+            // straight into the bias-table gradient [169, nH] (zeroed or accumulating, the caller's choice): the entry of (query i, key j)
+            // is (yi - yj + 6) * 13 + (xi - xj + 6).  The CTA folds its 2 x 49 x 49 values into 169 in shared memory first, then adds
+            // those with red.global.add: no partial slabs, no reduce kernels (two launches and 24 us per block before).  Adding the
+            // 4802 values straight to global memory serialised on the 169 addresses (stage 2: 47 -> 106 us).
+            if (i < WT) {
+                const int nk = part ? WT - AB_KSPLIT : AB_KSPLIT;
+                const int base_t = (i / WS + WS - 1) * (2 * WS - 1) + (i % WS) + WS - 1;
+#pragma unroll
+                for (int j = 0; j < 25; j++) {
+                    if (j < nk) {
+                        const int jj = j + (part ? AB_KSPLIT : 0);
+                        atomicAdd(&sTab[base_t - ((jj / WS) * (2 * WS - 1) + (jj % WS))], acc[j]);
+                    }
+                }
+            }
+            asm volatile("bar.sync 6, 256;" ::: "memory");           // the eight softmax warps
+            if (tid < AB_NTAB) atomicAdd(&dtable[tid * nH + h], sTab[tid]);
+        } else if (i < WT) {
             float* out = dbias_partial + (((int64_t)blockIdx.x * 2 + half) * nH + h) * (WT * WT) + i * WT + (part ? AB_KSPLIT : 0);
             const int nk = part ? WT - AB_KSPLIT : AB_KSPLIT;
 #pragma unroll
@@ -818,7 +848,7 @@ int winattn_bwd_tc_grid(int64_t n_windows, int nH) {
 }
 
 // returns 0 launched (dbias_partial holds 2*winattn_bwd_tc_grid slabs), 1 unsupported
-int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, int64_t n_windows,
+int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqkv, float* dbias_partial, float* dtable, int64_t n_windows,
                    int nH, const WinGeo& g, const AttnDrop& ad, const float* lse, cudaStream_t st) {
     if (tc_get_encode() == nullptr) return 1;
     const int C = nH * HD;
@@ -846,7 +876,7 @@ int winattn_bwd_tc(const void* qkv, const float* bias, const void* dO, void* dqk
 #endif
     {
         const cudaError_t e = launch_pdl<2>(winattn_bwd_tc_kernel, grid, dim3(AB_THREADS), (size_t)AB_SMEM, st, 1, tmQKV, tmDO, tmQKV4, tmDO3, tmOut,
-                                         bias, dbias_partial, n_windows, nH, g, ad, lse, trace_buf);
+                                         bias, dbias_partial, dtable, n_windows, nH, g, ad, lse, trace_buf);
         if (e != cudaSuccess) { set_error("winattn_bwd_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
 #ifdef MSU_ATT_TRACE_BUILD

@@ -335,16 +335,23 @@ def winattn_bwd(qkv, bias, o, do, n_windows: int, nH: int, geo, p_drop: float = 
     `lse`: the forward's log-sum-exp (`winattn_fwd(want_lse=True)`), or None (the kernel recomputes the row statistics)."""
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
-    gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
-    part = torch.empty(gx * nH * 2401, dtype=torch.float32, device=dev)
+    # direct: the kernel adds the bias-table gradient into dtable itself (atomics); else per-CTA partial slabs + a fixed-order reduce
+    direct = L.lib().msu_winattn_bwd_direct(L.dt(qkv)) == 1
+    dtable = grad_out(table, (169, nH)) if table is not None else torch.empty(169, nH, dtype=torch.float32, device=dev)
+    part = None
+    if direct:
+        dtable.zero_()
+    else:
+        gx = L.lib().msu_winattn_bwd_grid(L.dt(qkv), n_windows, nH)
+        part = torch.empty(gx * nH * 2401, dtype=torch.float32, device=dev)
     g = L.geo6(geo)
     e0 = _p0()
     L.check(L.lib().msu_winattn_bwd(L.dt(qkv), qkv.data_ptr(), bias.data_ptr(), o.data_ptr(), do.data_ptr(),
-                                    dqkv.data_ptr(), part.data_ptr(), n_windows, nH, C.cast(g, C.c_void_p), float(p_drop),
-                                    L.ptr(seed), L.ptr(lse), L.stream_ptr()), "msu_winattn_bwd")
-    dtable = grad_out(table, (169, nH)) if table is not None else torch.empty(169, nH, dtype=torch.float32, device=dev)
-    _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
-                              "msu_relbias_reduce"), part)
+                                    dqkv.data_ptr(), L.ptr(part), dtable.data_ptr() if direct else None, n_windows, nH,
+                                    C.cast(g, C.c_void_p), float(p_drop), L.ptr(seed), L.ptr(lse), L.stream_ptr()), "msu_winattn_bwd")
+    if not direct:
+        _off_path(lambda: L.check(L.lib().msu_relbias_reduce(part.data_ptr(), gx, nH, dtable.data_ptr(), 0, L.stream_ptr()),
+                                  "msu_relbias_reduce"), part)
     _p1(e0, (n_windows, nH, 0, "winattn_bwd"), (2 * qkv.numel() + 2 * o.numel()) * qkv.element_size(),
         5 * 2 * n_windows * nH * 49 * 49 * 32)
     return dqkv, dtable

@@ -384,8 +384,22 @@ def test_window_attention_bwd_tcgen05(ops, geom):
         dqkv, dtable = ops.winattn_bwd(qkv, bias, o, do, nwin, nH, geo)
         res[name] = (dqkv.float().cpu(), dtable.cpu())
     lib.msu_set_attn_backend(0)
+    # default: every CTA adds its share of the bias-table gradient into the table with atomics (order not fixed);
+    # msu_set_deterministic(1): per-CTA partial slabs + fixed-order reduce kernels, bit-reproducible
     dq2, dt2 = ops.winattn_bwd(qkv, bias, ops.winattn_fwd(qkv, bias, nwin, nH, geo), do, nwin, nH, geo)
-    assert torch.equal(dt2.cpu(), res["tc"][1]) and torch.equal(dq2.float().cpu(), res["tc"][0])   # deterministic
+    assert torch.equal(dq2.float().cpu(), res["tc"][0])
+    assert float((dt2.cpu() - res["tc"][1]).abs().max()) <= 1e-5 * float(res["tc"][1].abs().max())
+    assert lib.msu_winattn_bwd_direct(_lib.dt(qkv)) == 1
+    prev = lib.msu_set_deterministic(1)
+    try:
+        assert lib.msu_winattn_bwd_direct(_lib.dt(qkv)) == 0
+        o_d = ops.winattn_fwd(qkv, bias, nwin, nH, geo)
+        dq3, dt3 = ops.winattn_bwd(qkv, bias, o_d, do, nwin, nH, geo)
+        dq4, dt4 = ops.winattn_bwd(qkv, bias, o_d, do, nwin, nH, geo)
+    finally:
+        lib.msu_set_deterministic(prev)
+    assert torch.equal(dt3, dt4) and torch.equal(dq3, dq4)
+    assert float((dt3.cpu() - res["tc"][1]).abs().max()) <= 1e-5 * float(res["tc"][1].abs().max())
     # fp64 autograd reference
     _, _, sh, sw, _, region = O.window_geometry(H, W, shift)
     x = qkv.double().cpu().requires_grad_(True)
