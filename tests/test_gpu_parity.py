@@ -373,6 +373,38 @@ def test_model_embed128_vs_oracle(pkg, prec):
         assert abs(gn - rn) < (1e-3 if f32 else 6e-2) * rn + 1e-7, (k, gn, rn)
 
 
+@pytest.mark.gpu
+def test_deterministic_mode_reproduces_gradients_bit_for_bit(pkg):
+    """Default mode: weight gradients and the attention bias-table gradient are summed with TMA reduce-adds / atomics (order of the
+    fp32 additions not fixed).  msu_set_deterministic(1) switches to partial slabs + fixed-order reduce kernels: two passes over
+    the same input then give identical bits, and they agree with the default mode to fp32 summation noise."""
+    from semantic_segmentation_of_stylegan2_artifacts_b200 import _lib
+    from semantic_segmentation_of_stylegan2_artifacts_b200.loss.DynamicLoss import DynamicLoss
+    cfg = O.Cfg(img_size=128, embed_dim=96, depths=(2, 2, 2, 2), num_heads=(3, 6, 12, 24))
+    x, y = O.make_inputs(cfg, 2)
+    m = build_model(cfg, "bf16")
+    crit = DynamicLoss(alpha=0.2, beta=0.8, tversky_bce_mix=0.45)
+
+    def grads():
+        for p_ in m.parameters():
+            p_.grad = None
+        crit(m(x.to(DEV)), y.to(DEV)).backward()
+        torch.cuda.synchronize()
+        return {k: p_.grad.clone() for k, p_ in m.named_parameters() if p_.grad is not None}
+
+    lib = _lib.lib()
+    g_def = grads()
+    prev = lib.msu_set_deterministic(1)
+    try:
+        g1, g2 = grads(), grads()
+    finally:
+        lib.msu_set_deterministic(prev)
+    assert g1.keys() == g2.keys() == g_def.keys()
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+        assert relmax(g_def[k], g1[k]) < 2e-4, (k, relmax(g_def[k], g1[k]))
+
+
 class _Rows:
     def __init__(self):
         self.rows = []
