@@ -263,21 +263,26 @@ class SwinBlockFn(Function):
         qkv = torch.empty(Tw, 3 * Cd, dtype=dt, device=dev)
         gemm(operand(xw), w_fwd(qkvw, dt), epilogue(qkv, bias=qkvb), Tw, 3 * Cd, Cd, dev)
         bias = ops.relbias_expand(table, nH)
-        o, lse = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed, want_lse=True)
+        need_grad = any(ctx.needs_input_grad)     # inference: nothing is kept for a backward (no lse, no GELU' tensor)
+        if need_grad:
+            o, lse = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed, want_lse=True)
+        else:
+            o, lse = ops.winattn_fwd(qkv, bias, B * nW, nH, geo, attn_p, drop_seed), None
         # proj + window reverse + un-roll + crop + stochastic depth + residual in the GEMM epilogue
         x1 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(o), w_fwd(projw, dt),
              epilogue(x1, bias=projb, R=x, map=MAP_WINDOW, geo=geo, rowscale=sd1, rps=HW), Tw, Cd, Cd, dev)
         xn, mean2, rstd2 = ops.ln_fwd(x1, n2w, n2b, T, Cd)
-        h = torch.empty(T, hid, dtype=dt, device=dev)
+        h = torch.empty(T, hid, dtype=dt, device=dev) if need_grad else None
         a = torch.empty(T, hid, dtype=dt, device=dev)
         # `h` holds GELU'(pre-activation), not the pre-activation (act = 2): the backward's dh epilogue is then a plain multiply
         # (act = 3) instead of re-deriving GELU' (15 of its 31 instructions per element; MSUNET_B200_STORE_GELU_GRAD=0: keep h)
-        gemm(operand(xn), w_fwd(f1w, dt), epilogue(a, Cpre=h, bias=f1b, act=2 if _STORE_GELU_GRAD else 1), T, hid, Cd, dev)
+        gemm(operand(xn), w_fwd(f1w, dt), epilogue(a, Cpre=h, bias=f1b, act=2 if (_STORE_GELU_GRAD and need_grad) else 1), T, hid, Cd, dev)
         x2 = torch.empty(T, Cd, dtype=dt, device=dev)
         gemm(operand(a), w_fwd(f2w, dt), epilogue(x2, bias=f2b, R=x1, rowscale=sd2, rps=HW), T, Cd, hid, dev)
-        ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
-                              xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b, lse)
+        if need_grad:
+            ctx.save_for_backward(x, n1w, n1b, qkvw, projw, n2w, n2b, f1w, f2w, sd1, sd2,
+                                  xw, mean1, rstd1, qkv, bias, o, x1, xn, mean2, rstd2, h, a, qkvb, projb, table, f1b, f2b, lse)
         ctx.cfg = (B, H, W, nH, geo, nW)
         ctx.drop = (attn_p, drop_seed)
         return x2.view(B, H, W, Cd)
@@ -536,16 +541,17 @@ class HeadFn(Function):
         x2d = x.view(T, E)
         sgeo = [r, r, 4, E]
         cgeo = [S, S, E]
-        h0 = torch.empty(Mp, E, dtype=dt, device=dev)
+        need_grad = any(ctx.needs_input_grad)     # inference: the GELU' / pre-activation tensors of the expand and the first conv are not written
+        h0 = torch.empty(Mp, E, dtype=dt, device=dev) if need_grad else None
         a0 = torch.empty(Mp, E, dtype=dt, device=dev)
         # h0 / z1 hold GELU'(pre-activation) (act = 2), not the pre-activation: the two dgrad convolutions multiply by them (act = 3)
         # instead of deriving GELU' per element in their epilogues (3x3 conv dgrad 792 -> 705 us, forward 720 -> 739 us at 512^2 x 16)
-        act_f = 2 if _STORE_GELU_GRAD else 1
+        act_f = 2 if (_STORE_GELU_GRAD and need_grad) else 1
         gemm(operand(x2d), w_fwd(ew, dt), epilogue(a0, ldc=E, Cpre=h0, act=act_f, map=MAP_SHUFFLE, geo=sgeo), T, 16 * E, E, dev)
         wd = dt if dt == BF16 else torch.float32
         w1 = shadow(c1w, 2, E, E, (E, 9 * E), wd)
         w2 = shadow(c2w, 2, E, E, (E, 9 * E), wd)
-        z1 = torch.empty(Mp, E, dtype=dt, device=dev)
+        z1 = torch.empty(Mp, E, dtype=dt, device=dev) if need_grad else None
         a1 = torch.empty(Mp, E, dtype=dt, device=dev)
         gemm(operand(a0, ld=E, map=MAP_CONV3, geo=cgeo), operand(w1), epilogue(a1, Cpre=z1, bias=c1b, act=act_f),
              Mp, E, 9 * E, dev)
@@ -553,7 +559,6 @@ class HeadFn(Function):
         if _FUSED_HEAD_LN and dt == BF16 and E % 32 == 0 and E <= 256 and S % 128 == 0:
             # LayerNorm + 1x1 conv ride in the second conv's epilogue (per-row statistics in the epilogue registers): the
             # [Mp, E] tensor is not read again, and not even written when no gradient is wanted (inference)
-            need_grad = any(ctx.needs_input_grad)
             z2 = torch.empty(Mp, E, dtype=dt, device=dev) if need_grad else None
             logits = torch.empty(Mp, dtype=dt, device=dev)
             mean = torch.empty(Mp, dtype=torch.float32, device=dev)
@@ -566,7 +571,8 @@ class HeadFn(Function):
             z2 = torch.empty(Mp, E, dtype=dt, device=dev)
             gemm(operand(a1, ld=E, map=MAP_CONV3, geo=cgeo), operand(w2), epilogue(z2, bias=c2b), Mp, E, 9 * E, dev)
             logits, mean, rstd = ops.ln_fwd(z2, nw, nb, Mp, E, dotw=owv)
-        ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd, c1b, c2b)
+        if need_grad:
+            ctx.save_for_backward(x2d, ew, c1w, c2w, nw, nb, owv, h0, a0, z1, a1, z2, mean, rstd, c1b, c2b)
         ctx.cfg = (B, r, x.shape, ow.shape)
         return logits.view(B, 1, S, S)
 
